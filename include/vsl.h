@@ -1,0 +1,178 @@
+/*
+ * vsl.h — C ABI of the B200-native view-synthesis loss library (libvsl_b200.so).
+ *
+ * Drop-in boundary for the view-synthesis loss path of
+ * meghakalia/unsupervised_pose_estimation (a monodepth2 fork).  The reference has no
+ * FFI layer: its boundary is the Python call surface of layers.py / trainer.py.  Each
+ * entry point below names the reference interface it replaces (file:line in the
+ * reference tree); the Python host side (unsupervised_pose_estimation_b200/layers.py,
+ * trainer.py) binds these symbols with ctypes and mirrors the reference's classes.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, PODs; no torch types.  `stream` is a cudaStream_t passed
+ *    as void* (the caller passes torch.cuda.current_stream().cuda_stream).
+ *  - the CALLER allocates and owns every buffer (device memory unless stated); the
+ *    library never allocates, frees or keeps a pointer after the call returns.
+ *  - all work is enqueued on `stream`; no call synchronises the device.
+ *  - return value: VSL_OK (0) or a negative VslStatus; nothing throws across the ABI.
+ *  - tensors are dense row-major ("contiguous") with the shapes given; images are NCHW.
+ *  - arithmetic is fp32; images may be stored as fp32 or bf16 (VslDesc.image_dtype).
+ *  - there is no CPU implementation behind this ABI: without a CUDA device every compute
+ *    entry point returns VSL_ERR_CUDA.
+ */
+#ifndef VSL_H_
+#define VSL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSL_ABI_VERSION 1
+#define VSL_MAX_SCALES 4
+#define VSL_MAX_SRC 4
+
+typedef enum VslStatus {
+  VSL_OK = 0,
+  VSL_ERR_BAD_DESC = -1,      /* null / wrong abi_version / sizes out of range            */
+  VSL_ERR_NULL_POINTER = -2,  /* a required buffer pointer is null                        */
+  VSL_ERR_MISALIGNED = -3,    /* a buffer is not aligned to its element size              */
+  VSL_ERR_UNSUPPORTED = -4,   /* flag / dtype combination not implemented by this build   */
+  VSL_ERR_WORKSPACE = -5,     /* workspace smaller than vsl_loss_workspace_bytes()        */
+  VSL_ERR_CUDA = -6           /* a CUDA runtime call failed (see vsl_last_cuda_error)     */
+} VslStatus;
+
+/* option bits, named after the reference flags (options.py:145-159) */
+enum {
+  VSL_FLAG_AUTOMASK = 1 << 0,         /* NOT --disable_automasking (trainer.py:620-633, 654-661) */
+  VSL_FLAG_AVG_REPROJECTION = 1 << 1, /* --avg_reprojection (trainer.py:629-630, 649-650)        */
+  VSL_FLAG_NO_SSIM = 1 << 2,          /* --no_ssim (trainer.py:549-550)                          */
+  VSL_FLAG_V1_MULTISCALE = 1 << 3     /* --v1_multiscale (trainer.py:497-498, 604-605)           */
+};
+
+enum { VSL_DTYPE_F32 = 0, VSL_DTYPE_BF16 = 1 };
+
+/* arithmetic-order selectors (VslDesc.arith).  0 reproduces eager PyTorch-CUDA bit for bit
+ * (the order of the reference on a GPU).  VSL_ARITH_TRUE_DIV reproduces PyTorch-CPU's
+ * `x /= (W-1)` (a true division; CUDA multiplies by the rounded reciprocal).             */
+enum {
+  VSL_ARITH_TRUE_DIV = 1 << 0,
+  VSL_ARITH_DOT_NOFMA = 1 << 1,    /* probe: un-fused dot products in bmm                   */
+  VSL_ARITH_DOT_REVERSE = 1 << 2,  /* probe: k-descending accumulation in bmm               */
+  VSL_ARITH_UPS_RIGHT = 1 << 3,    /* probe: up-sample fuses the right-hand product         */
+  VSL_ARITH_UPS_NOFMA = 1 << 4,    /* probe: up-sample without FMA contraction              */
+  VSL_ARITH_TAP_NOFMA = 1 << 5,    /* probe: bilinear tap accumulation without FMA          */
+  VSL_ARITH_MEAN_DIV = 1 << 6      /* probe: channel mean as sum/3 instead of sum*(1/3)     */
+};
+
+/* Problem descriptor: what Trainer.__init__ fixes once (trainer.py:245-259, options.py). */
+typedef struct VslDesc {
+  int32_t abi_version;            /* VSL_ABI_VERSION                                        */
+  int32_t batch;                  /* opt.batch_size (local batch of this rank)              */
+  int32_t height, width;          /* opt.height, opt.width (scale 0)                        */
+  int32_t num_scales;             /* len(opt.scales), 1..VSL_MAX_SCALES                     */
+  int32_t scale_ids[VSL_MAX_SCALES]; /* opt.scales: level s has size (H >> s, W >> s)       */
+  int32_t num_src;                /* len(opt.frame_ids) - 1, 1..VSL_MAX_SRC                 */
+  int32_t flags;                  /* VSL_FLAG_*                                             */
+  int32_t image_dtype;            /* VSL_DTYPE_* of colour images                           */
+  int32_t arith;                  /* VSL_ARITH_*; 0 = PyTorch-CUDA order                    */
+  float min_disp;                 /* float32(1/opt.max_depth)           (layers.py:90)      */
+  float disp_range;               /* float32(1/min_depth - 1/max_depth) (layers.py:92)      */
+  float eps;                      /* Project3D eps, 1e-7                (layers.py:245)     */
+  float smooth_weight;            /* opt.disparity_smoothness           (trainer.py:680)    */
+} VslDesc;
+
+/* ------------------------------------------------------------------------------------ */
+int vsl_abi_version(void);
+const char* vsl_status_string(int status);
+/* cudaError_t of the last failing CUDA call made by this thread's previous vsl_* call. */
+int vsl_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * Fused loss, forward + backward in one pass.
+ * Replaces Trainer.generate_images_pred + Trainer.compute_losses + the autograd backward
+ * of that graph (trainer.py:491-541, 557-686, 312) for the default flags (automasking,
+ * per-pixel minimum, SSIM, multi-scale at full resolution), any mix of temporal and
+ * stereo source frames.
+ * ------------------------------------------------------------------------------------ */
+typedef struct VslLossBuffers {
+  /* inputs */
+  const void* target[VSL_MAX_SCALES];   /* inputs[("color",0,s)]  [B,3,H>>s,W>>s]; [0] is the photometric target */
+  const void* source[VSL_MAX_SRC];      /* inputs[("color",f,0)]  [B,3,H,W] per source frame          */
+  const float* disp[VSL_MAX_SCALES];    /* outputs[("disp",s)]    [B,1,H>>s,W>>s]                     */
+  const float* inv_K;                   /* inputs[("inv_K",0)]    [B,4,4]                             */
+  const float* P[VSL_MAX_SRC];          /* (K @ T_f)[:, :3, :]    [B,3,4]  (layers.py:254)            */
+  const float* noise[VSL_MAX_SCALES];   /* torch.randn draw of trainer.py:656 per scale [B,F,H,W]     */
+  /* outputs */
+  float* losses;                        /* [3*S+1]: min_loss/s (S), loss/s (S), loss, smooth/s (S)    */
+  float* mask[VSL_MAX_SCALES];          /* outputs["identity_selection/s"] [B,H,W]; may be null       */
+  float* grad_disp_photo[VSL_MAX_SCALES];  /* d(min_loss/s)/d disp_s   [B,1,H>>s,W>>s]                */
+  float* grad_disp_smooth[VSL_MAX_SCALES]; /* d(smooth_s)/d disp_s     [B,1,H>>s,W>>s]                */
+  float* grad_P;                        /* d(min_loss/s)/d P_f  [S][F][B][12]                         */
+} VslLossBuffers;
+
+size_t vsl_loss_workspace_bytes(const VslDesc* desc);
+int vsl_loss_forward_backward(const VslDesc* desc, const VslLossBuffers* buf,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Chain rule from the loss dict to the leaves: `upstream` holds dL/d(losses[k]) on the DEVICE in
+ * the order min_loss/0..S-1, loss/0..S-1, loss (2S+1 floats; trainer.py:672-685 defines how the
+ * entries depend on each other).  Writes grad_disp[s] [B,1,H>>s,W>>s] and grad_P_out [F][B][12]. */
+int vsl_loss_combine_grads(const VslDesc* desc, const float* upstream,
+                           const VslLossBuffers* buf, float* const grad_disp[VSL_MAX_SCALES],
+                           float* grad_P_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Side outputs of Trainer.generate_images_pred (trainer.py:491-541) for one scale:
+ * outputs[("depth",0,s)] [B,1,H,W], outputs[("sample",f,s)] [B,H,W,2], outputs[("color",f,s)]
+ * [B,3,H,W].  Any output pointer may be null.  Only read by logging in the reference
+ * (wandb_logging.py:134-143), so the fused loss never materialises them.
+ * ------------------------------------------------------------------------------------ */
+int vsl_warp_forward(const VslDesc* desc, int scale_index, const float* disp, const float* inv_K,
+                     const float* const P[VSL_MAX_SRC], const void* const source[VSL_MAX_SRC],
+                     float* depth, float* const sample[VSL_MAX_SRC], float* const color[VSL_MAX_SRC],
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Stand-alone layers (the layers.py call surface).  fp32 only.
+ * ------------------------------------------------------------------------------------ */
+/* BackprojectDepth.forward (layers.py:234-239): depth [B,1,h,w], inv_K [B,4,4] -> cam [B,4,hw] */
+int vsl_backproject_forward(int batch, int height, int width, int arith, const float* depth,
+                            const float* inv_K, float* cam_points, void* stream);
+/* its backward: grad_cam [B,4,hw] -> grad_depth [B,1,h,w] */
+int vsl_backproject_backward(int batch, int height, int width, const float* grad_cam,
+                             const float* inv_K, float* grad_depth, void* stream);
+/* Project3D.forward (layers.py:253-264) with P = (K@T)[:, :3, :] [B,3,4]: points [B,4,hw] -> pix [B,h,w,2] */
+int vsl_project_forward(int batch, int height, int width, float eps, int arith, const float* points,
+                        const float* P, float* pix, void* stream);
+/* its backward: grad_pix [B,h,w,2] -> grad_points [B,4,hw] and grad_P [B,3,4] (ws: vsl_project_workspace_bytes) */
+size_t vsl_project_workspace_bytes(int batch, int height, int width);
+int vsl_project_backward(int batch, int height, int width, float eps, const float* points, const float* P,
+                         const float* grad_pix, float* grad_points, float* grad_P,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* SSIM.forward (layers.py:318-332): x, y [B,C,H,W] -> [B,C,H,W] */
+int vsl_ssim_forward(int batch, int channels, int height, int width, const float* x, const float* y,
+                     float* out, void* stream);
+/* its backward; grad_x / grad_y may be null */
+int vsl_ssim_backward(int batch, int channels, int height, int width, const float* x, const float* y,
+                      const float* grad_out, float* grad_x, float* grad_y, void* stream);
+/* Trainer.compute_reprojection_loss (trainer.py:543-555): pred, target [B,3,H,W] -> [B,1,H,W] */
+int vsl_reprojection_loss_forward(int batch, int height, int width, int no_ssim, int arith,
+                                  const float* pred, const float* target, float* out, void* stream);
+int vsl_reprojection_loss_backward(int batch, int height, int width, int no_ssim, const float* pred,
+                                   const float* target, const float* grad_out, float* grad_pred,
+                                   float* grad_target, void* stream);
+/* get_smooth_loss (layers.py:286-299): disp [B,1,h,w], img [B,3,h,w] -> scalar; ws: vsl_smooth_workspace_bytes */
+size_t vsl_smooth_workspace_bytes(int batch, int height, int width);
+int vsl_smooth_loss_forward(int batch, int height, int width, const float* disp, const float* img,
+                            float* loss, void* workspace, size_t workspace_bytes, void* stream);
+/* grad_loss: device scalar */
+int vsl_smooth_loss_backward(int batch, int height, int width, const float* disp, const float* img,
+                             const float* grad_loss, float* grad_disp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSL_H_ */

@@ -1,0 +1,134 @@
+"""ctypes binding of libvsl_b200.so (C ABI declared in include/vsl.h).
+
+The library is the only compute path: if it cannot be loaded the package raises, it never
+falls back to PyTorch ops or to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
+
+VSL_ABI_VERSION = 1
+VSL_MAX_SCALES = 4
+VSL_MAX_SRC = 4
+
+FLAG_AUTOMASK = 1 << 0
+FLAG_AVG_REPROJECTION = 1 << 1
+FLAG_NO_SSIM = 1 << 2
+FLAG_V1_MULTISCALE = 1 << 3
+
+DTYPE_F32 = 0
+DTYPE_BF16 = 1
+
+ARITH_TRUE_DIV = 1 << 0
+ARITH_DOT_NOFMA = 1 << 1
+ARITH_DOT_REVERSE = 1 << 2
+ARITH_UPS_RIGHT = 1 << 3
+ARITH_UPS_NOFMA = 1 << 4
+ARITH_TAP_NOFMA = 1 << 5
+ARITH_MEAN_DIV = 1 << 6
+
+# every symbol include/vsl.h declares (tests check the shared object exports all of them)
+EXPORTED_SYMBOLS = [
+    "vsl_abi_version", "vsl_status_string", "vsl_last_cuda_error",
+    "vsl_loss_workspace_bytes", "vsl_loss_forward_backward", "vsl_loss_combine_grads",
+    "vsl_warp_forward",
+    "vsl_backproject_forward", "vsl_backproject_backward",
+    "vsl_project_forward", "vsl_project_workspace_bytes", "vsl_project_backward",
+    "vsl_ssim_forward", "vsl_ssim_backward",
+    "vsl_reprojection_loss_forward", "vsl_reprojection_loss_backward",
+    "vsl_smooth_workspace_bytes", "vsl_smooth_loss_forward", "vsl_smooth_loss_backward",
+]
+
+
+class VslDesc(Structure):
+    _fields_ = [
+        ("abi_version", c_int32), ("batch", c_int32), ("height", c_int32), ("width", c_int32),
+        ("num_scales", c_int32), ("scale_ids", c_int32 * VSL_MAX_SCALES), ("num_src", c_int32),
+        ("flags", c_int32), ("image_dtype", c_int32), ("arith", c_int32),
+        ("min_disp", c_float), ("disp_range", c_float), ("eps", c_float), ("smooth_weight", c_float),
+    ]
+
+
+class VslLossBuffers(Structure):
+    _fields_ = [
+        ("target", c_void_p * VSL_MAX_SCALES), ("source", c_void_p * VSL_MAX_SRC),
+        ("disp", c_void_p * VSL_MAX_SCALES), ("inv_K", c_void_p), ("P", c_void_p * VSL_MAX_SRC),
+        ("noise", c_void_p * VSL_MAX_SCALES),
+        ("losses", c_void_p), ("mask", c_void_p * VSL_MAX_SCALES),
+        ("grad_disp_photo", c_void_p * VSL_MAX_SCALES), ("grad_disp_smooth", c_void_p * VSL_MAX_SCALES),
+        ("grad_P", c_void_p),
+    ]
+
+
+class VslError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvsl_b200.so")
+
+
+def load():
+    """Load (building first if the in-tree .so is missing or stale and nvcc is present)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    from . import build as _build
+    if _build.is_stale() and _build.find_nvcc() is not None:
+        _build.build()
+    if not os.path.exists(path):
+        raise VslError(
+            "libvsl_b200.so is missing and nvcc is not available to build it; run "
+            "`python -m unsupervised_pose_estimation_b200.build`. There is no CPU/PyTorch fallback.")
+    lib = ctypes.CDLL(path)
+    if lib.vsl_abi_version() != VSL_ABI_VERSION:
+        raise VslError("libvsl_b200.so ABI version mismatch; rebuild it")
+
+    vp = c_void_p
+    lib.vsl_status_string.restype = c_char_p
+    lib.vsl_status_string.argtypes = [c_int]
+    lib.vsl_loss_workspace_bytes.restype = c_size_t
+    lib.vsl_loss_workspace_bytes.argtypes = [POINTER(VslDesc)]
+    lib.vsl_loss_forward_backward.argtypes = [POINTER(VslDesc), POINTER(VslLossBuffers), vp, c_size_t, vp]
+    lib.vsl_loss_combine_grads.argtypes = [POINTER(VslDesc), vp, POINTER(VslLossBuffers),
+                                           POINTER(c_void_p * VSL_MAX_SCALES), vp, vp]
+    lib.vsl_warp_forward.argtypes = [POINTER(VslDesc), c_int, vp, vp, POINTER(c_void_p * VSL_MAX_SRC),
+                                     POINTER(c_void_p * VSL_MAX_SRC), vp, POINTER(c_void_p * VSL_MAX_SRC),
+                                     POINTER(c_void_p * VSL_MAX_SRC), vp]
+    lib.vsl_backproject_forward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp]
+    lib.vsl_backproject_backward.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
+    lib.vsl_project_forward.argtypes = [c_int, c_int, c_int, c_float, c_int, vp, vp, vp, vp]
+    lib.vsl_project_workspace_bytes.restype = c_size_t
+    lib.vsl_project_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.vsl_project_backward.argtypes = [c_int, c_int, c_int, c_float, vp, vp, vp, vp, vp, vp, c_size_t, vp]
+    lib.vsl_ssim_forward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp]
+    lib.vsl_ssim_backward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    lib.vsl_reprojection_loss_forward.argtypes = [c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp]
+    lib.vsl_reprojection_loss_backward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    lib.vsl_smooth_workspace_bytes.restype = c_size_t
+    lib.vsl_smooth_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.vsl_smooth_loss_forward.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]
+    lib.vsl_smooth_loss_backward.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, vp]
+    _LIB = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        lib = load()
+        msg = lib.vsl_status_string(status).decode()
+        extra = ""
+        if status == -6:
+            extra = " (cudaError %d)" % lib.vsl_last_cuda_error()
+        raise VslError("%s failed: %s%s" % (what, msg, extra))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,573 @@
+// Fused view-synthesis loss for sm_100a: kernels + C ABI (include/vsl.h).
+//
+// Launch sequence of vsl_loss_forward_backward (one stream, no host sync):
+//   k_smooth_mean   per-image mean of disp_s                     (trainer.py:676)
+//   k_smooth_terms  edge-aware smoothness terms + d/d(norm disp)  (layers.py:286-299)
+//   k_photometric   warp + SSIM/L1 + automask min + adjoint       (trainer.py:491-674)  <- the hot kernel
+//   k_epilogue      up-sample adjoint, smoothness chain rule, deterministic reductions, loss dict
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vsl.h"
+#include "vsl_tile.cuh"
+
+namespace vsl {
+
+thread_local int g_last_cuda_error = 0;  // shared with vsl_layers.cu
+
+#define VSL_CUDA_OK(expr)                         \
+  do {                                            \
+    cudaError_t e__ = (expr);                     \
+    if (e__ != cudaSuccess) {                     \
+      g_last_cuda_error = (int)e__;               \
+      return VSL_ERR_CUDA;                        \
+    }                                             \
+  } while (0)
+
+constexpr int kChunk = 1024;   // native-resolution pixels per block in the small kernels
+constexpr int kSmallNT = 256;
+
+struct SmallParams {  // smoothness + epilogue
+  const float* disp[kMaxScales];
+  const float* img[kMaxScales];   // target pyramid
+  float* gsmooth[kMaxScales];     // d smooth_s / d disp_s
+  float* gphoto[kMaxScales];      // d min_loss_s / d disp_s
+  const float* gD[kMaxScales];    // full-res adjoint input (null for identity scales)
+  float* mean_part;               // [S][B][chunks0]
+  float* smooth_part;             // [S][B][chunks0][3]  (sum_x, sum_y, sum g*d)
+  const float* partials;          // photometric partials [numCTA][S][kPartial]
+  float* lossb;                   // [S][B]
+  float* smoothb;                 // [S][B][2]
+  float* gradP;                   // [S][F][B][12]
+  float* losses;                  // [3S+1]: min_loss (S), loss/s (S), loss, smooth (S)
+  unsigned* counter;
+  int B, H, W, S, F;
+  int hs[kMaxScales], ws[kMaxScales], scale_id[kMaxScales], identity_scale[kMaxScales];
+  float scale_h[kMaxScales], scale_w[kMaxScales];
+  int chunks0, tiles_per_image, kpartial;
+  float smooth_weight;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum in a fixed order; result valid in every thread
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < NT / 32; ++i) r += scratch[i];
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSmallNT) k_smooth_mean(const SmallParams p) {
+  __shared__ float scratch[kSmallNT / 32];
+  int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
+  int n = p.hs[s] * p.ws[s];
+  if (chunk * kChunk >= n) return;
+  const float* d = p.disp[s] + (size_t)b * n;
+  float acc = 0.f;
+  for (int i = chunk * kChunk + threadIdx.x; i < min(n, (chunk + 1) * kChunk); i += kSmallNT) acc += d[i];
+  acc = block_sum<kSmallNT>(acc, scratch);
+  if (threadIdx.x == 0) p.mean_part[(s * p.B + b) * p.chunks0 + chunk] = acc;
+}
+
+__device__ __forceinline__ float image_mean(const SmallParams& p, int s, int b, float* scratch) {
+  int n = p.hs[s] * p.ws[s];
+  int nchunk = (n + kChunk - 1) / kChunk;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nchunk; i += kSmallNT) acc += p.mean_part[(s * p.B + b) * p.chunks0 + i];
+  return block_sum<kSmallNT>(acc, scratch) / (float)n;
+}
+
+// edge weight exp(-mean_c |img(a) - img(b)|)  (layers.py:293-297)
+__device__ __forceinline__ float edge_weight(const float* img, int n, int ia, int ib) {
+  float g = fabsf(img[ia] - img[ib]) + fabsf(img[n + ia] - img[n + ib]) + fabsf(img[2 * n + ia] - img[2 * n + ib]);
+  return expf(-g * (1.0f / 3.0f));
+}
+__device__ __forceinline__ float sgnf(float t) { return t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f); }
+
+__global__ void __launch_bounds__(kSmallNT) k_smooth_terms(const SmallParams p) {
+  __shared__ float scratch[kSmallNT / 32];
+  int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
+  int h = p.hs[s], w = p.ws[s], n = h * w;
+  if (chunk * kChunk >= n) return;
+  float inv = 1.0f / (image_mean(p, s, b, scratch) + 1e-7f);
+  const float* d = p.disp[s] + (size_t)b * n;
+  const float* img = p.img[s] + (size_t)b * 3 * n;
+  float* g_out = p.gsmooth[s] + (size_t)b * n;
+  float cx = 1.0f / ((float)p.B * h * (w - 1)), cy = 1.0f / ((float)p.B * (h - 1) * w);
+  float sx = 0.f, sy = 0.f, sgd = 0.f;
+  for (int i = chunk * kChunk + threadIdx.x; i < min(n, (chunk + 1) * kChunk); i += kSmallNT) {
+    int v = i / w, u = i - v * w;
+    float di = d[i], g = 0.f;
+    if (u + 1 < w) {
+      float e = edge_weight(img, n, i, i + 1), t = (di - d[i + 1]) * inv;
+      sx += fabsf(t) * e;
+      g += sgnf(t) * e * cx;
+    }
+    if (u > 0) {
+      float e = edge_weight(img, n, i - 1, i), t = (d[i - 1] - di) * inv;
+      g -= sgnf(t) * e * cx;
+    }
+    if (v + 1 < h) {
+      float e = edge_weight(img, n, i, i + w), t = (di - d[i + w]) * inv;
+      sy += fabsf(t) * e;
+      g += sgnf(t) * e * cy;
+    }
+    if (v > 0) {
+      float e = edge_weight(img, n, i - w, i), t = (d[i - w] - di) * inv;
+      g -= sgnf(t) * e * cy;
+    }
+    g_out[i] = g;  // d smooth / d(norm disp); the chain through the mean is finished in k_epilogue
+    sgd += g * di;
+  }
+  sx = block_sum<kSmallNT>(sx, scratch);
+  sy = block_sum<kSmallNT>(sy, scratch);
+  sgd = block_sum<kSmallNT>(sgd, scratch);
+  if (threadIdx.x == 0) {
+    float* o = p.smooth_part + ((size_t)(s * p.B + b) * p.chunks0 + chunk) * 3;
+    o[0] = sx; o[1] = sy; o[2] = sgd;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
+  extern __shared__ float sm[];
+  TileCtx t;
+  t.b = blockIdx.z;
+  t.x0 = blockIdx.x * C::TW;
+  t.y0 = blockIdx.y * C::TH;
+  t.cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int tid = threadIdx.x;
+  const size_t img_off = (size_t)t.b * 3 * p.H * p.W;
+
+  phase_load_region<C>(p, t, p.tgt + img_off, sm + C::oT, tid);
+  __syncthreads();
+  phase_target_stats<C>(p, t, sm, tid);
+  for (int f = 0; f < C::F; ++f) {
+    __syncthreads();
+    phase_load_region<C>(p, t, p.src[f] + img_off, sm + C::oX, tid);
+    __syncthreads();
+    phase_identity<C>(p, t, sm, f, tid);
+  }
+
+  float* red = sm + C::oRed;
+  for (int s = 0; s < p.S; ++s) {
+    ThreadState<C> ts;
+    ts.loss = 0.f;
+#pragma unroll
+    for (int k = 0; k < C::F * 12; ++k) ts.dP[k] = 0.f;
+    __syncthreads();
+    phase_warp<C>(p, t, sm, s, tid);
+    __syncthreads();
+    phase_windows<C>(p, t, sm, s, tid, ts);
+    __syncthreads();
+    phase_backward<C>(p, t, sm, s, tid, ts);
+    // deterministic block reduction of (loss, dP) -> one partial per CTA and scale
+    const int w = tid >> 5, l = tid & 31;
+    float v = warp_sum(ts.loss);
+    if (l == 0) red[w * C::kPartial] = v;
+#pragma unroll
+    for (int k = 0; k < C::F * 12; ++k) {
+      v = warp_sum(ts.dP[k]);
+      if (l == 0) red[w * C::kPartial + 1 + k] = v;
+    }
+    __syncthreads();
+    if (tid < C::kPartial) {
+      float r = 0.f;
+#pragma unroll
+      for (int i = 0; i < C::NT / 32; ++i) r += red[i * C::kPartial + tid];
+      p.partials[((size_t)t.cta * p.S + s) * C::kPartial + tid] = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
+  __shared__ float scratch[kSmallNT / 32];
+  __shared__ bool is_last;
+  int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
+  int h = p.hs[s], w = p.ws[s], n = h * w;
+  int nchunk = (n + kChunk - 1) / kChunk;
+  if (chunk < nchunk) {
+    float inv = 1.0f / (image_mean(p, s, b, scratch) + 1e-7f);
+    float gd = 0.f;
+    for (int i = threadIdx.x; i < nchunk; i += kSmallNT)
+      gd += p.smooth_part[((size_t)(s * p.B + b) * p.chunks0 + i) * 3 + 2];
+    gd = block_sum<kSmallNT>(gd, scratch);
+    float corr = gd * inv * inv / (float)n;
+    float* gs = p.gsmooth[s] + (size_t)b * n;
+    float* gp = p.gphoto[s] + (size_t)b * n;
+    const float* gD = p.identity_scale[s] ? nullptr : p.gD[s] + (size_t)b * p.H * p.W;
+    for (int i = chunk * kChunk + threadIdx.x; i < min(n, (chunk + 1) * kChunk); i += kSmallNT) {
+      gs[i] = gs[i] * inv - corr;
+      if (gD) gp[i] = upsample_adjoint_pixel(gD, p.H, p.W, h, w, p.scale_h[s], p.scale_w[s], i / w, i % w);
+    }
+    if (chunk == 0) {
+      // photometric partials of image b, scale s: loss sum and dP, tiles in a fixed order
+      const float* base = p.partials + ((size_t)b * p.tiles_per_image * p.S + s) * p.kpartial;
+      for (int k = threadIdx.x; k < p.kpartial; k += kSmallNT) {
+        double acc = 0.0;
+        for (int tl = 0; tl < p.tiles_per_image; ++tl) acc += (double)base[(size_t)tl * p.S * p.kpartial + k];
+        if (k == 0) p.lossb[s * p.B + b] = (float)acc;
+        else {
+          int f = (k - 1) / 12, e = (k - 1) % 12;
+          p.gradP[((size_t)(s * p.F + f) * p.B + b) * 12 + e] = (float)acc;
+        }
+      }
+      float sx = 0.f, sy = 0.f;
+      for (int i = threadIdx.x; i < nchunk; i += kSmallNT) {
+        const float* sp = p.smooth_part + ((size_t)(s * p.B + b) * p.chunks0 + i) * 3;
+        sx += sp[0]; sy += sp[1];
+      }
+      sx = block_sum<kSmallNT>(sx, scratch);
+      sy = block_sum<kSmallNT>(sy, scratch);
+      if (threadIdx.x == 0) {
+        p.smoothb[(s * p.B + b) * 2] = sx;
+        p.smoothb[(s * p.B + b) * 2 + 1] = sy;
+      }
+    }
+  }
+  // last block done: assemble the loss dict (trainer.py:672-685)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    is_last = atomicAdd(p.counter, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int si = 0; si < p.S; ++si) {
+      double ml = 0.0, sx = 0.0, sy = 0.0;
+      for (int bi = 0; bi < p.B; ++bi) {
+        ml += (double)((volatile float*)p.lossb)[si * p.B + bi];
+        sx += (double)((volatile float*)p.smoothb)[(si * p.B + bi) * 2];
+        sy += (double)((volatile float*)p.smoothb)[(si * p.B + bi) * 2 + 1];
+      }
+      int hh = p.hs[si], ww = p.ws[si];
+      double min_loss = ml / ((double)p.B * p.H * p.W);
+      double smooth = sx / ((double)p.B * hh * (ww - 1)) + sy / ((double)p.B * (hh - 1) * ww);
+      double loss = min_loss + (double)p.smooth_weight * smooth / (double)(1 << p.scale_id[si]);
+      p.losses[si] = (float)min_loss;
+      p.losses[p.S + si] = (float)loss;
+      p.losses[2 * p.S + 1 + si] = (float)smooth;
+      total += loss;
+    }
+    p.losses[2 * p.S] = (float)(total / p.S);
+    *p.counter = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct CombineParams {
+  const float* up;  // [2S+1] device
+  const float* gphoto[kMaxScales];
+  const float* gsmooth[kMaxScales];
+  float* out[kMaxScales];
+  const float* gradP;  // [S][F][B][12]
+  float* gradP_out;    // [F][B][12]
+  int B, S, F, chunks0;
+  int n[kMaxScales], scale_id[kMaxScales];
+  float smooth_weight;
+};
+
+__global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
+  int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
+  float tot = p.up[2 * p.S] / (float)p.S;
+  if (chunk * kChunk < p.n[s]) {
+    float a = p.up[s] + p.up[p.S + s] + tot;
+    float bb = (p.up[p.S + s] + tot) * p.smooth_weight / (float)(1 << p.scale_id[s]);
+    const float* gp = p.gphoto[s] + (size_t)b * p.n[s];
+    const float* gs = p.gsmooth[s] + (size_t)b * p.n[s];
+    float* o = p.out[s] + (size_t)b * p.n[s];
+    for (int i = chunk * kChunk + threadIdx.x; i < min(p.n[s], (chunk + 1) * kChunk); i += kSmallNT)
+      o[i] = a * gp[i] + bb * gs[i];
+  }
+  if (chunk == 0 && s == 0 && p.gradP_out) {
+    for (int k = threadIdx.x; k < p.F * 12; k += kSmallNT) {
+      int f = k / 12, e = k % 12;
+      float acc = 0.f;
+      for (int si = 0; si < p.S; ++si) {
+        float a = p.up[si] + p.up[p.S + si] + tot;
+        acc += a * p.gradP[((size_t)(si * p.F + f) * p.B + b) * 12 + e];
+      }
+      p.gradP_out[((size_t)f * p.B + b) * 12 + e] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// side outputs of generate_images_pred for one scale (trainer.py:500-537)
+struct WarpParams {
+  const float* disp; const float* invK; const float* P[kMaxSrc]; const float* src[kMaxSrc];
+  float* depth; float* sample[kMaxSrc]; float* color[kMaxSrc];
+  int B, H, W, F, hs, ws, identity;
+  float scale_h, scale_w;
+  GeoConst g;
+};
+
+__global__ void __launch_bounds__(256) k_warp_forward(const WarpParams p) {
+  int HW = p.H * p.W;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)p.B * HW) return;
+  int b = (int)(gid / HW), i = (int)(gid - (size_t)b * HW);
+  int v = i / p.W, u = i - v * p.W;
+  float D = upsample_disp(p.disp + (size_t)b * p.hs * p.ws, p.hs, p.ws, p.scale_h, p.scale_w, p.identity != 0, v, u,
+                          p.g.arith);
+  Cam cam = backproject_pixel(D, p.invK + b * 16, u, v, p.g);
+  if (p.depth) p.depth[gid] = cam.z;
+  for (int f = 0; f < p.F; ++f) {
+    Proj pr = project_pixel(cam, p.P[f] + b * 12, p.g);
+    if (p.sample[f]) {
+      p.sample[f][gid * 2] = pr.gx;
+      p.sample[f][gid * 2 + 1] = pr.gy;
+    }
+    if (p.color[f]) {
+      Taps tp = bilinear_taps(pr, p.W, p.H);
+      const float* img = p.src[f] + (size_t)b * 3 * HW + pr.y0 * p.W + pr.x0;
+      int dx = tp.x1ok ? 1 : 0, dy = tp.y1ok ? p.W : 0;
+      for (int c = 0; c < 3; ++c) {
+        const float* q = img + c * HW;
+        p.color[f][(size_t)b * 3 * HW + c * HW + i] = bilinear_value(tp, q[0], q[dx], q[dy], q[dy + dx], p.g.arith);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+static bool desc_ok(const VslDesc* d) {
+  if (!d || d->abi_version != VSL_ABI_VERSION) return false;
+  if (d->batch < 1 || d->height < 2 || d->width < 2) return false;
+  if (d->num_scales < 1 || d->num_scales > VSL_MAX_SCALES) return false;
+  if (d->num_src < 1 || d->num_src > VSL_MAX_SRC) return false;
+  for (int s = 0; s < d->num_scales; ++s) {
+    int e = d->scale_ids[s];
+    if (e < 0 || e > 8) return false;
+    if ((d->height >> e) < 2 || (d->width >> e) < 2) return false;
+    if (((d->height >> e) << e) != d->height || ((d->width >> e) << e) != d->width) return false;
+  }
+  return true;
+}
+
+static GeoConst make_geo(const VslDesc* d) {
+  GeoConst g;
+  g.min_disp = d->min_disp; g.disp_range = d->disp_range; g.eps = d->eps;
+  g.W = d->width; g.H = d->height;
+  g.wm1 = (float)(d->width - 1); g.hm1 = (float)(d->height - 1);
+  g.inv_wm1 = 1.0f / g.wm1; g.inv_hm1 = 1.0f / g.hm1;
+  g.arith = d->arith;
+  return g;
+}
+
+struct Plan {  // sizes derived from the descriptor; identical in workspace_bytes() and the launcher
+  int tw, th, tiles_x, tiles_y, num_cta, kpartial, chunks0;
+  size_t off_partials, off_gD[kMaxScales], off_mean, off_smooth, off_lossb, off_smoothb, off_counter, total;
+};
+
+static Plan make_plan(const VslDesc* d) {
+  Plan pl;
+  pl.tw = 32; pl.th = 16;
+  pl.tiles_x = (d->width + pl.tw - 1) / pl.tw;
+  pl.tiles_y = (d->height + pl.th - 1) / pl.th;
+  pl.num_cta = pl.tiles_x * pl.tiles_y * d->batch;
+  pl.kpartial = 1 + d->num_src * 12;
+  pl.chunks0 = (d->height * d->width + kChunk - 1) / kChunk;
+  size_t off = 0;
+  auto take = [&](size_t floats) { size_t o = off; off += (floats + 63) / 64 * 64; return o; };
+  pl.off_partials = take((size_t)pl.num_cta * d->num_scales * pl.kpartial);
+  for (int s = 0; s < d->num_scales; ++s)
+    pl.off_gD[s] = d->scale_ids[s] == 0 ? 0 : take((size_t)d->batch * d->height * d->width);
+  pl.off_mean = take((size_t)d->num_scales * d->batch * pl.chunks0);
+  pl.off_smooth = take((size_t)d->num_scales * d->batch * pl.chunks0 * 3);
+  pl.off_lossb = take((size_t)d->num_scales * d->batch);
+  pl.off_smoothb = take((size_t)d->num_scales * d->batch * 2);
+  pl.off_counter = take(64);
+  pl.total = off * sizeof(float);
+  return pl;
+}
+
+template <class C>
+static int launch_photometric(const PhotoParams& pp, const Plan& pl, int batch, cudaStream_t st) {
+  static bool attr_done = false;  // idempotent; a race only repeats the call
+  if (!attr_done) {
+    VSL_CUDA_OK(cudaFuncSetAttribute(k_photometric<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kBytes));
+    attr_done = true;
+  }
+  dim3 grid(pl.tiles_x, pl.tiles_y, batch);
+  k_photometric<C><<<grid, C::NT, C::kBytes, st>>>(pp);
+  VSL_CUDA_OK(cudaGetLastError());
+  return VSL_OK;
+}
+
+}  // namespace vsl
+
+using namespace vsl;
+
+extern "C" {
+
+int vsl_abi_version(void) { return VSL_ABI_VERSION; }
+
+const char* vsl_status_string(int status) {
+  switch (status) {
+    case VSL_OK: return "ok";
+    case VSL_ERR_BAD_DESC: return "bad descriptor";
+    case VSL_ERR_NULL_POINTER: return "null pointer";
+    case VSL_ERR_MISALIGNED: return "misaligned buffer";
+    case VSL_ERR_UNSUPPORTED: return "unsupported option";
+    case VSL_ERR_WORKSPACE: return "workspace too small";
+    case VSL_ERR_CUDA: return "CUDA error";
+    default: return "unknown status";
+  }
+}
+
+int vsl_last_cuda_error(void) { return g_last_cuda_error; }
+
+size_t vsl_loss_workspace_bytes(const VslDesc* desc) {
+  if (!desc_ok(desc)) return 0;
+  return make_plan(desc).total;
+}
+
+int vsl_loss_forward_backward(const VslDesc* d, const VslLossBuffers* buf, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
+  if (!buf || !workspace) return VSL_ERR_NULL_POINTER;
+  if (d->flags != VSL_FLAG_AUTOMASK) return VSL_ERR_UNSUPPORTED;   // default reference flags only
+  if (d->image_dtype != VSL_DTYPE_F32) return VSL_ERR_UNSUPPORTED;
+  if (d->num_src > 3) return VSL_ERR_UNSUPPORTED;
+  const int S = d->num_scales, F = d->num_src;
+  Plan pl = make_plan(d);
+  if (workspace_bytes < pl.total) return VSL_ERR_WORKSPACE;
+  if (((uintptr_t)workspace & 15u) != 0) return VSL_ERR_MISALIGNED;
+  if (!buf->inv_K || !buf->losses || !buf->grad_P) return VSL_ERR_NULL_POINTER;
+  for (int s = 0; s < S; ++s)
+    if (!buf->target[s] || !buf->disp[s] || !buf->noise[s] || !buf->grad_disp_photo[s] || !buf->grad_disp_smooth[s])
+      return VSL_ERR_NULL_POINTER;
+  for (int f = 0; f < F; ++f)
+    if (!buf->source[f] || !buf->P[f]) return VSL_ERR_NULL_POINTER;
+  if (d->scale_ids[0] != 0) return VSL_ERR_UNSUPPORTED;  // level 0 is the photometric target
+
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+
+  SmallParams sp = {};
+  PhotoParams pp = {};
+  pp.tgt = (const float*)buf->target[0];
+  pp.invK = buf->inv_K;
+  pp.B = sp.B = d->batch; pp.H = sp.H = d->height; pp.W = sp.W = d->width; pp.S = sp.S = S; pp.F = sp.F = F;
+  pp.g = make_geo(d);
+  pp.wpix = 1.0f / ((float)d->batch * d->height * d->width);
+  pp.partials = ws + pl.off_partials;
+  for (int f = 0; f < F; ++f) { pp.src[f] = (const float*)buf->source[f]; pp.P[f] = buf->P[f]; }
+  for (int s = 0; s < S; ++s) {
+    int e = d->scale_ids[s];
+    int hs = d->height >> e, wsz = d->width >> e;
+    pp.hs[s] = sp.hs[s] = hs; pp.ws[s] = sp.ws[s] = wsz;
+    pp.scale_h[s] = sp.scale_h[s] = (float)hs / (float)d->height;
+    pp.scale_w[s] = sp.scale_w[s] = (float)wsz / (float)d->width;
+    pp.identity_scale[s] = sp.identity_scale[s] = (e == 0);
+    pp.disp[s] = sp.disp[s] = buf->disp[s];
+    pp.noise[s] = buf->noise[s];
+    pp.mask[s] = buf->mask[s];
+    pp.gD[s] = (e == 0) ? buf->grad_disp_photo[s] : ws + pl.off_gD[s];
+    sp.gD[s] = (e == 0) ? nullptr : ws + pl.off_gD[s];
+    sp.img[s] = (const float*)buf->target[s];
+    sp.gsmooth[s] = buf->grad_disp_smooth[s];
+    sp.gphoto[s] = buf->grad_disp_photo[s];
+    sp.scale_id[s] = e;
+  }
+  sp.mean_part = ws + pl.off_mean;
+  sp.smooth_part = ws + pl.off_smooth;
+  sp.partials = pp.partials;
+  sp.lossb = ws + pl.off_lossb;
+  sp.smoothb = ws + pl.off_smoothb;
+  sp.gradP = buf->grad_P;
+  sp.losses = buf->losses;
+  sp.counter = (unsigned*)(ws + pl.off_counter);
+  sp.chunks0 = pl.chunks0;
+  sp.tiles_per_image = pl.tiles_x * pl.tiles_y;
+  sp.kpartial = pl.kpartial;
+  sp.smooth_weight = d->smooth_weight;
+
+  VSL_CUDA_OK(cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), st));
+  dim3 sgrid(pl.chunks0, d->batch, S);
+  k_smooth_mean<<<sgrid, kSmallNT, 0, st>>>(sp);
+  VSL_CUDA_OK(cudaGetLastError());
+  k_smooth_terms<<<sgrid, kSmallNT, 0, st>>>(sp);
+  VSL_CUDA_OK(cudaGetLastError());
+  int rc;
+  if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256>>(pp, pl, d->batch, st);
+  else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256>>(pp, pl, d->batch, st);
+  else rc = launch_photometric<TileCfg<32, 16, 3, 256>>(pp, pl, d->batch, st);
+  if (rc != VSL_OK) return rc;
+  k_epilogue<<<sgrid, kSmallNT, 0, st>>>(sp);
+  VSL_CUDA_OK(cudaGetLastError());
+  return VSL_OK;
+}
+
+int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLossBuffers* buf,
+                           float* const grad_disp[VSL_MAX_SCALES], float* grad_P_out, void* stream) {
+  if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
+  if (!upstream || !buf || !grad_disp) return VSL_ERR_NULL_POINTER;
+  CombineParams cp = {};
+  cp.up = upstream; cp.B = d->batch; cp.S = d->num_scales; cp.F = d->num_src;
+  cp.chunks0 = (d->height * d->width + kChunk - 1) / kChunk;
+  cp.smooth_weight = d->smooth_weight;
+  cp.gradP = buf->grad_P; cp.gradP_out = grad_P_out;
+  for (int s = 0; s < d->num_scales; ++s) {
+    if (!buf->grad_disp_photo[s] || !buf->grad_disp_smooth[s] || !grad_disp[s]) return VSL_ERR_NULL_POINTER;
+    int e = d->scale_ids[s];
+    cp.n[s] = (d->height >> e) * (d->width >> e);
+    cp.scale_id[s] = e;
+    cp.gphoto[s] = buf->grad_disp_photo[s]; cp.gsmooth[s] = buf->grad_disp_smooth[s]; cp.out[s] = grad_disp[s];
+  }
+  if (grad_P_out && !buf->grad_P) return VSL_ERR_NULL_POINTER;
+  dim3 grid(cp.chunks0, d->batch, d->num_scales);
+  k_combine<<<grid, kSmallNT, 0, (cudaStream_t)stream>>>(cp);
+  VSL_CUDA_OK(cudaGetLastError());
+  return VSL_OK;
+}
+
+int vsl_warp_forward(const VslDesc* d, int scale_index, const float* disp, const float* inv_K,
+                     const float* const P[VSL_MAX_SRC], const void* const source[VSL_MAX_SRC], float* depth,
+                     float* const sample[VSL_MAX_SRC], float* const color[VSL_MAX_SRC], void* stream) {
+  if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
+  if (scale_index < 0 || scale_index >= d->num_scales) return VSL_ERR_BAD_DESC;
+  if (d->image_dtype != VSL_DTYPE_F32 || (d->flags & VSL_FLAG_V1_MULTISCALE)) return VSL_ERR_UNSUPPORTED;
+  if (!disp || !inv_K || !P || !source) return VSL_ERR_NULL_POINTER;
+  WarpParams wp = {};
+  int e = d->scale_ids[scale_index];
+  wp.disp = disp; wp.invK = inv_K; wp.depth = depth;
+  wp.B = d->batch; wp.H = d->height; wp.W = d->width; wp.F = d->num_src;
+  wp.hs = d->height >> e; wp.ws = d->width >> e; wp.identity = (e == 0);
+  wp.scale_h = (float)wp.hs / (float)d->height; wp.scale_w = (float)wp.ws / (float)d->width;
+  wp.g = make_geo(d);
+  for (int f = 0; f < d->num_src; ++f) {
+    if (!P[f]) return VSL_ERR_NULL_POINTER;
+    wp.P[f] = P[f];
+    wp.src[f] = (const float*)source[f];
+    wp.sample[f] = sample ? sample[f] : nullptr;
+    wp.color[f] = color ? color[f] : nullptr;
+    if (wp.color[f] && !wp.src[f]) return VSL_ERR_NULL_POINTER;
+  }
+  size_t n = (size_t)d->batch * d->height * d->width;
+  k_warp_forward<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wp);
+  VSL_CUDA_OK(cudaGetLastError());
+  return VSL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,412 @@
+// Stand-alone layers behind the reference's layers.py call surface (include/vsl.h, second half):
+// BackprojectDepth, Project3D, SSIM, compute_reprojection_loss, get_smooth_loss, forward and
+// backward.  These serve callers that use the layers one at a time; the training hot path is the
+// fused kernel in vsl_fused.cu.  Forward arithmetic follows eager PyTorch-CUDA's rounding
+// (vsl_math.cuh); backward arithmetic is plain fp32.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vsl.h"
+#include "vsl_math.cuh"
+
+namespace vsl {
+
+extern thread_local int g_last_cuda_error;  // defined in vsl_fused.cu
+#define VSL_L_OK(expr)                                                \
+  do {                                                                \
+    cudaError_t e__ = (expr);                                         \
+    if (e__ != cudaSuccess) { g_last_cuda_error = (int)e__; return VSL_ERR_CUDA; } \
+  } while (0)
+
+constexpr int kNT = 256;
+
+__device__ __forceinline__ float warp_sum_l(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float block_sum_l(float v, float* scratch) {
+  v = warp_sum_l(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNT / 32; ++i) r += scratch[i];
+  return r;
+}
+
+// ---- BackprojectDepth (layers.py:234-239) ---------------------------------------------------------
+__global__ void __launch_bounds__(kNT) k_backproject_fwd(int B, int H, int W, int arith, const float* __restrict__ depth,
+                                                         const float* __restrict__ invK, float* __restrict__ cam) {
+  int HW = H * W;
+  size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
+  if (gid >= (size_t)B * HW) return;
+  int b = (int)(gid / HW), i = (int)(gid - (size_t)b * HW);
+  float fu = (float)(i % W), fv = (float)(i / W);
+  const float* k = invK + b * 16;
+  float z = depth[gid];
+  float* o = cam + (size_t)b * 4 * HW + i;
+  o[0] = mul_rn(z, dot3(k[0], fu, k[1], fv, k[2], 1.0f, arith));
+  o[HW] = mul_rn(z, dot3(k[4], fu, k[5], fv, k[6], 1.0f, arith));
+  o[2 * HW] = mul_rn(z, dot3(k[8], fu, k[9], fv, k[10], 1.0f, arith));
+  o[3 * HW] = 1.0f;
+}
+__global__ void __launch_bounds__(kNT) k_backproject_bwd(int B, int H, int W, const float* __restrict__ gcam,
+                                                         const float* __restrict__ invK, float* __restrict__ gdepth) {
+  int HW = H * W;
+  size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
+  if (gid >= (size_t)B * HW) return;
+  int b = (int)(gid / HW), i = (int)(gid - (size_t)b * HW);
+  float fu = (float)(i % W), fv = (float)(i / W);
+  const float* k = invK + b * 16;
+  const float* g = gcam + (size_t)b * 4 * HW + i;
+  gdepth[gid] = g[0] * (k[0] * fu + k[1] * fv + k[2]) + g[HW] * (k[4] * fu + k[5] * fv + k[6]) +
+                g[2 * HW] * (k[8] * fu + k[9] * fv + k[10]);
+}
+
+// ---- Project3D (layers.py:253-264) ------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT) k_project_fwd(int B, int H, int W, float eps, int arith,
+                                                     const float* __restrict__ pts, const float* __restrict__ P,
+                                                     float* __restrict__ pix) {
+  int HW = H * W;
+  size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
+  if (gid >= (size_t)B * HW) return;
+  int b = (int)(gid / HW), i = (int)(gid - (size_t)b * HW);
+  const float* q = pts + (size_t)b * 4 * HW + i;
+  const float* p = P + b * 12;
+  float X = q[0], Y = q[HW], Z = q[2 * HW], Wc = q[3 * HW];
+  float c0 = dot4(p[0], X, p[1], Y, p[2], Z, p[3], Wc, arith);
+  float c1 = dot4(p[4], X, p[5], Y, p[6], Z, p[7], Wc, arith);
+  float c2 = dot4(p[8], X, p[9], Y, p[10], Z, p[11], Wc, arith);
+  float zeta = add_rn(c2, eps);
+  float px = div_rn(c0, zeta), py = div_rn(c1, zeta);
+  float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  float nx = (arith & kTrueDiv) ? div_rn(px, wm1) : mul_rn(px, 1.0f / wm1);
+  float ny = (arith & kTrueDiv) ? div_rn(py, hm1) : mul_rn(py, 1.0f / hm1);
+  pix[gid * 2] = mul_rn(sub_rn(nx, 0.5f), 2.0f);
+  pix[gid * 2 + 1] = mul_rn(sub_rn(ny, 0.5f), 2.0f);
+}
+// grad_points per pixel + per-block partial sums of grad_P (12 floats), reduced by k_project_bwd_reduce
+__global__ void __launch_bounds__(kNT) k_project_bwd(int B, int H, int W, float eps, const float* __restrict__ pts,
+                                                     const float* __restrict__ P, const float* __restrict__ gpix,
+                                                     float* __restrict__ gpts, float* __restrict__ part) {
+  __shared__ float scratch[kNT / 32];
+  int HW = H * W, b = blockIdx.y;
+  int i = blockIdx.x * kNT + threadIdx.x;
+  float acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+  if (i < HW) {
+    const float* q = pts + (size_t)b * 4 * HW + i;
+    const float* p = P + b * 12;
+    float X[4] = {q[0], q[HW], q[2 * HW], q[3 * HW]};
+    float c0 = p[0] * X[0] + p[1] * X[1] + p[2] * X[2] + p[3] * X[3];
+    float c1 = p[4] * X[0] + p[5] * X[1] + p[6] * X[2] + p[7] * X[3];
+    float c2 = p[8] * X[0] + p[9] * X[1] + p[10] * X[2] + p[11] * X[3];
+    float iz = 1.0f / (c2 + eps);
+    size_t gid = (size_t)b * HW + i;
+    float gpx = gpix[gid * 2] * 2.0f / (float)(W - 1), gpy = gpix[gid * 2 + 1] * 2.0f / (float)(H - 1);
+    float g0 = gpx * iz, g1 = gpy * iz, g2 = -(g0 * c0 + g1 * c1) * iz;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc[k] = g0 * X[k]; acc[4 + k] = g1 * X[k]; acc[8 + k] = g2 * X[k];
+      gpts[(size_t)b * 4 * HW + (size_t)k * HW + i] = g0 * p[k] + g1 * p[4 + k] + g2 * p[8 + k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    float r = block_sum_l(acc[k], scratch);
+    if (threadIdx.x == 0) part[((size_t)b * gridDim.x + blockIdx.x) * 12 + k] = r;
+  }
+}
+__global__ void k_project_bwd_reduce(int nblk, const float* __restrict__ part, float* __restrict__ gP) {
+  int b = blockIdx.x, k = threadIdx.x;
+  if (k >= 12) return;
+  double acc = 0.0;
+  for (int j = 0; j < nblk; ++j) acc += (double)part[((size_t)b * nblk + j) * 12 + k];
+  gP[b * 12 + k] = (float)acc;
+}
+
+// ---- SSIM (layers.py:318-332) and the reprojection loss (trainer.py:543-555) --------------------------
+struct Win {  // reflect-padded 3x3 neighbourhood offsets of a window centre
+  int o[9];
+};
+__device__ __forceinline__ Win window_offsets(int y, int x, int H, int W) {
+  Win w;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) w.o[(dy + 1) * 3 + dx + 1] = reflect1(y + dy, H) * W + reflect1(x + dx, W);
+  return w;
+}
+__device__ __forceinline__ SsimOut ssim_at(const float* __restrict__ x, const float* __restrict__ y, const Win& w) {
+  float sx = 0.f, sxx = 0.f, sxy = 0.f, sy = 0.f, syy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float xv = x[w.o[k]], yv = y[w.o[k]];
+    sx = add_rn(sx, xv); sxx = add_rn(sxx, mul_rn(xv, xv)); sxy = add_rn(sxy, mul_rn(xv, yv));
+    sy = add_rn(sy, yv); syy = add_rn(syy, mul_rn(yv, yv));
+  }
+  float mu_y = div9(sy);
+  float sig_y = sub_rn(div9(syy), mul_rn(mu_y, mu_y));
+  return ssim_from_sums(sx, sxx, sxy, mu_y, sig_y);
+}
+
+__global__ void __launch_bounds__(kNT) k_ssim_fwd(int planes, int H, int W, const float* __restrict__ x,
+                                                  const float* __restrict__ y, float* __restrict__ out) {
+  int HW = H * W;
+  size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
+  if (gid >= (size_t)planes * HW) return;
+  size_t pl = gid / HW;
+  int i = (int)(gid - pl * HW);
+  Win w = window_offsets(i / W, i % W, H, W);
+  out[gid] = ssim_at(x + pl * HW, y + pl * HW, w).val;
+}
+
+// d ssim(window p) / d x_q contributions gathered at q.  `swap` computes the gradient for y instead
+// (SSIM is symmetric in its arguments).  Returns sum_p cnt * go[p] * dssim_p/dx_q.
+__device__ __forceinline__ float ssim_grad_gather(const float* __restrict__ x, const float* __restrict__ y,
+                                                  const float* __restrict__ go, float go_scale, int qy, int qx, int H,
+                                                  int W) {
+  float xq = x[qy * W + qx], yq = y[qy * W + qx];
+  float acc = 0.f;
+  for (int dy = -1; dy <= 1; ++dy) {
+    int py = qy + dy;
+    if (py < 0 || py >= H) continue;
+    float cy = ((dy == -1 && qy == 1) || (dy == 1 && qy == H - 2)) ? 2.f : 1.f;
+    for (int dx = -1; dx <= 1; ++dx) {
+      int px = qx + dx;
+      if (px < 0 || px >= W) continue;
+      float cx = ((dx == -1 && qx == 1) || (dx == 1 && qx == W - 2)) ? 2.f : 1.f;
+      float g = go[py * W + px];
+      if (g == 0.f) continue;
+      Win w = window_offsets(py, px, H, W);
+      // window sums of y for mu_y (ssim_at recomputes them; needed for the gradient too)
+      float sy = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) sy = add_rn(sy, y[w.o[k]]);
+      float mu_y = div9(sy);
+      SsimOut so = ssim_at(x, y, w);
+      if (!so.live) continue;
+      float dmu, dexx, dexy;
+      ssim_r_grads(so, mu_y, dmu, dexx, dexy);
+      acc += cy * cx * g * go_scale * (-0.5f / 9.0f) * (dmu + 2.f * xq * dexx + yq * dexy);
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kNT) k_ssim_bwd(int planes, int H, int W, const float* __restrict__ x,
+                                                  const float* __restrict__ y, const float* __restrict__ go,
+                                                  float* __restrict__ gx, float* __restrict__ gy) {
+  int HW = H * W;
+  size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
+  if (gid >= (size_t)planes * HW) return;
+  size_t pl = gid / HW;
+  int i = (int)(gid - pl * HW);
+  const float* xp = x + pl * HW;
+  const float* yp = y + pl * HW;
+  const float* gp = go + pl * HW;
+  if (gx) gx[gid] = ssim_grad_gather(xp, yp, gp, 1.f, i / W, i % W, H, W);
+  if (gy) gy[gid] = ssim_grad_gather(yp, xp, gp, 1.f, i / W, i % W, H, W);
+}
+
+__global__ void __launch_bounds__(kNT) k_reproj_fwd(int B, int H, int W, int no_ssim, int arith,
+                                                    const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                    float* __restrict__ out) {
+  int HW = H * W;
+  size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
+  if (gid >= (size_t)B * HW) return;
+  int b = (int)(gid / HW), i = (int)(gid - (size_t)b * HW);
+  const float* x = pred + (size_t)b * 3 * HW;
+  const float* y = tgt + (size_t)b * 3 * HW;
+  float l1[3], ss[3];
+  Win w = window_offsets(i / W, i % W, H, W);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    l1[c] = fabsf(sub_rn(y[c * HW + i], x[c * HW + i]));
+    ss[c] = no_ssim ? 0.f : ssim_at(x + c * HW, y + c * HW, w).val;
+  }
+  float ml = mean3(l1[0], l1[1], l1[2], arith);
+  out[gid] = no_ssim ? ml : add_rn(mul_rn(0.85f, mean3(ss[0], ss[1], ss[2], arith)), mul_rn(0.15f, ml));
+}
+
+__global__ void __launch_bounds__(kNT) k_reproj_bwd(int B, int H, int W, int no_ssim, const float* __restrict__ pred,
+                                                    const float* __restrict__ tgt, const float* __restrict__ go,
+                                                    float* __restrict__ gpred, float* __restrict__ gtgt) {
+  int HW = H * W;
+  size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
+  if (gid >= (size_t)B * HW) return;
+  int b = (int)(gid / HW), i = (int)(gid - (size_t)b * HW);
+  const float* gp = go + (size_t)b * HW;
+  float wl1 = no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f);
+  for (int c = 0; c < 3; ++c) {
+    const float* x = pred + ((size_t)b * 3 + c) * HW;
+    const float* y = tgt + ((size_t)b * 3 + c) * HW;
+    float d = x[i] - y[i];
+    float s = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    float l1g = gp[i] * wl1 * s;
+    if (gpred) gpred[((size_t)b * 3 + c) * HW + i] =
+        l1g + (no_ssim ? 0.f : ssim_grad_gather(x, y, gp, 0.85f / 3.0f, i / W, i % W, H, W));
+    if (gtgt) gtgt[((size_t)b * 3 + c) * HW + i] =
+        -l1g + (no_ssim ? 0.f : ssim_grad_gather(y, x, gp, 0.85f / 3.0f, i / W, i % W, H, W));
+  }
+}
+
+// ---- get_smooth_loss (layers.py:286-299) --------------------------------------------------------------
+__device__ __forceinline__ float edge_w(const float* img, int n, int ia, int ib) {
+  float g = fabsf(img[ia] - img[ib]) + fabsf(img[n + ia] - img[n + ib]) + fabsf(img[2 * n + ia] - img[2 * n + ib]);
+  return expf(-g * (1.0f / 3.0f));
+}
+__global__ void __launch_bounds__(kNT) k_smooth_fwd(int H, int W, const float* __restrict__ disp,
+                                                    const float* __restrict__ img, float* __restrict__ part) {
+  __shared__ float scratch[kNT / 32];
+  int n = H * W, b = blockIdx.y;
+  int i = blockIdx.x * kNT + threadIdx.x;
+  const float* d = disp + (size_t)b * n;
+  const float* im = img + (size_t)b * 3 * n;
+  float sx = 0.f, sy = 0.f;
+  if (i < n) {
+    int v = i / W, u = i - v * W;
+    if (u + 1 < W) sx = fabsf(d[i] - d[i + 1]) * edge_w(im, n, i, i + 1);
+    if (v + 1 < H) sy = fabsf(d[i] - d[i + W]) * edge_w(im, n, i, i + W);
+  }
+  sx = block_sum_l(sx, scratch);
+  sy = block_sum_l(sy, scratch);
+  if (threadIdx.x == 0) {
+    part[((size_t)b * gridDim.x + blockIdx.x) * 2] = sx;
+    part[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = sy;
+  }
+}
+__global__ void k_smooth_fwd_reduce(int nblk, int B, int H, int W, const float* __restrict__ part,
+                                    float* __restrict__ loss) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double sx = 0.0, sy = 0.0;
+  for (size_t j = 0; j < (size_t)nblk * B; ++j) { sx += (double)part[j * 2]; sy += (double)part[j * 2 + 1]; }
+  *loss = (float)(sx / ((double)B * H * (W - 1)) + sy / ((double)B * (H - 1) * W));
+}
+__global__ void __launch_bounds__(kNT) k_smooth_bwd(int B, int H, int W, const float* __restrict__ disp,
+                                                    const float* __restrict__ img, const float* __restrict__ gl,
+                                                    float* __restrict__ gdisp) {
+  int n = H * W, b = blockIdx.y;
+  int i = blockIdx.x * kNT + threadIdx.x;
+  if (i >= n) return;
+  const float* d = disp + (size_t)b * n;
+  const float* im = img + (size_t)b * 3 * n;
+  float cx = *gl / ((float)B * H * (W - 1)), cy = *gl / ((float)B * (H - 1) * W);
+  int v = i / W, u = i - v * W;
+  float di = d[i], g = 0.f;
+  auto sg = [](float t) { return t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f); };
+  if (u + 1 < W) g += sg(di - d[i + 1]) * edge_w(im, n, i, i + 1) * cx;
+  if (u > 0) g -= sg(d[i - 1] - di) * edge_w(im, n, i - 1, i) * cx;
+  if (v + 1 < H) g += sg(di - d[i + W]) * edge_w(im, n, i, i + W) * cy;
+  if (v > 0) g -= sg(d[i - W] - di) * edge_w(im, n, i - W, i) * cy;
+  gdisp[(size_t)b * n + i] = g;
+}
+
+static unsigned blocks_for(size_t n) { return (unsigned)((n + kNT - 1) / kNT); }
+
+}  // namespace vsl
+
+using namespace vsl;
+
+extern "C" {
+
+int vsl_backproject_forward(int B, int H, int W, int arith, const float* depth, const float* inv_K, float* cam,
+                            void* stream) {
+  if (B < 1 || H < 1 || W < 1) return VSL_ERR_BAD_DESC;
+  if (!depth || !inv_K || !cam) return VSL_ERR_NULL_POINTER;
+  k_backproject_fwd<<<blocks_for((size_t)B * H * W), kNT, 0, (cudaStream_t)stream>>>(B, H, W, arith, depth, inv_K, cam);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+int vsl_backproject_backward(int B, int H, int W, const float* gcam, const float* inv_K, float* gdepth, void* stream) {
+  if (B < 1 || H < 1 || W < 1) return VSL_ERR_BAD_DESC;
+  if (!gcam || !inv_K || !gdepth) return VSL_ERR_NULL_POINTER;
+  k_backproject_bwd<<<blocks_for((size_t)B * H * W), kNT, 0, (cudaStream_t)stream>>>(B, H, W, gcam, inv_K, gdepth);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+int vsl_project_forward(int B, int H, int W, float eps, int arith, const float* points, const float* P, float* pix,
+                        void* stream) {
+  if (B < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
+  if (!points || !P || !pix) return VSL_ERR_NULL_POINTER;
+  k_project_fwd<<<blocks_for((size_t)B * H * W), kNT, 0, (cudaStream_t)stream>>>(B, H, W, eps, arith, points, P, pix);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+size_t vsl_project_workspace_bytes(int B, int H, int W) {
+  if (B < 1 || H < 1 || W < 1) return 0;
+  return (size_t)B * blocks_for((size_t)H * W) * 12 * sizeof(float);
+}
+int vsl_project_backward(int B, int H, int W, float eps, const float* points, const float* P, const float* gpix,
+                         float* gpoints, float* gP, void* ws, size_t ws_bytes, void* stream) {
+  if (B < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
+  if (!points || !P || !gpix || !gpoints || !gP || !ws) return VSL_ERR_NULL_POINTER;
+  if (ws_bytes < vsl_project_workspace_bytes(B, H, W)) return VSL_ERR_WORKSPACE;
+  unsigned nblk = blocks_for((size_t)H * W);
+  k_project_bwd<<<dim3(nblk, B), kNT, 0, (cudaStream_t)stream>>>(B, H, W, eps, points, P, gpix, gpoints, (float*)ws);
+  VSL_L_OK(cudaGetLastError());
+  k_project_bwd_reduce<<<B, 32, 0, (cudaStream_t)stream>>>((int)nblk, (const float*)ws, gP);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+int vsl_ssim_forward(int B, int C, int H, int W, const float* x, const float* y, float* out, void* stream) {
+  if (B < 1 || C < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
+  if (!x || !y || !out) return VSL_ERR_NULL_POINTER;
+  k_ssim_fwd<<<blocks_for((size_t)B * C * H * W), kNT, 0, (cudaStream_t)stream>>>(B * C, H, W, x, y, out);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+int vsl_ssim_backward(int B, int C, int H, int W, const float* x, const float* y, const float* go, float* gx, float* gy,
+                      void* stream) {
+  if (B < 1 || C < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
+  if (!x || !y || !go) return VSL_ERR_NULL_POINTER;
+  k_ssim_bwd<<<blocks_for((size_t)B * C * H * W), kNT, 0, (cudaStream_t)stream>>>(B * C, H, W, x, y, go, gx, gy);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+int vsl_reprojection_loss_forward(int B, int H, int W, int no_ssim, int arith, const float* pred, const float* target,
+                                  float* out, void* stream) {
+  if (B < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
+  if (!pred || !target || !out) return VSL_ERR_NULL_POINTER;
+  k_reproj_fwd<<<blocks_for((size_t)B * H * W), kNT, 0, (cudaStream_t)stream>>>(B, H, W, no_ssim, arith, pred, target, out);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+int vsl_reprojection_loss_backward(int B, int H, int W, int no_ssim, const float* pred, const float* target,
+                                   const float* go, float* gpred, float* gtarget, void* stream) {
+  if (B < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
+  if (!pred || !target || !go) return VSL_ERR_NULL_POINTER;
+  k_reproj_bwd<<<blocks_for((size_t)B * H * W), kNT, 0, (cudaStream_t)stream>>>(B, H, W, no_ssim, pred, target, go, gpred, gtarget);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+size_t vsl_smooth_workspace_bytes(int B, int H, int W) {
+  if (B < 1 || H < 1 || W < 1) return 0;
+  return (size_t)B * blocks_for((size_t)H * W) * 2 * sizeof(float);
+}
+int vsl_smooth_loss_forward(int B, int H, int W, const float* disp, const float* img, float* loss, void* ws,
+                            size_t ws_bytes, void* stream) {
+  if (B < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
+  if (!disp || !img || !loss || !ws) return VSL_ERR_NULL_POINTER;
+  if (ws_bytes < vsl_smooth_workspace_bytes(B, H, W)) return VSL_ERR_WORKSPACE;
+  unsigned nblk = blocks_for((size_t)H * W);
+  k_smooth_fwd<<<dim3(nblk, B), kNT, 0, (cudaStream_t)stream>>>(H, W, disp, img, (float*)ws);
+  VSL_L_OK(cudaGetLastError());
+  k_smooth_fwd_reduce<<<1, 32, 0, (cudaStream_t)stream>>>((int)nblk, B, H, W, (const float*)ws, loss);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+int vsl_smooth_loss_backward(int B, int H, int W, const float* disp, const float* img, const float* gl, float* gdisp,
+                             void* stream) {
+  if (B < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
+  if (!disp || !img || !gl || !gdisp) return VSL_ERR_NULL_POINTER;
+  k_smooth_bwd<<<dim3(blocks_for((size_t)H * W), B), kNT, 0, (cudaStream_t)stream>>>(B, H, W, disp, img, gl, gdisp);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+// Per-pixel arithmetic of the view-synthesis loss path, written once for the device kernels.
+//
+// The forward chain is rounded step by step exactly like eager PyTorch-CUDA runs the reference
+// (one rounding per Python-level op, FMA contraction only where a single ATen kernel contracts),
+// because bilinear tap indices and the auto-mask arg-min are compared bit for bit.  Everything
+// that matters for that is spelt with *_rn intrinsics so nvcc cannot re-associate or contract it.
+// Reference formulas: layers.py:85-94 (disp_to_depth), :234-239 (BackprojectDepth), :253-264
+// (Project3D), :318-332 (SSIM); trainer.py:500-501 (up-sample), :534-537 (grid_sample), :543-555.
+//
+// The header also compiles as plain C++ (tests/emul builds the tile logic for the host to check
+// indexing and the analytic gradients without a GPU); the host build is test-only.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VSL_HD __host__ __device__ __forceinline__
+#else
+#define VSL_HD inline
+#endif
+
+namespace vsl {
+
+#if defined(__CUDA_ARCH__)
+VSL_HD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+VSL_HD float add_rn(float a, float b) { return __fadd_rn(a, b); }
+VSL_HD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+VSL_HD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+VSL_HD float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+VSL_HD float rcp_rn(float a) { return __frcp_rn(a); }
+VSL_HD float fast_rcp(float a) { return __frcp_rn(a); }
+#else  // host build (tests/emul): compiled with -ffp-contract=off
+VSL_HD float mul_rn(float a, float b) { volatile float r = a * b; return r; }
+VSL_HD float add_rn(float a, float b) { volatile float r = a + b; return r; }
+VSL_HD float sub_rn(float a, float b) { volatile float r = a - b; return r; }
+VSL_HD float fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
+VSL_HD float div_rn(float a, float b) { volatile float r = a / b; return r; }
+VSL_HD float rcp_rn(float a) { volatile float r = 1.0f / a; return r; }
+VSL_HD float fast_rcp(float a) { return 1.0f / a; }
+#endif
+
+// arithmetic-order selectors; mirror VSL_ARITH_* in include/vsl.h
+enum : int {
+  kTrueDiv = 1 << 0, kDotNoFma = 1 << 1, kDotReverse = 1 << 2, kUpsRight = 1 << 3,
+  kUpsNoFma = 1 << 4, kTapNoFma = 1 << 5, kMeanDiv = 1 << 6
+};
+
+// ---- bmm dot products (cuBLAS SGEMM with K = 3 / K = 4: one FMA chain, k ascending) ----------
+VSL_HD float dot3(float a0, float b0, float a1, float b1, float a2, float b2, int arith) {
+  if (arith & kDotNoFma) return add_rn(add_rn(mul_rn(a0, b0), mul_rn(a1, b1)), mul_rn(a2, b2));
+  if (arith & kDotReverse) return fma_rn(a0, b0, fma_rn(a1, b1, mul_rn(a2, b2)));
+  return fma_rn(a2, b2, fma_rn(a1, b1, mul_rn(a0, b0)));
+}
+VSL_HD float dot4(float a0, float b0, float a1, float b1, float a2, float b2, float a3, float b3, int arith) {
+  if (arith & kDotNoFma)
+    return add_rn(add_rn(add_rn(mul_rn(a0, b0), mul_rn(a1, b1)), mul_rn(a2, b2)), mul_rn(a3, b3));
+  if (arith & kDotReverse) return fma_rn(a0, b0, fma_rn(a1, b1, fma_rn(a2, b2, mul_rn(a3, b3))));
+  return fma_rn(a3, b3, fma_rn(a2, b2, fma_rn(a1, b1, mul_rn(a0, b0))));
+}
+
+// ---- F.interpolate(disp, [H,W], "bilinear", align_corners=False)  (trainer.py:500-501) --------
+// Source index / weights as ATen's upsample_bilinear2d CUDA kernel computes them
+// (torch/include/ATen/native/cuda/UpSample.cuh:115-130).
+struct UpsTap { int i0, i1; float l0, l1; };
+VSL_HD UpsTap ups_tap(int dst, int src_size, float scale) {
+  float s = fma_rn(scale, (float)dst + 0.5f, -0.5f);
+  if (s < 0.f) s = 0.f;
+  UpsTap t;
+  t.i0 = (int)s;
+  t.i1 = t.i0 + ((t.i0 < src_size - 1) ? 1 : 0);
+  t.l1 = sub_rn(s, (float)t.i0);
+  t.l0 = sub_rn(1.0f, t.l1);
+  return t;
+}
+VSL_HD float ups_combine(float l0, float a, float l1, float b, int arith) {
+  if (arith & kUpsNoFma) return add_rn(mul_rn(l0, a), mul_rn(l1, b));
+  if (arith & kUpsRight) return fma_rn(l1, b, mul_rn(l0, a));
+  return fma_rn(l0, a, mul_rn(l1, b));
+}
+// disp: one image plane [hs, ws]; returns the up-sampled value at full-res pixel (v, u)
+VSL_HD float upsample_disp(const float* __restrict__ disp, int hs, int ws, float scale_h, float scale_w,
+                           bool identity, int v, int u, int arith) {
+  if (identity) return disp[v * ws + u];
+  UpsTap ty = ups_tap(v, hs, scale_h), tx = ups_tap(u, ws, scale_w);
+  const float* r0 = disp + ty.i0 * ws;
+  const float* r1 = disp + ty.i1 * ws;
+  float top = ups_combine(tx.l0, r0[tx.i0], tx.l1, r0[tx.i1], arith);
+  float bot = ups_combine(tx.l0, r1[tx.i0], tx.l1, r1[tx.i1], arith);
+  return ups_combine(ty.l0, top, ty.l1, bot, arith);
+}
+
+// ---- geometry ---------------------------------------------------------------------------------
+struct GeoConst {  // per call
+  float min_disp, disp_range, eps;
+  float wm1, hm1;          // (float)(W-1), (float)(H-1)
+  float inv_wm1, inv_hm1;  // 1.0f/(W-1), 1.0f/(H-1) rounded (PyTorch-CUDA divides by a CPU scalar this way)
+  int W, H, arith;
+};
+
+struct Cam {  // camera-space point of a target pixel: X~ = (z*ray, 1)
+  float z, rx, ry, rz, X, Y, Z;
+};
+
+// disp_to_depth (layers.py:90-93) + BackprojectDepth (layers.py:235-236); invK: row-major 4x4
+VSL_HD Cam backproject_pixel(float D, const float* __restrict__ invK, int u, int v, const GeoConst& g) {
+  Cam c;
+  float scaled = add_rn(mul_rn(g.disp_range, D), g.min_disp);
+  c.z = rcp_rn(scaled);
+  float fu = (float)u, fv = (float)v;
+  c.rx = dot3(invK[0], fu, invK[1], fv, invK[2], 1.0f, g.arith);
+  c.ry = dot3(invK[4], fu, invK[5], fv, invK[6], 1.0f, g.arith);
+  c.rz = dot3(invK[8], fu, invK[9], fv, invK[10], 1.0f, g.arith);
+  c.X = mul_rn(c.z, c.rx);
+  c.Y = mul_rn(c.z, c.ry);
+  c.Z = mul_rn(c.z, c.rz);
+  return c;
+}
+
+struct Proj {       // Project3D + grid_sample coordinate chain for one source frame
+  float gx, gy;     // outputs[("sample",f,s)] (normalised grid)
+  float ix, iy;     // clipped sample position in pixels
+  int x0, y0;       // north-west tap (the "projection indices")
+  bool inx, iny;    // gradient passes through the clip (strictly inside)
+};
+
+// P: row-major 3x4 = (K@T)[:3,:]  (layers.py:254-263) then grid_sample's un-normalise + border clip
+// (torch/include/ATen/native/cuda/GridSampler.cuh:23-31, 55-57), align_corners=True.
+VSL_HD Proj project_pixel(const Cam& c, const float* __restrict__ P, const GeoConst& g) {
+  float c0 = dot4(P[0], c.X, P[1], c.Y, P[2], c.Z, P[3], 1.0f, g.arith);
+  float c1 = dot4(P[4], c.X, P[5], c.Y, P[6], c.Z, P[7], 1.0f, g.arith);
+  float c2 = dot4(P[8], c.X, P[9], c.Y, P[10], c.Z, P[11], 1.0f, g.arith);
+  float zeta = add_rn(c2, g.eps);
+  float px = div_rn(c0, zeta), py = div_rn(c1, zeta);
+  float nx = (g.arith & kTrueDiv) ? div_rn(px, g.wm1) : mul_rn(px, g.inv_wm1);
+  float ny = (g.arith & kTrueDiv) ? div_rn(py, g.hm1) : mul_rn(py, g.inv_hm1);
+  Proj r;
+  r.gx = mul_rn(sub_rn(nx, 0.5f), 2.0f);
+  r.gy = mul_rn(sub_rn(ny, 0.5f), 2.0f);
+  float ix = mul_rn(mul_rn(add_rn(r.gx, 1.0f), 0.5f), g.wm1);
+  float iy = mul_rn(mul_rn(add_rn(r.gy, 1.0f), 0.5f), g.hm1);
+  r.inx = (ix > 0.f) && (ix < g.wm1);
+  r.iny = (iy > 0.f) && (iy < g.hm1);
+  r.ix = fminf(g.wm1, fmaxf(ix, 0.f));
+  r.iy = fminf(g.hm1, fmaxf(iy, 0.f));
+  r.x0 = (int)floorf(r.ix);
+  r.y0 = (int)floorf(r.iy);
+  return r;
+}
+
+struct Taps {  // bilinear weights of grid_sampler_2d (nw, ne, sw, se)
+  float nw, ne, sw, se, wx0, wx1, wy0, wy1;
+  bool x1ok, y1ok;
+};
+VSL_HD Taps bilinear_taps(const Proj& r, int W, int H) {
+  Taps t;
+  t.wx1 = sub_rn((float)(r.x0 + 1), r.ix);  // weight of the west column
+  t.wx0 = sub_rn(r.ix, (float)r.x0);        // weight of the east column
+  t.wy1 = sub_rn((float)(r.y0 + 1), r.iy);
+  t.wy0 = sub_rn(r.iy, (float)r.y0);
+  t.nw = mul_rn(t.wx1, t.wy1);
+  t.ne = mul_rn(t.wx0, t.wy1);
+  t.sw = mul_rn(t.wx1, t.wy0);
+  t.se = mul_rn(t.wx0, t.wy0);
+  t.x1ok = r.x0 + 1 < W;
+  t.y1ok = r.y0 + 1 < H;
+  return t;
+}
+VSL_HD float bilinear_value(const Taps& t, float vnw, float vne, float vsw, float vse, int arith) {
+  if (arith & kTapNoFma) {
+    float acc = mul_rn(vnw, t.nw);
+    if (t.x1ok) acc = add_rn(acc, mul_rn(vne, t.ne));
+    if (t.y1ok) acc = add_rn(acc, mul_rn(vsw, t.sw));
+    if (t.x1ok && t.y1ok) acc = add_rn(acc, mul_rn(vse, t.se));
+    return acc;
+  }
+  float acc = mul_rn(vnw, t.nw);
+  if (t.x1ok) acc = fma_rn(vne, t.ne, acc);
+  if (t.y1ok) acc = fma_rn(vsw, t.sw, acc);
+  if (t.x1ok && t.y1ok) acc = fma_rn(vse, t.se, acc);
+  return acc;
+}
+
+// ---- SSIM + L1 (layers.py:318-332, trainer.py:546-553) ------------------------------------------
+VSL_HD float c1f() { return (float)(0.01 * 0.01); }
+VSL_HD float c2f() { return (float)(0.03 * 0.03); }
+
+// avg_pool2d's `sum / 9` (ATen AveragePool2d.cu divides the sequential window sum by the pool size)
+VSL_HD float div9(float a) { return div_rn(a, 9.0f); }
+
+// torch.mean over the 3 channels: sequential sum times float(1/3)
+VSL_HD float mean3(float a, float b, float c, int arith) {
+  float s = add_rn(add_rn(a, b), c);
+  if (arith & kMeanDiv) return div_rn(s, 3.0f);
+  return mul_rn(s, 1.0f / 3.0f);
+}
+
+struct SsimOut {
+  float val;                 // clamp((1 - n/d)/2, 0, 1)
+  float mu_x, n1, n2, d1, d2, r;
+  bool live;                 // clamp passes gradient
+};
+// window sums are the row-major sequential sums ATen's avg_pool2d forms
+VSL_HD SsimOut ssim_from_sums(float sx, float sxx, float sxy, float mu_y, float sig_y) {
+  SsimOut o;
+  o.mu_x = div9(sx);
+  float mu_x2 = mul_rn(o.mu_x, o.mu_x);
+  float sig_x = sub_rn(div9(sxx), mu_x2);
+  float sig_xy = sub_rn(div9(sxy), mul_rn(o.mu_x, mu_y));
+  o.n1 = add_rn(mul_rn(mul_rn(2.0f, o.mu_x), mu_y), c1f());
+  o.n2 = add_rn(mul_rn(2.0f, sig_xy), c2f());
+  o.d1 = add_rn(add_rn(mu_x2, mul_rn(mu_y, mu_y)), c1f());
+  o.d2 = add_rn(add_rn(sig_x, sig_y), c2f());
+  o.r = div_rn(mul_rn(o.n1, o.n2), mul_rn(o.d1, o.d2));
+  float t = mul_rn(sub_rn(1.0f, o.r), 0.5f);
+  o.live = (t >= 0.f) && (t <= 1.f);
+  o.val = fminf(fmaxf(t, 0.f), 1.f);
+  return o;
+}
+
+// d r / d(mu_x, E[x^2], E[xy]) of r = n1 n2 / (d1 d2)  
+VSL_HD void ssim_r_grads(const SsimOut& o, float mu_y, float& dmu, float& dexx, float& dexy) {
+  float inv_d = fast_rcp(o.d1 * o.d2);
+  dexy = 2.0f * o.n1 * inv_d;
+  dexx = -o.r * o.d1 * inv_d;  // -r/d2
+  dmu = inv_d * (2.0f * mu_y * (o.n2 - o.n1) - o.r * 2.0f * o.mu_x * (o.d2 - o.d1));
+}
+
+// reflect-pad-1 index map (nn.ReflectionPad2d(1), layers.py:313): -1 -> 1, n -> n-2
+VSL_HD int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+}  // namespace vsl

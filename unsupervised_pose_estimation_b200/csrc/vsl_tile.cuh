@@ -1,0 +1,387 @@
+// Tile logic of the fused photometric kernel (forward + backward in one pass).
+//
+// One CTA owns a TW x TH tile of target pixels of one image and walks every scale and source
+// frame for it.  Per CTA, once: target tile (+2 halo, reflect-mapped), target window moments,
+// identity-reprojection losses (trainer.py:620-633; independent of scale and pose).  Per scale:
+// warp all source frames on the tile +2 halo (trainer.py:500-537), SSIM+L1 per window on the tile
+// +1 halo (trainer.py:543-555), tie-break noise + min/arg-min (trainer.py:654-670), then the
+// adjoint: SSIM 3x3 gather with the reflection-pad fold, bilinear, projection, depth.
+//
+// Each phase is a function of (tile, thread id) so the same code runs as CUDA threads between
+// __syncthreads() and, in tests/emul, as a host loop over thread ids.
+#pragma once
+#include "vsl_math.cuh"
+
+namespace vsl {
+
+constexpr int kMaxScales = 4;
+constexpr int kMaxSrc = 4;
+
+struct PhotoParams {
+  const float* tgt;               // [B,3,H,W]
+  const float* src[kMaxSrc];      // [B,3,H,W]
+  const float* disp[kMaxScales];  // [B,1,hs,ws]
+  const float* invK;              // [B,4,4]
+  const float* P[kMaxSrc];        // [B,3,4]
+  const float* noise[kMaxScales]; // [B,F,H,W]
+  float* mask[kMaxScales];        // [B,H,W] or null
+  float* gD[kMaxScales];          // [B,H,W]: d(min_loss/s)/d(up-sampled disp_s)
+  float* partials;                // [numCTA][S][1 + F*12]
+  int B, H, W, S, F;
+  int hs[kMaxScales], ws[kMaxScales];
+  float scale_h[kMaxScales], scale_w[kMaxScales];
+  int identity_scale[kMaxScales];  // up-sample is the identity (level size == H x W)
+  GeoConst g;
+  float wpix;                     // 1 / (B*H*W): weight of one pixel in min_loss/s
+};
+
+template <int TW_, int TH_, int F_, int NT_>
+struct TileCfg {
+  static constexpr int TW = TW_, TH = TH_, F = F_, NT = NT_;
+  static constexpr int RW = TW + 4, RH = TH + 4, RN = RW * RH;  // region: tile + 2 halo (warped / target pixels)
+  static constexpr int WW = TW + 2, WH = TH + 2, WN = WW * WH;  // windows: tile + 1 halo (SSIM centres)
+  static constexpr int IN = TW * TH;                            // interior
+  // shared memory layout, in floats
+  static constexpr int oT = 0;                  // target region           [3][RN]
+  static constexpr int oTS = oT + 3 * RN;       // target mu_y, sigma_y    [6][WN]
+  static constexpr int oX = oTS + 6 * WN;       // warped / source region  [F][3][RN]
+  static constexpr int oId = oX + F * 3 * RN;   // identity losses         [F][WN]
+  static constexpr int oCoef = oId + F * WN;    // winner's SSIM adjoint coefficients [9][WN]
+  static constexpr int oIdx = oCoef + 9 * WN;   // winning source frame or -1 [WN] (int)
+  static constexpr int oG = oIdx + WN;          // d warped / d(ix,iy)     [F][6][IN]
+  static constexpr int oRed = oG + F * 6 * IN;  // block-reduction scratch [NT/32][1 + F*12]
+  static constexpr int kFloats = oRed + (NT / 32) * (1 + F * 12);
+  static constexpr int kBytes = kFloats * 4;
+  static constexpr int kPartial = 1 + F * 12;
+};
+
+template <class C>
+struct ThreadState {
+  float loss;
+  float dP[C::F * 12];
+};
+
+struct TileCtx {
+  int b, x0, y0;  // image index, tile origin (pixels)
+  int cta;        // linear CTA id
+};
+
+// ---- phase: load an image tile + 2 halo into a region buffer, reflect-mapped --------------------
+template <class C>
+VSL_HD void phase_load_region(const PhotoParams& p, const TileCtx& t, const float* __restrict__ img_b,
+                              float* __restrict__ dst, int tid) {
+  const int HW = p.H * p.W;
+  for (int i = tid; i < C::RN; i += C::NT) {
+    int ry = i / C::RW, rx = i - ry * C::RW;
+    int gy = t.y0 - 2 + ry, gx = t.x0 - 2 + rx;
+    bool valid = gy >= -1 && gy <= p.H && gx >= -1 && gx <= p.W;
+    int o = reflect1(gy, p.H) * p.W + reflect1(gx, p.W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[c * C::RN + i] = valid ? img_b[c * HW + o] : 0.f;
+  }
+}
+
+// ---- phase: target window moments mu_y, sigma_y on the window grid ------------------------------
+template <class C>
+VSL_HD void phase_target_stats(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int tid) {
+  const float* T = sm + C::oT;
+  float* TS = sm + C::oTS;
+  for (int i = tid; i < C::WN; i += C::NT) {
+    int wy = i / C::WW, wx = i - wy * C::WW;
+    int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
+    bool inside = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float mu = 0.f, sig = 0.f;
+      if (inside) {
+        const float* y = T + c * C::RN + (wy + 1) * C::RW + (wx + 1);
+        float sy = 0.f, syy = 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            float v = y[dy * C::RW + dx];
+            sy = add_rn(sy, v);
+            syy = add_rn(syy, mul_rn(v, v));
+          }
+        mu = div9(sy);
+        sig = sub_rn(div9(syy), mul_rn(mu, mu));
+      }
+      TS[c * C::WN + i] = mu;
+      TS[(3 + c) * C::WN + i] = sig;
+    }
+  }
+}
+
+// SSIM + L1 of one window for one image buffer X (3 channels, region layout); returns the
+// reprojection loss (trainer.py:546-553) and leaves the per-channel SSIM state in `so`.
+template <class C>
+VSL_HD float reproj_window(const float* __restrict__ X, const float* __restrict__ T,
+                           const float* __restrict__ TS, int wy, int wx, int widx, int arith, SsimOut so[3]) {
+  float ss[3], l1[3];
+  const int center = (wy + 1) * C::RW + (wx + 1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* x = X + c * C::RN + center;
+    const float* y = T + c * C::RN + center;
+    float sx = 0.f, sxx = 0.f, sxy = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        float xv = x[dy * C::RW + dx], yv = y[dy * C::RW + dx];
+        sx = add_rn(sx, xv);
+        sxx = add_rn(sxx, mul_rn(xv, xv));
+        sxy = add_rn(sxy, mul_rn(xv, yv));
+      }
+    so[c] = ssim_from_sums(sx, sxx, sxy, TS[c * C::WN + widx], TS[(3 + c) * C::WN + widx]);
+    ss[c] = so[c].val;
+    l1[c] = fabsf(sub_rn(y[0], x[0]));
+  }
+  float ms = mean3(ss[0], ss[1], ss[2], arith);
+  float ml = mean3(l1[0], l1[1], l1[2], arith);
+  return add_rn(mul_rn(0.85f, ms), mul_rn(0.15f, ml));
+}
+
+// ---- phase: identity reprojection loss of source frame f (its region is staged in X[0]) ---------
+template <class C>
+VSL_HD void phase_identity(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int f, int tid) {
+  const float* T = sm + C::oT;
+  const float* TS = sm + C::oTS;
+  const float* X = sm + C::oX;
+  float* Id = sm + C::oId + f * C::WN;
+  for (int i = tid; i < C::WN; i += C::NT) {
+    int wy = i / C::WW, wx = i - wy * C::WW;
+    int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
+    float v = 0.f;
+    if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+      SsimOut so[3];
+      v = reproj_window<C>(X, T, TS, wy, wx, i, p.g.arith, so);
+    }
+    Id[i] = v;
+  }
+}
+
+// ---- phase: warp every source frame on the region for scale s -----------------------------------
+template <class C>
+VSL_HD void phase_warp(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
+  float* X = sm + C::oX;
+  float* G = sm + C::oG;
+  const int HW = p.H * p.W;
+  const float* invK = p.invK + t.b * 16;
+  const float* disp = p.disp[s] + (size_t)t.b * p.hs[s] * p.ws[s];
+  for (int i = tid; i < C::RN; i += C::NT) {
+    int ry = i / C::RW, rx = i - ry * C::RW;
+    int gy = t.y0 - 2 + ry, gx = t.x0 - 2 + rx;
+    bool valid = gy >= -1 && gy <= p.H && gx >= -1 && gx <= p.W;
+    if (!valid) {
+#pragma unroll
+      for (int k = 0; k < C::F * 3; ++k) X[k * C::RN + i] = 0.f;
+      continue;
+    }
+    int v = reflect1(gy, p.H), u = reflect1(gx, p.W);
+    float D = upsample_disp(disp, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s], p.identity_scale[s] != 0, v, u,
+                            p.g.arith);
+    Cam cam = backproject_pixel(D, invK, u, v, p.g);
+    bool interior = ry >= 2 && ry < C::TH + 2 && rx >= 2 && rx < C::TW + 2 && gy < p.H && gx < p.W;
+    int j = (ry - 2) * C::TW + (rx - 2);
+#pragma unroll
+    for (int f = 0; f < C::F; ++f) {
+      Proj pr = project_pixel(cam, p.P[f] + t.b * 12, p.g);
+      Taps tp = bilinear_taps(pr, p.W, p.H);
+      const float* img = p.src[f] + (size_t)t.b * 3 * HW + pr.y0 * p.W + pr.x0;
+      int dx = tp.x1ok ? 1 : 0, dy = tp.y1ok ? p.W : 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* q = img + c * HW;
+        float vnw = q[0], vne = q[dx], vsw = q[dy], vse = q[dy + dx];
+        X[(f * 3 + c) * C::RN + i] = bilinear_value(tp, vnw, vne, vsw, vse, p.g.arith);
+        if (interior) {
+          // grid_sampler_2d_backward's d out / d(ix, iy); zero where the border clip is active
+          float ddx = pr.inx ? ((vne - vnw) * tp.wy1 + (vse - vsw) * tp.wy0) : 0.f;
+          float ddy = pr.iny ? ((vsw - vnw) * tp.wx1 + (vse - vne) * tp.wx0) : 0.f;
+          G[(f * 6 + c) * C::IN + j] = ddx;
+          G[(f * 6 + 3 + c) * C::IN + j] = ddy;
+        }
+      }
+    }
+  }
+}
+
+// ---- phase: per-window losses, auto-mask arg-min, adjoint coefficients ---------------------------
+template <class C>
+VSL_HD void phase_windows(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid,
+                          ThreadState<C>& ts) {
+  const float* T = sm + C::oT;
+  const float* TS = sm + C::oTS;
+  const float* X = sm + C::oX;
+  const float* Id = sm + C::oId;
+  float* Coef = sm + C::oCoef;
+  int* Idx = reinterpret_cast<int*>(sm + C::oIdx);
+  const int HW = p.H * p.W;
+  const float kc = p.wpix * (0.85f / 3.0f) * (-0.5f) * (1.0f / 9.0f);
+  for (int i = tid; i < C::WN; i += C::NT) {
+    int wy = i / C::WW, wx = i - wy * C::WW;
+    int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
+    if (!(gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)) {
+      Idx[i] = -1;
+      continue;
+    }
+    // identity candidates first (trainer.py:659: cat(identity, reprojection)), ties keep the lower index
+    float best = INFINITY;
+    int bidx = -1;
+    const float* nz = p.noise[s] + (size_t)t.b * C::F * HW + gy * p.W + gx;
+#pragma unroll
+    for (int f = 0; f < C::F; ++f) {
+      float cand = add_rn(Id[f * C::WN + i], mul_rn(nz[f * HW], 1e-5f));
+      if (cand < best) { best = cand; bidx = f; }
+    }
+    float coef[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) coef[k] = 0.f;
+#pragma unroll
+    for (int f = 0; f < C::F; ++f) {
+      SsimOut so[3];
+      float l = reproj_window<C>(X + f * 3 * C::RN, T, TS, wy, wx, i, p.g.arith, so);
+      if (l < best) {
+        best = l;
+        bidx = C::F + f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float dmu, dexx, dexy;
+          ssim_r_grads(so[c], TS[c * C::WN + i], dmu, dexx, dexy);
+          float k = so[c].live ? kc : 0.f;
+          coef[c] = k * dmu;
+          coef[3 + c] = k * dexx;
+          coef[6 + c] = k * dexy;
+        }
+      }
+    }
+    bool warped = bidx >= C::F;
+    Idx[i] = warped ? bidx - C::F : -1;
+    if (warped) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Coef[k * C::WN + i] = coef[k];
+    }
+    bool interior = wy >= 1 && wy <= C::TH && wx >= 1 && wx <= C::TW;
+    if (interior) {
+      ts.loss += best;
+      if (p.mask[s]) p.mask[s][(size_t)t.b * HW + gy * p.W + gx] = warped ? 1.f : 0.f;
+    }
+  }
+}
+
+// ---- phase: adjoint for the interior pixels of scale s -------------------------------------------
+template <class C>
+VSL_HD void phase_backward(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid,
+                           ThreadState<C>& ts) {
+  const float* T = sm + C::oT;
+  const float* X = sm + C::oX;
+  const float* Coef = sm + C::oCoef;
+  const int* Idx = reinterpret_cast<const int*>(sm + C::oIdx);
+  const float* G = sm + C::oG;
+  const int HW = p.H * p.W;
+  const float* invK = p.invK + t.b * 16;
+  const float* disp = p.disp[s] + (size_t)t.b * p.hs[s] * p.ws[s];
+  const float kl1 = p.wpix * (0.15f / 3.0f);
+  for (int j = tid; j < C::IN; j += C::NT) {
+    int iy = j / C::TW, ix = j - iy * C::TW;
+    int gy = t.y0 + iy, gx = t.x0 + ix;
+    if (gy >= p.H || gx >= p.W) continue;
+    // masked 3x3 gather of the winners' coefficients; reflected border rows/cols count twice
+    float acc[C::F][9];
+#pragma unroll
+    for (int f = 0; f < C::F; ++f)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[f][k] = 0.f;
+    unsigned used = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      float cy = ((dy == -1 && gy == 1) || (dy == 1 && gy == p.H - 2)) ? 2.f : 1.f;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        float cx = ((dx == -1 && gx == 1) || (dx == 1 && gx == p.W - 2)) ? 2.f : 1.f;
+        int w = (iy + 1 + dy) * C::WW + (ix + 1 + dx);
+        int idx = Idx[w];
+        if (idx < 0) continue;
+        used |= 1u << idx;
+        float cnt = cy * cx;
+#pragma unroll
+        for (int f = 0; f < C::F; ++f)
+          if (idx == f) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[f][k] += cnt * Coef[k * C::WN + w];
+          }
+      }
+    }
+    float gz = 0.f;
+    Cam cam;
+    cam.z = 0.f;
+    if (used) {
+      float D = upsample_disp(disp, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s], p.identity_scale[s] != 0, gy,
+                              gx, p.g.arith);
+      cam = backproject_pixel(D, invK, gx, gy, p.g);
+      const int center = (iy + 2) * C::RW + (ix + 2);
+      const int own = Idx[(iy + 1) * C::WW + (ix + 1)];
+#pragma unroll
+      for (int f = 0; f < C::F; ++f) {
+        if (!(used & (1u << f))) continue;
+        float gix = 0.f, giy = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float xq = X[(f * 3 + c) * C::RN + center], yq = T[c * C::RN + center];
+          float g = acc[f][c] + 2.f * xq * acc[f][3 + c] + yq * acc[f][6 + c];
+          if (own == f) g += (xq > yq) ? kl1 : ((xq < yq) ? -kl1 : 0.f);
+          gix += g * G[(f * 6 + c) * C::IN + j];
+          giy += g * G[(f * 6 + 3 + c) * C::IN + j];
+        }
+        const float* P = p.P[f] + t.b * 12;
+        float c0 = P[0] * cam.X + P[1] * cam.Y + P[2] * cam.Z + P[3];
+        float c1 = P[4] * cam.X + P[5] * cam.Y + P[6] * cam.Z + P[7];
+        float c2 = P[8] * cam.X + P[9] * cam.Y + P[10] * cam.Z + P[11];
+        float iz = fast_rcp(c2 + p.g.eps);
+        float g0 = gix * iz, g1 = giy * iz;
+        float g2 = -(g0 * c0 + g1 * c1) * iz;
+        float* dP = ts.dP + f * 12;
+        dP[0] += g0 * cam.X; dP[1] += g0 * cam.Y; dP[2] += g0 * cam.Z; dP[3] += g0;
+        dP[4] += g1 * cam.X; dP[5] += g1 * cam.Y; dP[6] += g1 * cam.Z; dP[7] += g1;
+        dP[8] += g2 * cam.X; dP[9] += g2 * cam.Y; dP[10] += g2 * cam.Z; dP[11] += g2;
+        float gX = g0 * P[0] + g1 * P[4] + g2 * P[8];
+        float gY = g0 * P[1] + g1 * P[5] + g2 * P[9];
+        float gZ = g0 * P[2] + g1 * P[6] + g2 * P[10];
+        gz += gX * cam.rx + gY * cam.ry + gZ * cam.rz;
+      }
+    }
+    // z = 1/(min_disp + range*D)  ->  dz/dD = -range * z^2
+    p.gD[s][(size_t)t.b * HW + gy * p.W + gx] = -gz * p.g.disp_range * cam.z * cam.z;
+  }
+}
+
+// ---- bilinear up-sample adjoint: d/d disp_s from d/d(up-sampled disp) (trainer.py:500-501) -------
+// gather form for one coarse pixel (jy, jx) of a [hs, ws] level; gD: one full-res plane [H, W]
+VSL_HD float upsample_adjoint_pixel(const float* __restrict__ gD, int H, int W, int hs, int ws, float scale_h,
+                                    float scale_w, int jy, int jx) {
+  int ry = H / hs, rx = W / ws;  // integer ratios (levels are exact halvings)
+  int oy0 = jy * ry - ry / 2 - 1, oy1 = jy * ry + (3 * ry) / 2 + 1;
+  int ox0 = jx * rx - rx / 2 - 1, ox1 = jx * rx + (3 * rx) / 2 + 1;
+  if (oy0 < 0) oy0 = 0;
+  if (ox0 < 0) ox0 = 0;
+  if (oy1 > H) oy1 = H;
+  if (ox1 > W) ox1 = W;
+  float acc = 0.f;
+  for (int oy = oy0; oy < oy1; ++oy) {
+    UpsTap ty = ups_tap(oy, hs, scale_h);
+    float wy = (ty.i0 == jy ? ty.l0 : 0.f) + (ty.i1 == jy ? ty.l1 : 0.f);
+    if (wy == 0.f) continue;
+    float row = 0.f;
+    for (int ox = ox0; ox < ox1; ++ox) {
+      UpsTap tx = ups_tap(ox, ws, scale_w);
+      float wx = (tx.i0 == jx ? tx.l0 : 0.f) + (tx.i1 == jx ? tx.l1 : 0.f);
+      row += wx * gD[oy * W + ox];
+    }
+    acc += wy * row;
+  }
+  return acc;
+}
+
+}  // namespace vsl

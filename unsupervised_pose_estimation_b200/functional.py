@@ -1,0 +1,351 @@
+"""torch.autograd wrappers over the C ABI (include/vsl.h).  PyTorch is used for device memory,
+streams and autograd plumbing only; every arithmetic step runs in libvsl_b200.so.
+
+The functions refuse CPU tensors: there is no CPU implementation of this path in the product.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import VSL_MAX_SCALES, VSL_MAX_SRC, VslDesc, VslLossBuffers, check, ptr
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a tensor" % name)
+    if not t.is_cuda:
+        raise _lib.VslError(
+            "%s is on %s: the view-synthesis loss path only runs on CUDA (no CPU fallback)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# fused loss
+# --------------------------------------------------------------------------------------------------
+class FusedLossPlan:
+    """What Trainer.__init__ fixes once for the path (reference trainer.py:245-259): sizes, scales,
+    number of source frames, depth range, smoothness weight.  Owns the workspace; one call at a time
+    per plan (calls are stream-ordered)."""
+
+    def __init__(self, batch, height, width, scales, num_src, min_depth, max_depth,
+                 disparity_smoothness, flags=_lib.FLAG_AUTOMASK, arith=0):
+        scales = list(scales)
+        if not (1 <= len(scales) <= VSL_MAX_SCALES):
+            raise ValueError("1..%d scales supported" % VSL_MAX_SCALES)
+        if not (1 <= num_src <= VSL_MAX_SRC):
+            raise ValueError("1..%d source frames supported" % VSL_MAX_SRC)
+        self.batch, self.height, self.width = int(batch), int(height), int(width)
+        self.scales, self.num_src = scales, int(num_src)
+        d = VslDesc()
+        d.abi_version = _lib.VSL_ABI_VERSION
+        d.batch, d.height, d.width = self.batch, self.height, self.width
+        d.num_scales = len(scales)
+        for i, s in enumerate(scales):
+            d.scale_ids[i] = int(s)
+        d.num_src = self.num_src
+        d.flags = int(flags)
+        d.image_dtype = _lib.DTYPE_F32
+        d.arith = int(arith)
+        # Python-double scalars rounded to fp32 at the op, as PyTorch does (layers.py:90-93)
+        d.min_disp = float(np.float32(1.0 / max_depth))
+        d.disp_range = float(np.float32(1.0 / min_depth - 1.0 / max_depth))
+        d.eps = float(np.float32(1e-7))
+        d.smooth_weight = float(disparity_smoothness)
+        self.desc = d
+        self.lib = _lib.load()
+        self.ws_bytes = self.lib.vsl_loss_workspace_bytes(ctypes.byref(d))
+        if self.ws_bytes == 0:
+            raise _lib.VslError("invalid problem descriptor (sizes must be divisible by 2**scale)")
+        self._ws = {}
+        self.level_shapes = [(self.batch, 1, self.height >> s, self.width >> s) for s in scales]
+
+    def workspace(self, device):
+        ws = self._ws.get(device)
+        if ws is None:
+            ws = torch.empty(self.ws_bytes // 4, dtype=torch.float32, device=device)
+            self._ws[device] = ws
+        return ws
+
+
+class _FusedLoss(torch.autograd.Function):
+    """losses vector [2S+1] = (min_loss/s ..., loss/s ..., loss), masks...  <- disps, P matrices."""
+
+    @staticmethod
+    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, *leaves):
+        S, F = len(plan.scales), plan.num_src
+        disps, Ps = leaves[:S], leaves[S:]
+        dev = disps[0].device
+        B, H, W = plan.batch, plan.height, plan.width
+        buf = VslLossBuffers()
+        keep = []
+        for s in range(S):
+            t = _dev(targets[s], "target[%d]" % s)
+            d = _dev(disps[s], "disp[%d]" % s)
+            z = _dev(noise[s], "noise[%d]" % s)
+            if tuple(d.shape) != plan.level_shapes[s]:
+                raise ValueError("disp[%d] has shape %s, plan expects %s" % (s, tuple(d.shape), plan.level_shapes[s]))
+            if tuple(t.shape) != (B, 3, H >> plan.scales[s], W >> plan.scales[s]):
+                raise ValueError("target[%d] has shape %s" % (s, tuple(t.shape)))
+            if tuple(z.shape) != (B, F, H, W):
+                raise ValueError("noise[%d] has shape %s, expected %s" % (s, tuple(z.shape), (B, F, H, W)))
+            buf.target[s], buf.disp[s], buf.noise[s] = t.data_ptr(), d.data_ptr(), z.data_ptr()
+            keep += [t, d, z]
+        for f in range(F):
+            src = _dev(sources[f], "source[%d]" % f)
+            P = _dev(Ps[f], "P[%d]" % f)
+            if tuple(src.shape) != (B, 3, H, W) or tuple(P.shape) != (B, 3, 4):
+                raise ValueError("source/P[%d] have shapes %s / %s" % (f, tuple(src.shape), tuple(P.shape)))
+            buf.source[f], buf.P[f] = src.data_ptr(), P.data_ptr()
+            keep += [src, P]
+        iK = _dev(inv_K, "inv_K")
+        if tuple(iK.shape) != (B, 4, 4):
+            raise ValueError("inv_K has shape %s" % (tuple(iK.shape),))
+        buf.inv_K = iK.data_ptr()
+        keep.append(iK)
+
+        # one flat allocation for everything the backward keeps
+        n_levels = [B * (H >> s) * (W >> s) for s in plan.scales]
+        sizes = [3 * S + 1, S * F * B * 12] + n_levels + n_levels
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        parts = torch.split(flat, sizes)
+        losses, gradP = parts[0], parts[1]
+        gphoto, gsmooth = parts[2:2 + S], parts[2 + S:2 + 2 * S]
+        buf.losses, buf.grad_P = losses.data_ptr(), gradP.data_ptr()
+        masks = []
+        for s in range(S):
+            buf.grad_disp_photo[s] = gphoto[s].data_ptr()
+            buf.grad_disp_smooth[s] = gsmooth[s].data_ptr()
+            if want_mask:
+                m = torch.empty(B, H, W, dtype=torch.float32, device=dev)
+                buf.mask[s] = m.data_ptr()
+                masks.append(m)
+        ws = plan.workspace(dev)
+        check(plan.lib.vsl_loss_forward_backward(ctypes.byref(plan.desc), ctypes.byref(buf), ws.data_ptr(),
+                                                 plan.ws_bytes, _stream()), "vsl_loss_forward_backward")
+        ctx.plan, ctx.buf, ctx.flat, ctx.keep = plan, buf, flat, keep
+        ctx.mark_non_differentiable(*masks)
+        out = losses[:2 * S + 1]
+        ctx.smooth_terms = losses[2 * S + 1:]
+        return (out,) + tuple(masks)
+
+    @staticmethod
+    def backward(ctx, gvec, *_gmasks):
+        plan = ctx.plan
+        S, F, B = len(plan.scales), plan.num_src, plan.batch
+        dev = gvec.device
+        up = _dev(gvec, "upstream gradient")
+        n_levels = [int(np.prod(sh)) for sh in plan.level_shapes]
+        flat = torch.empty(sum(n_levels) + F * B * 12, dtype=torch.float32, device=dev)
+        parts = torch.split(flat, n_levels + [F * B * 12])
+        out_ptrs = (ctypes.c_void_p * VSL_MAX_SCALES)()
+        for s in range(S):
+            out_ptrs[s] = parts[s].data_ptr()
+        gP = parts[S]
+        check(plan.lib.vsl_loss_combine_grads(ctypes.byref(plan.desc), up.data_ptr(), ctypes.byref(ctx.buf),
+                                              ctypes.byref(out_ptrs), gP.data_ptr(), _stream()),
+              "vsl_loss_combine_grads")
+        gd = [parts[s].view(plan.level_shapes[s]) for s in range(S)]
+        gPs = [gP.view(F, B, 3, 4)[f] for f in range(F)]
+        return (None, None, None, None, None, None) + tuple(gd) + tuple(gPs)
+
+
+def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True):
+    """Run the fused path.  Returns (loss_vector[2S+1], [mask_s ...]).
+
+    loss_vector order: min_loss/s for every scale, loss/s for every scale, loss
+    (reference trainer.py:672-685).  Gradients flow to ``disps`` and ``Ps``.
+    """
+    res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise), bool(want_mask),
+                           *(list(disps) + list(Ps)))
+    return res[0], list(res[1:])
+
+
+def warp_side_outputs(plan, scale_index, disp, inv_K, Ps, sources, want_depth=True, want_sample=True,
+                      want_color=True):
+    """outputs[("depth",0,s)], [("sample",f,s)], [("color",f,s)] of trainer.py:500-537 for one scale
+    (non-differentiable: in the reference they feed the loss, here the fused kernel recomputes them)."""
+    B, H, W, F = plan.batch, plan.height, plan.width, plan.num_src
+    disp = _dev(disp.detach(), "disp")
+    dev = disp.device
+    iK = _dev(inv_K, "inv_K")
+    Pp = (ctypes.c_void_p * VSL_MAX_SRC)()
+    Sp = (ctypes.c_void_p * VSL_MAX_SRC)()
+    samp = (ctypes.c_void_p * VSL_MAX_SRC)()
+    colp = (ctypes.c_void_p * VSL_MAX_SRC)()
+    keep, samples, colors = [], [], []
+    for f in range(F):
+        P = _dev(Ps[f].detach(), "P")
+        src = _dev(sources[f], "source")
+        keep += [P, src]
+        Pp[f], Sp[f] = P.data_ptr(), src.data_ptr()
+        if want_sample:
+            samples.append(torch.empty(B, H, W, 2, dtype=torch.float32, device=dev))
+            samp[f] = samples[-1].data_ptr()
+        if want_color:
+            colors.append(torch.empty(B, 3, H, W, dtype=torch.float32, device=dev))
+            colp[f] = colors[-1].data_ptr()
+    depth = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev) if want_depth else None
+    check(plan.lib.vsl_warp_forward(ctypes.byref(plan.desc), scale_index, disp.data_ptr(), iK.data_ptr(),
+                                    ctypes.byref(Pp), ctypes.byref(Sp), ptr(depth), ctypes.byref(samp),
+                                    ctypes.byref(colp), _stream()), "vsl_warp_forward")
+    return depth, samples, colors
+
+
+# --------------------------------------------------------------------------------------------------
+# stand-alone layers
+# --------------------------------------------------------------------------------------------------
+class _Backproject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, inv_K, arith):
+        depth, inv_K = _dev(depth, "depth"), _dev(inv_K, "inv_K")
+        B, _, H, W = depth.shape
+        cam = torch.empty(B, 4, H * W, dtype=torch.float32, device=depth.device)
+        check(_lib.load().vsl_backproject_forward(B, H, W, arith, depth.data_ptr(), inv_K.data_ptr(),
+                                                  cam.data_ptr(), _stream()), "vsl_backproject_forward")
+        ctx.save_for_backward(inv_K)
+        ctx.shape = (B, H, W)
+        return cam
+
+    @staticmethod
+    def backward(ctx, g):
+        (inv_K,) = ctx.saved_tensors
+        B, H, W = ctx.shape
+        g = _dev(g, "grad")
+        gd = torch.empty(B, 1, H, W, dtype=torch.float32, device=g.device)
+        check(_lib.load().vsl_backproject_backward(B, H, W, g.data_ptr(), inv_K.data_ptr(), gd.data_ptr(),
+                                                   _stream()), "vsl_backproject_backward")
+        return gd, None, None
+
+
+def backproject(depth, inv_K, arith=0):
+    return _Backproject.apply(depth, inv_K, arith)
+
+
+class _Project(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, P, height, width, eps, arith):
+        points, P = _dev(points, "points"), _dev(P, "P")
+        B = points.shape[0]
+        pix = torch.empty(B, height, width, 2, dtype=torch.float32, device=points.device)
+        check(_lib.load().vsl_project_forward(B, height, width, eps, arith, points.data_ptr(), P.data_ptr(),
+                                              pix.data_ptr(), _stream()), "vsl_project_forward")
+        ctx.save_for_backward(points, P)
+        ctx.meta = (B, height, width, eps)
+        return pix
+
+    @staticmethod
+    def backward(ctx, g):
+        points, P = ctx.saved_tensors
+        B, H, W, eps = ctx.meta
+        lib = _lib.load()
+        g = _dev(g, "grad")
+        gpts = torch.empty_like(points)
+        gP = torch.empty_like(P)
+        nbytes = lib.vsl_project_workspace_bytes(B, H, W)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=g.device)
+        check(lib.vsl_project_backward(B, H, W, eps, points.data_ptr(), P.data_ptr(), g.data_ptr(),
+                                       gpts.data_ptr(), gP.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+              "vsl_project_backward")
+        return gpts, gP, None, None, None, None
+
+
+def project(points, P, height, width, eps=1e-7, arith=0):
+    return _Project.apply(points, P, height, width, float(np.float32(eps)), arith)
+
+
+class _Ssim(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = _dev(x, "x"), _dev(y, "y")
+        B, C, H, W = x.shape
+        out = torch.empty_like(x)
+        check(_lib.load().vsl_ssim_forward(B, C, H, W, x.data_ptr(), y.data_ptr(), out.data_ptr(), _stream()),
+              "vsl_ssim_forward")
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        B, C, H, W = x.shape
+        g = _dev(g, "grad")
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        check(_lib.load().vsl_ssim_backward(B, C, H, W, x.data_ptr(), y.data_ptr(), g.data_ptr(), ptr(gx), ptr(gy),
+                                            _stream()), "vsl_ssim_backward")
+        return gx, gy
+
+
+def ssim(x, y):
+    return _Ssim.apply(x, y)
+
+
+class _ReprojLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, no_ssim, arith):
+        pred, target = _dev(pred, "pred"), _dev(target, "target")
+        B, C, H, W = pred.shape
+        if C != 3:
+            raise ValueError("compute_reprojection_loss expects 3-channel images")
+        out = torch.empty(B, 1, H, W, dtype=torch.float32, device=pred.device)
+        check(_lib.load().vsl_reprojection_loss_forward(B, H, W, int(no_ssim), arith, pred.data_ptr(),
+                                                        target.data_ptr(), out.data_ptr(), _stream()),
+              "vsl_reprojection_loss_forward")
+        ctx.save_for_backward(pred, target)
+        ctx.no_ssim = int(no_ssim)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        B, _, H, W = pred.shape
+        g = _dev(g, "grad")
+        gp = torch.empty_like(pred) if ctx.needs_input_grad[0] else None
+        gt = torch.empty_like(target) if ctx.needs_input_grad[1] else None
+        check(_lib.load().vsl_reprojection_loss_backward(B, H, W, ctx.no_ssim, pred.data_ptr(), target.data_ptr(),
+                                                         g.data_ptr(), ptr(gp), ptr(gt), _stream()),
+              "vsl_reprojection_loss_backward")
+        return gp, gt, None, None
+
+
+def reprojection_loss(pred, target, no_ssim=False, arith=0):
+    return _ReprojLoss.apply(pred, target, no_ssim, arith)
+
+
+class _SmoothLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, img):
+        disp, img = _dev(disp, "disp"), _dev(img, "img")
+        B, _, H, W = disp.shape
+        lib = _lib.load()
+        nbytes = lib.vsl_smooth_workspace_bytes(B, H, W)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=disp.device)
+        loss = torch.empty((), dtype=torch.float32, device=disp.device)
+        check(lib.vsl_smooth_loss_forward(B, H, W, disp.data_ptr(), img.data_ptr(), loss.data_ptr(), ws.data_ptr(),
+                                          nbytes, _stream()), "vsl_smooth_loss_forward")
+        ctx.save_for_backward(disp, img)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        disp, img = ctx.saved_tensors
+        B, _, H, W = disp.shape
+        g = _dev(g, "grad")
+        gd = torch.empty_like(disp)
+        check(_lib.load().vsl_smooth_loss_backward(B, H, W, disp.data_ptr(), img.data_ptr(), g.data_ptr(),
+                                                   gd.data_ptr(), _stream()), "vsl_smooth_loss_backward")
+        return gd, None
+
+
+def smooth_loss(disp, img):
+    return _SmoothLoss.apply(disp, img)

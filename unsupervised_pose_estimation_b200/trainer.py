@@ -1,0 +1,161 @@
+"""Drop-in for the loss half of the reference ``Trainer`` (reference trainer.py:491-686).
+
+``ViewSynthesisLossMixin`` provides ``generate_images_pred``, ``compute_reprojection_loss`` and
+``compute_losses`` with the reference's signatures; a maintainer mixes it into the reference
+``Trainer``.  ``LossPath`` is the same thing stand-alone: it carries exactly the
+attributes those methods read (``opt``, ``device``, ``num_scales``), so tests and the benchmark can
+drive the path without the rest of the trainer.
+
+How the work is split (differs from the reference on purpose):
+  * ``compute_losses`` launches ONE fused forward+backward pass (libvsl_b200.so) that warps, scores,
+    auto-masks, reduces and produces the gradients w.r.t. every ``("disp", s)`` and every
+    ``P_f = (K @ T_f)[:, :3, :]``; autograd connects those to the depth and pose networks.
+  * ``generate_images_pred`` only has to provide the reference's *side outputs*
+    (``("depth",0,s)``, ``("sample",f,s)``, ``("color",f,s)``, ``("color_identity",f,s)``), which the
+    reference reads on logging steps only (wandb_logging.py:134-143).  ``vsl_side_outputs``:
+    ``"eager"`` (default, faithful: written every call by a small CUDA kernel), ``"none"`` (skip;
+    call ``materialize_side_outputs`` on logging steps).
+The tie-break noise is drawn with ``torch.randn`` in the reference's order (trainer.py:656-657), so
+the global RNG stream is consumed identically.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+
+from . import _lib
+from . import functional as VF
+
+
+def _unsupported(opt):
+    bad = []
+    if getattr(opt, "v1_multiscale", False):
+        bad.append("--v1_multiscale")
+    if getattr(opt, "avg_reprojection", False):
+        bad.append("--avg_reprojection")
+    if getattr(opt, "disable_automasking", False):
+        bad.append("--disable_automasking")
+    if getattr(opt, "predictive_mask", False):
+        bad.append("--predictive_mask")
+    if getattr(opt, "no_ssim", False):
+        bad.append("--no_ssim")
+    if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn":
+        bad.append("--pose_model_type posecnn")
+    if getattr(opt, "pre_trained_generator", False):
+        bad.append("--pre_trained_generator")
+    return bad
+
+
+class ViewSynthesisLossMixin:
+    """Methods of reference ``Trainer`` on the view-synthesis loss path, CUDA-backed."""
+
+    vsl_side_outputs = "eager"
+    vsl_arith = 0  # VSL_ARITH_* (0 = eager PyTorch-CUDA rounding order)
+
+    # -- plan ---------------------------------------------------------------------------------
+    def _vsl_plan(self):
+        opt = self.opt
+        key = (opt.batch_size, opt.height, opt.width, tuple(opt.scales), len(opt.frame_ids) - 1,
+               opt.min_depth, opt.max_depth, opt.disparity_smoothness, self.vsl_arith)
+        plan = getattr(self, "_vsl_plan_cache", None)
+        if plan is None or plan[0] != key:
+            bad = _unsupported(opt)
+            if bad:
+                raise NotImplementedError(
+                    "the CUDA view-synthesis path implements the reference's default loss "
+                    "(automask + per-pixel min + SSIM at full resolution); not yet: " + ", ".join(bad))
+            plan = (key, VF.FusedLossPlan(opt.batch_size, opt.height, opt.width, opt.scales,
+                                          len(opt.frame_ids) - 1, opt.min_depth, opt.max_depth,
+                                          opt.disparity_smoothness, arith=self.vsl_arith))
+            self._vsl_plan_cache = plan
+        return plan[1]
+
+    def _vsl_projections(self, inputs, outputs):
+        """P_f = (K @ T_f)[:, :3, :] per source frame (reference layers.py:254; T as trainer.py:510-513)."""
+        K = inputs[("K", 0)]
+        Ps = []
+        for frame_id in self.opt.frame_ids[1:]:
+            T = inputs["stereo_T"] if frame_id == "s" else outputs[("cam_T_cam", 0, frame_id)]
+            Ps.append(torch.matmul(K, T)[:, :3, :])
+        return Ps
+
+    # -- reference surface ----------------------------------------------------------------------
+    def generate_images_pred(self, inputs, outputs):
+        """Reference trainer.py:491-541.  See the module docstring for ``vsl_side_outputs``."""
+        self._vsl_plan()  # validates the options early, like the reference would fail early
+        if self.vsl_side_outputs == "eager":
+            self.materialize_side_outputs(inputs, outputs)
+        elif self.vsl_side_outputs != "none":
+            raise ValueError("vsl_side_outputs must be 'eager' or 'none'")
+
+    def materialize_side_outputs(self, inputs, outputs):
+        """Write ("depth",0,s), ("sample",f,s), ("color",f,s), ("color_identity",f,s) into ``outputs``."""
+        plan = self._vsl_plan()
+        with torch.no_grad():
+            Ps = self._vsl_projections(inputs, outputs)
+            sources = [inputs[("color", f, 0)] for f in self.opt.frame_ids[1:]]
+            for si, scale in enumerate(self.opt.scales):
+                depth, samples, colors = VF.warp_side_outputs(
+                    plan, si, outputs[("disp", scale)], inputs[("inv_K", 0)], Ps, sources)
+                outputs[("depth", 0, scale)] = depth
+                for fi, frame_id in enumerate(self.opt.frame_ids[1:]):
+                    outputs[("sample", frame_id, scale)] = samples[fi]
+                    outputs[("color", frame_id, scale)] = colors[fi]
+                    outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, 0)]
+
+    def compute_reprojection_loss(self, pred, target):
+        """Reference trainer.py:543-555: 0.85 * mean_c SSIM + 0.15 * mean_c L1 -> [B,1,H,W]."""
+        return VF.reprojection_loss(pred, target, no_ssim=bool(self.opt.no_ssim), arith=self.vsl_arith)
+
+    def compute_losses(self, inputs, outputs):
+        """Reference trainer.py:557-686: returns the loss dict, writes ``identity_selection/s``."""
+        opt = self.opt
+        plan = self._vsl_plan()
+        S, F = len(opt.scales), len(opt.frame_ids) - 1
+        targets = [inputs[("color", 0, s)] for s in opt.scales]
+        sources = [inputs[("color", f, 0)] for f in opt.frame_ids[1:]]
+        disps = [outputs[("disp", s)] for s in opt.scales]
+        Ps = self._vsl_projections(inputs, outputs)
+        dev = disps[0].device
+        # one draw per scale, same shape/order/device as trainer.py:656-657
+        noise = [torch.randn((opt.batch_size, F, opt.height, opt.width), device=dev) for _ in opt.scales]
+        vec, masks = VF.fused_loss(plan, targets, sources, disps, inputs[("inv_K", 0)], Ps, noise)
+        losses = {}
+        for si, scale in enumerate(opt.scales):
+            losses["min_loss/{}".format(scale)] = vec[si]
+            losses["loss/{}".format(scale)] = vec[S + si]
+            outputs["identity_selection/{}".format(scale)] = masks[si]
+        losses["loss"] = vec[2 * S]
+        return losses
+
+
+class LossPath(ViewSynthesisLossMixin):
+    """Stand-alone carrier of the path: ``LossPath(opt).generate_images_pred / compute_losses``.
+
+    ``opt`` needs the fields the reference methods read: height, width, batch_size, scales, frame_ids,
+    min_depth, max_depth, disparity_smoothness and the ablation flags (options.py:59-159).
+    """
+
+    def __init__(self, opt, device="cuda", side_outputs="eager", arith=0):
+        self.opt = opt
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.VslError("LossPath runs on CUDA only (the reference's --no_cuda path has no "
+                                "counterpart here; use the reference itself for CPU)")
+        self.num_scales = len(opt.scales)
+        self.vsl_side_outputs = side_outputs
+        self.vsl_arith = arith
+        _lib.load()
+
+
+def make_opt(**kw):
+    """Namespace with the reference's defaults for the fields the path reads (options.py)."""
+    opt = types.SimpleNamespace(
+        height=192, width=640, batch_size=12, scales=[0, 1, 2, 3], frame_ids=[0, -1, 1],
+        min_depth=0.1, max_depth=150.0, disparity_smoothness=1e-4,
+        v1_multiscale=False, avg_reprojection=False, disable_automasking=False, predictive_mask=False,
+        no_ssim=False, pose_model_type="separate_resnet", pre_trained_generator=False, no_cuda=False)
+    for k, v in kw.items():
+        setattr(opt, k, v)
+    return opt
