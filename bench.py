@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the view-synthesis loss path (BASELINE.json metric: target-pixels/s, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config C1] [--family smooth]
+
+One "step" = one pass of the hot path over one batch: generate_images_pred + compute_losses +
+backward to the leaves (disp_0..3, axisangle, translation) through the package's public API
+(unsupervised_pose_estimation_b200.trainer.LossPath).  `value` is measured with the inputs resident
+in HBM (a ring of input sets larger than L2 is cycled, so no step re-reads L2-warm inputs); `e2e`
+copies every step's inputs from pinned host memory and reads the loss dict back.  The `roofline`
+object times the dominant kernel (k_photometric) with CUDA events recorded by the library around its
+launch, inside the timed region.  `cpu_baseline` / `--impl reference` time the oracle port of the
+reference (oracle/vsl_oracle.py, test infrastructure) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from unsupervised_pose_estimation_b200 import synthetic  # noqa: E402
+
+METRIC = "view_synthesis_loss_target_pixels_per_s_fwd_bwd"
+UNIT = "px/s"
+
+
+def algorithmic_bytes_per_pixel(num_src, e_img=4):
+    """SURVEY.md §8d bytes_min per target pixel: target + F sources + target pyramid levels 1-3 +
+    disp pyramid read + disp-grad pyramid write."""
+    p = 1 + 0.25 + 1 / 16 + 1 / 64
+    return e_img * (3 + 3 * num_src + 3 * (p - 1)) + 4 * p + 4 * p
+
+
+def peak_hbm_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, reasons = [], set()
+        for line in self.tmp.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                out["sm_max_mhz"] = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        os.unlink(self.tmp.name)
+        return out
+
+
+def oracle_step_cpu(cfg, family, batch, threads):
+    """One forward+backward of the reference path on the host cores via the oracle port."""
+    from oracle import vsl_oracle as O
+    torch.set_num_threads(threads)
+    opt = O.make_opt(height=cfg["height"], width=cfg["width"], batch_size=batch, frame_ids=list(cfg["frame_ids"]))
+    inputs, outputs, leaves = synthetic.make_batch(batch, cfg["height"], cfg["width"], cfg["frame_ids"], cfg["K"],
+                                                   seed=0, family=family, device="cpu")
+
+    def run():
+        out = dict(outputs)
+        for f in cfg["frame_ids"][1:]:
+            if f != "s":
+                out[("cam_T_cam", 0, f)] = O.transformation_from_parameters(
+                    leaves[("axisangle", 0, f)][:, 0], leaves[("translation", 0, f)][:, 0], f < 0)
+        t0 = time.perf_counter()
+        losses = O.loss_step(opt, inputs, out)
+        torch.autograd.grad(losses["loss"], list(leaves.values()))
+        return time.perf_counter() - t0
+    return run
+
+
+def run_reference(args, cfg, rank):
+    """`--impl reference`: the reference's CPU path (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = cfg["batch"]
+    t_full = oracle_step_cpu(cfg, args.family, B, threads)()
+    budget = 150.0
+    b_s = max(1, min(B, int(B * budget / max(1e-6, (args.steps + args.warmup) * t_full))))
+    run = oracle_step_cpu(cfg, args.family, b_s, threads)
+    for _ in range(args.warmup):
+        run()
+    t = sum(run() for _ in range(args.steps))
+    px = b_s * cfg["height"] * cfg["width"] * args.steps
+    val = px / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d of %d images per step (%dx%d, %d source frames, 4 scales), fwd+bwd, %d steps"
+                                   % (b_s, B, cfg["width"], cfg["height"], len(cfg["frame_ids"]) - 1, args.steps)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, cfg):
+    return {"workload": "%s: %dx%d, batch %d per GPU, frames %s, 4 scales, fp32, %s synthetic frames"
+                        % (args.config, cfg["width"], cfg["height"], cfg["batch"], cfg["frame_ids"], args.family),
+            "l2": "ring of input sets larger than L2 (126 MB) cycled between timed steps",
+            "side_outputs": "none (fused path; reference side outputs are materialised on logging steps only)"}
+
+
+class Workload:
+    """A ring of device-resident input sets + the public-API step."""
+
+    def __init__(self, cfg, family, device, ring, pinned=False):
+        from unsupervised_pose_estimation_b200 import layers as L
+        from unsupervised_pose_estimation_b200.trainer import LossPath, make_opt
+        self.cfg, self.device, self.L = cfg, device, L
+        self.opt = make_opt(height=cfg["height"], width=cfg["width"], batch_size=cfg["batch"],
+                            frame_ids=list(cfg["frame_ids"]), max_depth=100.0, disparity_smoothness=1e-3)
+        self.path = LossPath(self.opt, device=device, side_outputs="none")
+        self.sets = []
+        self.host = []
+        for r in range(ring):
+            inputs, outputs, leaves = synthetic.make_batch(cfg["batch"], cfg["height"], cfg["width"], cfg["frame_ids"],
+                                                           cfg["K"], seed=r, family=family, device="cpu",
+                                                           requires_grad=False)
+            # only what the path reads
+            keep = {k: v for k, v in inputs.items()
+                    if k == "stereo_T" or k[0] in ("K", "inv_K") and k[1] == 0
+                    or (k[0] == "color" and (k[1] == 0 or k[2] == 0))}
+            host = {"inputs": keep, "leaves": leaves}
+            if pinned:
+                host = {"inputs": {k: v.pin_memory() for k, v in keep.items()},
+                        "leaves": {k: v.pin_memory() for k, v in leaves.items()}}
+                self.host.append(host)
+            if not pinned or r == 0:
+                self.sets.append({"inputs": {k: v.to(device) for k, v in keep.items()},
+                                  "leaves": {k: v.to(device).requires_grad_(True) for k, v in leaves.items()}})
+        self.h2d_bytes = sum(v.numel() * v.element_size() for h in [host] for d in h.values() for v in d.values())
+
+    def step(self, s):
+        inputs, leaves = s["inputs"], s["leaves"]
+        outputs = {k: v for k, v in leaves.items() if k[0] == "disp"}
+        for f in self.cfg["frame_ids"][1:]:
+            if f != "s":
+                outputs[("cam_T_cam", 0, f)] = self.L.transformation_from_parameters(
+                    leaves[("axisangle", 0, f)][:, 0], leaves[("translation", 0, f)][:, 0], f < 0)
+        self.path.generate_images_pred(inputs, outputs)
+        losses = self.path.compute_losses(inputs, outputs)
+        grads = torch.autograd.grad(losses["loss"], list(leaves.values()))
+        return losses, grads
+
+    def step_e2e(self, host, dev_set):
+        """Host buffers in, loss dict out: H2D of the step's inputs, the step, D2H of the losses."""
+        for k, v in host["inputs"].items():
+            dev_set["inputs"][k].copy_(v, non_blocking=True)
+        with torch.no_grad():
+            for k, v in host["leaves"].items():
+                dev_set["leaves"][k].copy_(v, non_blocking=True)
+        losses, _ = self.step(dev_set)
+        vec = torch.stack([losses[k] for k in sorted(losses)]).cpu()  # device->host read (synchronises)
+        return vec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C1", choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--family", default="smooth", choices=["smooth", "iid"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = dict(synthetic.CONFIGS[args.config])
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    from unsupervised_pose_estimation_b200 import functional as VF
+    B, H, W = cfg["batch"], cfg["height"], cfg["width"]
+    F = len(cfg["frame_ids"]) - 1
+    n0 = B * H * W
+    ring = 4  # 4 x ~79 MB of inputs (+ 47 MB of fresh tie-break noise per step) > 126 MB L2
+    wl = Workload(cfg, args.family, device, ring)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM --------------------------------------------------------
+    for i in range(args.warmup):
+        wl.step(wl.sets[i % ring])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    events = VF.KernelEvents()
+    wl.path._vsl_plan().kernel_events = events
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        wl.step(wl.sets[i % ring])
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = events.drain_ms()
+    wl.path._vsl_plan().kernel_events = None
+    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * n0 * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers in, loss dict out ---------------------------------------------------
+    wl_h = Workload(cfg, args.family, device, ring, pinned=True)
+    dev_set = wl_h.sets[0]
+    for i in range(3):
+        wl_h.step_e2e(wl_h.host[i % ring], dev_set)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        vec = wl_h.step_e2e(wl_h.host[i % ring], dev_set)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * n0 * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = peak_hbm_gbs()
+        kms = sum(kernel_ms) / max(1, len(kernel_ms))
+        alg_bytes = algorithmic_bytes_per_pixel(F) * n0
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, cfg),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": wl_h.h2d_bytes,
+                    "d2h_bytes_per_step": int(vec.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": 5 * args.steps,
+            "kernels_per_step": ["k_smooth_mean", "k_smooth_terms", "k_photometric", "k_epilogue", "k_combine"],
+            "host_wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_photometric", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "note": "fused kernel is FP32-issue bound (SURVEY.md 8d); see DESIGN.md"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            run = oracle_step_cpu(cfg, args.family, B, threads)
+            run()
+            ts = [run() for _ in range(3)]
+            line["cpu_baseline"] = {"value": n0 / min(ts), "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "3 full %s steps (batch %d) after 1 warm-up, best of 3, oracle port "
+                                              "of the reference on the host cores" % (args.config, B)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -117,6 +117,17 @@ size_t vsl_loss_workspace_bytes(const VslDesc* desc);
 int vsl_loss_forward_backward(const VslDesc* desc, const VslLossBuffers* buf,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same call, additionally recording two caller-owned CUDA events (cudaEvent_t as void*, either may
+ * be null) on `stream` immediately before and after the photometric kernel, so a benchmark can time
+ * the dominant kernel inside its own timed region.  Events come from vsl_event_create. */
+int vsl_loss_forward_backward_timed(const VslDesc* desc, const VslLossBuffers* buf,
+                                    void* workspace, size_t workspace_bytes, void* stream,
+                                    void* event_before, void* event_after);
+int vsl_event_create(void** event);
+int vsl_event_destroy(void* event);
+/* waits for `stop` to complete, then returns the time between the two records in milliseconds */
+int vsl_event_elapsed_ms(void* start, void* stop, float* ms);
+
 /* Chain rule from the loss dict to the leaves: `upstream` holds dL/d(losses[k]) on the DEVICE in
  * the order min_loss/0..S-1, loss/0..S-1, loss (2S+1 floats; trainer.py:672-685 defines how the
  * entries depend on each other).  Writes grad_disp[s] [B,1,H>>s,W>>s] and grad_P_out [F][B][12]. */

@@ -32,7 +32,8 @@ ARITH_MEAN_DIV = 1 << 6
 # every symbol include/vsl.h declares (tests check the shared object exports all of them)
 EXPORTED_SYMBOLS = [
     "vsl_abi_version", "vsl_status_string", "vsl_last_cuda_error",
-    "vsl_loss_workspace_bytes", "vsl_loss_forward_backward", "vsl_loss_combine_grads",
+    "vsl_loss_workspace_bytes", "vsl_loss_forward_backward", "vsl_loss_forward_backward_timed",
+    "vsl_event_create", "vsl_event_destroy", "vsl_event_elapsed_ms", "vsl_loss_combine_grads",
     "vsl_warp_forward",
     "vsl_backproject_forward", "vsl_backproject_backward",
     "vsl_project_forward", "vsl_project_workspace_bytes", "vsl_project_backward",
@@ -96,6 +97,10 @@ def load():
     lib.vsl_loss_workspace_bytes.restype = c_size_t
     lib.vsl_loss_workspace_bytes.argtypes = [POINTER(VslDesc)]
     lib.vsl_loss_forward_backward.argtypes = [POINTER(VslDesc), POINTER(VslLossBuffers), vp, c_size_t, vp]
+    lib.vsl_loss_forward_backward_timed.argtypes = [POINTER(VslDesc), POINTER(VslLossBuffers), vp, c_size_t, vp, vp, vp]
+    lib.vsl_event_create.argtypes = [POINTER(c_void_p)]
+    lib.vsl_event_destroy.argtypes = [vp]
+    lib.vsl_event_elapsed_ms.argtypes = [vp, vp, POINTER(c_float)]
     lib.vsl_loss_combine_grads.argtypes = [POINTER(VslDesc), vp, POINTER(VslLossBuffers),
                                            POINTER(c_void_p * VSL_MAX_SCALES), vp, vp]
     lib.vsl_warp_forward.argtypes = [POINTER(VslDesc), c_int, vp, vp, POINTER(c_void_p * VSL_MAX_SRC),

@@ -444,6 +444,30 @@ size_t vsl_loss_workspace_bytes(const VslDesc* desc) {
 
 int vsl_loss_forward_backward(const VslDesc* d, const VslLossBuffers* buf, void* workspace, size_t workspace_bytes,
                               void* stream) {
+  return vsl_loss_forward_backward_timed(d, buf, workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+int vsl_event_create(void** event) {
+  if (!event) return VSL_ERR_NULL_POINTER;
+  cudaEvent_t e;
+  VSL_CUDA_OK(cudaEventCreate(&e));
+  *event = (void*)e;
+  return VSL_OK;
+}
+int vsl_event_destroy(void* event) {
+  if (!event) return VSL_ERR_NULL_POINTER;
+  VSL_CUDA_OK(cudaEventDestroy((cudaEvent_t)event));
+  return VSL_OK;
+}
+int vsl_event_elapsed_ms(void* start, void* stop, float* ms) {
+  if (!start || !stop || !ms) return VSL_ERR_NULL_POINTER;
+  VSL_CUDA_OK(cudaEventSynchronize((cudaEvent_t)stop));
+  VSL_CUDA_OK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return VSL_OK;
+}
+
+int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf, void* workspace,
+                                    size_t workspace_bytes, void* stream, void* event_before, void* event_after) {
   if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
   if (!buf || !workspace) return VSL_ERR_NULL_POINTER;
   if (d->flags != VSL_FLAG_AUTOMASK) return VSL_ERR_UNSUPPORTED;   // default reference flags only
@@ -509,11 +533,13 @@ int vsl_loss_forward_backward(const VslDesc* d, const VslLossBuffers* buf, void*
   VSL_CUDA_OK(cudaGetLastError());
   k_smooth_terms<<<sgrid, kSmallNT, 0, st>>>(sp);
   VSL_CUDA_OK(cudaGetLastError());
+  if (event_before) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_before, st));
   int rc;
   if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256>>(pp, pl, d->batch, st);
   else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256>>(pp, pl, d->batch, st);
   else rc = launch_photometric<TileCfg<32, 16, 3, 256>>(pp, pl, d->batch, st);
   if (rc != VSL_OK) return rc;
+  if (event_after) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after, st));
   k_epilogue<<<sgrid, kSmallNT, 0, st>>>(sp);
   VSL_CUDA_OK(cudaGetLastError());
   return VSL_OK;

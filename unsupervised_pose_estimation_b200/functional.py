@@ -67,6 +67,7 @@ class FusedLossPlan:
         if self.ws_bytes == 0:
             raise _lib.VslError("invalid problem descriptor (sizes must be divisible by 2**scale)")
         self._ws = {}
+        self.kernel_events = None  # set to a KernelEvents() to time the photometric kernel per call
         self.level_shapes = [(self.batch, 1, self.height >> s, self.width >> s) for s in scales]
 
     def workspace(self, device):
@@ -75,6 +76,33 @@ class FusedLossPlan:
             ws = torch.empty(self.ws_bytes // 4, dtype=torch.float32, device=device)
             self._ws[device] = ws
         return ws
+
+
+class KernelEvents:
+    """CUDA event pairs recorded by the library around the photometric kernel (bench instrumentation)."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.pairs = []
+
+    def new_pair(self):
+        a, b = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self.lib.vsl_event_create(ctypes.byref(a)), "vsl_event_create")
+        check(self.lib.vsl_event_create(ctypes.byref(b)), "vsl_event_create")
+        self.pairs.append((a, b))
+        return a, b
+
+    def drain_ms(self):
+        """Elapsed ms of every recorded pair (waits for them); the pairs are destroyed."""
+        out = []
+        for a, b in self.pairs:
+            ms = ctypes.c_float()
+            check(self.lib.vsl_event_elapsed_ms(a, b, ctypes.byref(ms)), "vsl_event_elapsed_ms")
+            out.append(ms.value)
+            self.lib.vsl_event_destroy(a)
+            self.lib.vsl_event_destroy(b)
+        self.pairs = []
+        return out
 
 
 class _FusedLoss(torch.autograd.Function):
@@ -130,8 +158,10 @@ class _FusedLoss(torch.autograd.Function):
                 buf.mask[s] = m.data_ptr()
                 masks.append(m)
         ws = plan.workspace(dev)
-        check(plan.lib.vsl_loss_forward_backward(ctypes.byref(plan.desc), ctypes.byref(buf), ws.data_ptr(),
-                                                 plan.ws_bytes, _stream()), "vsl_loss_forward_backward")
+        ev = plan.kernel_events.new_pair() if plan.kernel_events is not None else (None, None)
+        check(plan.lib.vsl_loss_forward_backward_timed(ctypes.byref(plan.desc), ctypes.byref(buf), ws.data_ptr(),
+                                                       plan.ws_bytes, _stream(), ev[0], ev[1]),
+              "vsl_loss_forward_backward")
         ctx.plan, ctx.buf, ctx.flat, ctx.keep = plan, buf, flat, keep
         ctx.mark_non_differentiable(*masks)
         out = losses[:2 * S + 1]
