@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config C1] [--family smooth]
 
 One "step" = one pass of the hot path over one batch: generate_images_pred + compute_losses +
-backward to the leaves (disp_0..3, axisangle, translation) through the package's public API
+backward to the leaves (disp_0..3 and cam_T_cam per temporal frame) through the package's public API
 (unsupervised_pose_estimation_b200.trainer.LossPath).  `value` is measured with the inputs resident
 in HBM (a ring of input sets larger than L2 is cycled, so no step re-reads L2-warm inputs); `e2e`
 copies every step's inputs from pinned host memory and reads the loss dict back.  The `roofline`
@@ -172,6 +172,14 @@ class Workload:
             keep = {k: v for k, v in inputs.items()
                     if k == "stereo_T" or k[0] in ("K", "inv_K") and k[1] == 0
                     or (k[0] == "color" and (k[1] == 0 or k[2] == 0))}
+            # the path starts at outputs[("cam_T_cam",0,f)] (trainer.py:513): the pose network's
+            # axis-angle -> 4x4 conversion (predict_poses, trainer.py:437-438) is upstream of it
+            poses = {}
+            for f in cfg["frame_ids"][1:]:
+                if f != "s":
+                    poses[("cam_T_cam", 0, f)] = L.transformation_from_parameters(
+                        leaves.pop(("axisangle", 0, f))[:, 0], leaves.pop(("translation", 0, f))[:, 0], f < 0)
+            leaves.update(poses)
             host = {"inputs": keep, "leaves": leaves}
             if pinned:
                 host = {"inputs": {k: v.pin_memory() for k, v in keep.items()},
@@ -184,11 +192,7 @@ class Workload:
 
     def step(self, s):
         inputs, leaves = s["inputs"], s["leaves"]
-        outputs = {k: v for k, v in leaves.items() if k[0] == "disp"}
-        for f in self.cfg["frame_ids"][1:]:
-            if f != "s":
-                outputs[("cam_T_cam", 0, f)] = self.L.transformation_from_parameters(
-                    leaves[("axisangle", 0, f)][:, 0], leaves[("translation", 0, f)][:, 0], f < 0)
+        outputs = dict(leaves)  # ("disp", s) and ("cam_T_cam", 0, f)
         self.path.generate_images_pred(inputs, outputs)
         losses = self.path.compute_losses(inputs, outputs)
         grads = torch.autograd.grad(losses["loss"], list(leaves.values()))

@@ -72,7 +72,7 @@ def rot_from_axisangle(vec):
     xs, ys, zs = x * sa, y * sa, z * sa
     xC, yC, zC = x * C, y * C, z * C
     xyC, yzC, zxC = x * yC, y * zC, z * xC
-    rot = torch.zeros((vec.shape[0], 4, 4)).to(device=vec.device)
+    rot = torch.zeros((vec.shape[0], 4, 4), dtype=vec.dtype).to(device=vec.device)  # dtype: fp64 runs of the oracle
     entries = {
         (0, 0): x * xC + ca, (0, 1): xyC - zs, (0, 2): zxC + ys,
         (1, 0): xyC + zs, (1, 1): y * yC + ca, (1, 2): yzC - xs,
@@ -86,7 +86,7 @@ def rot_from_axisangle(vec):
 
 def get_translation_matrix(t):
     """layers.py:117-130 — [B,1,3] -> homogeneous translation [B,4,4]."""
-    T = torch.zeros(t.shape[0], 4, 4).to(device=t.device)
+    T = torch.zeros(t.shape[0], 4, 4, dtype=t.dtype).to(device=t.device)
     col = t.contiguous().view(-1, 3, 1)
     for i in range(4):
         T[:, i, i] = 1

@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA path (through the C ABI / ctypes host layer) against the oracle.
+
+The oracle (oracle/vsl_oracle.py) is run on the same GPU, where it IS the eager PyTorch-CUDA
+reference; integer / index-like results (sampling grid, bilinear tap indices, auto-mask) must be
+bit-exact, floating-point results within the tolerances written next to each assert
+(north_star: 1e-5 relative for losses and warped images; gradients are compared in rel-L2 and, because
+fp32 autograd itself is only that accurate, three-way against the fp64 oracle).
+Nothing here reads /root/reference: the committed goldens under tests/golden/ came from it.
+"""
+import ctypes
+
+import pytest
+import torch
+
+from helpers import golden_cases, load_golden
+from oracle import vsl_oracle as O
+from unsupervised_pose_estimation_b200 import _lib, synthetic
+from unsupervised_pose_estimation_b200 import functional as VF
+from unsupervised_pose_estimation_b200 import layers as L
+from unsupervised_pose_estimation_b200.trainer import LossPath, make_opt
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def with_poses(outputs, leaves, frame_ids, pose_fn):
+    out = dict(outputs)
+    for f in frame_ids[1:]:
+        if f != "s":
+            out[("cam_T_cam", 0, f)] = pose_fn(leaves[("axisangle", 0, f)][:, 0], leaves[("translation", 0, f)][:, 0], f < 0)
+    return out
+
+
+def run_oracle(opt, inputs, outputs, leaves, seed=123, dtype=torch.float32, noise=None):
+    if dtype != torch.float32:
+        inputs = {k: v.to(dtype) for k, v in inputs.items()}
+        leaves = {k: v.detach().to(dtype).requires_grad_(True) for k, v in leaves.items()}
+        outputs = dict(leaves)
+        noise = [z.to(dtype) for z in noise]
+    out = with_poses(outputs, leaves, opt.frame_ids, O.transformation_from_parameters)
+    O.generate_images_pred(opt, inputs, out)
+    torch.manual_seed(seed)
+    losses = O.compute_losses(opt, inputs, out, noise)
+    grads = torch.autograd.grad(losses["loss"], list(leaves.values()))
+    return out, losses, dict(zip(leaves.keys(), grads))
+
+
+def run_ours(opt, inputs, outputs, leaves, seed=123, side="eager"):
+    path = LossPath(make_opt(**vars(opt)), device=DEV, side_outputs=side)
+    out = with_poses(outputs, leaves, opt.frame_ids, L.transformation_from_parameters)
+    path.generate_images_pred(inputs, out)
+    torch.manual_seed(seed)
+    losses = path.compute_losses(inputs, out)
+    grads = torch.autograd.grad(losses["loss"], list(leaves.values()))
+    return out, losses, dict(zip(leaves.keys(), grads))
+
+
+def tap_indices(grid, H, W):
+    """grid_sample's north-west tap from a normalised grid (GridSampler.cuh:23-31, 55-57)."""
+    ix = ((grid[..., 0] + 1) / 2) * (W - 1)
+    iy = ((grid[..., 1] + 1) / 2) * (H - 1)
+    return torch.floor(ix.clamp(0, W - 1)).long(), torch.floor(iy.clamp(0, H - 1)).long()
+
+
+CASES = {
+    # name: B, H, W, frame_ids, K, family, seed, opt
+    "mono_iid_64x96": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "iid", 0, {}),
+    "mono_smooth_c1_b3": (3, 192, 640, [0, -1, 1], synthetic.K_KITTI, "smooth", 1, {}),
+    "mono_iid_c1_b2": (2, 192, 640, [0, -1, 1], synthetic.K_KITTI, "iid", 2, {}),
+    "scared_c2_b2": (2, 256, 320, [0, -1, 1], synthetic.K_SCARED, "smooth", 3,
+                     {"max_depth": 150.0, "disparity_smoothness": 1e-4}),
+    "stereo_c3_b2": (2, 192, 640, [0, -1, 1, "s"], synthetic.K_KITTI, "iid", 4, {}),
+    "stereo_only": (2, 64, 128, [0, "s"], synthetic.K_KITTI, "smooth", 5, {}),
+    "ragged_tiles_40x72": (3, 40, 72, [0, -1, 1], synthetic.K_LUNG, "iid", 6, {}),   # not a multiple of the 32x16 tile
+    "two_scales": (2, 64, 96, [0, 1], synthetic.K_KITTI, "smooth", 7, {"scales": [0, 2]}),
+    "single_scale": (1, 32, 64, [0, -1, 1], synthetic.K_KITTI, "iid", 8, {"scales": [0]}),
+}
+
+
+def build_case(name):
+    B, H, W, frames, K, family, seed, o = CASES[name]
+    opt = O.make_opt(height=H, width=W, batch_size=B, frame_ids=list(frames), **o)
+    inputs, outputs, leaves = synthetic.make_batch(B, H, W, frames, K, scales=tuple(range(4)), seed=seed,
+                                                   family=family, device=DEV)
+    return opt, inputs, outputs, leaves
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fused_path_matches_oracle(name):
+    opt, inputs, outputs, leaves = build_case(name)
+    H, W = opt.height, opt.width
+    ref_out, ref_losses, ref_g = run_oracle(opt, inputs, outputs, leaves)
+    out, losses, g = run_ours(opt, inputs, outputs, leaves)
+
+    for s in opt.scales:
+        # bit-exact: depth, sampling grid, tap indices, warped colours, auto-mask
+        assert torch.equal(out[("depth", 0, s)], ref_out[("depth", 0, s)]), ("depth", s)
+        for f in opt.frame_ids[1:]:
+            assert torch.equal(out[("sample", f, s)], ref_out[("sample", f, s)]), ("sample", f, s)
+            a, b = tap_indices(out[("sample", f, s)], H, W), tap_indices(ref_out[("sample", f, s)], H, W)
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+            assert torch.equal(out[("color", f, s)], ref_out[("color", f, s)]), ("color", f, s)
+            assert out[("color_identity", f, s)] is inputs[("color", f, 0)]
+        k = "identity_selection/%d" % s
+        assert torch.equal(out[k], ref_out[k]), k
+    assert set(losses) == set(ref_losses)
+    for k in ref_losses:  # 1e-6 relative (north_star asks 1e-5)
+        assert abs(losses[k].item() - ref_losses[k].item()) <= 1e-6 * abs(ref_losses[k].item()), k
+    for k in ref_g:  # rel-L2 of every input gradient
+        err = ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item()
+        assert err <= 5e-5, (k, err)
+
+
+@pytest.mark.parametrize("name", ["mono_smooth_c1_b3", "mono_iid_c1_b2", "stereo_c3_b2"])
+def test_gradients_three_way_against_fp64(name):
+    """Our fp32 gradients are as close to the fp64 oracle as the fp32 oracle's own (same discrete
+    decisions, so what is left is fp32 rounding of ill-conditioned sums)."""
+    opt, inputs, outputs, leaves = build_case(name)
+    torch.manual_seed(123)
+    F = len(opt.frame_ids) - 1
+    noise = [torch.randn(opt.batch_size, F, opt.height, opt.width, device=DEV) for _ in opt.scales]
+    _, _, g32 = run_oracle(opt, inputs, outputs, leaves, noise=noise)
+    _, _, g64 = run_oracle(opt, inputs, outputs, leaves, dtype=torch.float64, noise=noise)
+    _, _, g = run_ours(opt, inputs, outputs, leaves)  # seed 123 -> identical noise draw
+    for k in g:
+        ref = g64[k]
+        e_ours = ((g[k].double() - ref).norm() / ref.norm()).item()
+        e_o32 = ((g32[k].double() - ref).norm() / ref.norm()).item()
+        assert e_ours <= 1.5 * e_o32 + 1e-6, (k, e_ours, e_o32)
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_golden_fixtures(case):
+    """Committed reference outputs (made on CPU by tests/golden/make_golden.py).  CPU and CUDA PyTorch
+    round a few ops differently, so discrete outputs may differ on ~1e-4 of the pixels."""
+    g = load_golden(case, device=DEV)
+    opt = g["opt"]
+    leaves = {k: v.clone().requires_grad_(True) for k, v in g["leaves"].items()}
+    S, F = len(opt.scales), len(opt.frame_ids) - 1
+    plan = VF.FusedLossPlan(opt.batch_size, opt.height, opt.width, opt.scales, F, opt.min_depth, opt.max_depth,
+                            opt.disparity_smoothness)
+    K = g["inputs"][("K", 0)]
+    Ps = []
+    for f in opt.frame_ids[1:]:
+        T = g["inputs"]["stereo_T"] if f == "s" else L.transformation_from_parameters(
+            leaves[("axisangle", 0, f)][:, 0], leaves[("translation", 0, f)][:, 0], f < 0)
+        Ps.append(torch.matmul(K, T)[:, :3, :])
+    vec, masks = VF.fused_loss(plan, [g["inputs"][("color", 0, s)] for s in opt.scales],
+                               [g["inputs"][("color", f, 0)] for f in opt.frame_ids[1:]],
+                               [leaves[("disp", s)] for s in opt.scales], g["inputs"][("inv_K", 0)], Ps, g["noise"])
+    grads = torch.autograd.grad(vec[2 * S], list(leaves.values()))
+    for si, s in enumerate(opt.scales):
+        for key, got in (("min_loss/%d" % s, vec[si]), ("loss/%d" % s, vec[S + si])):
+            assert abs(got.item() - g["losses"][key].item()) <= 1e-5 * abs(g["losses"][key].item()), key
+        mism = (masks[si] != g["outputs"]["identity_selection/%d" % s]).float().mean().item()
+        assert mism <= 5e-4, (s, mism)
+    assert abs(vec[2 * S].item() - g["losses"]["loss"].item()) <= 1e-5 * g["losses"]["loss"].item()
+    for (k, ref), got in zip(g["grads"].items(), grads):
+        assert list(g["grads"].keys()) == list(leaves.keys())
+        err = ((got - ref).norm() / ref.norm()).item()
+        assert err <= 2e-2, (k, err)  # flips of ~1e-4 of the arg-min / floor decisions move the gradient by ~1 %
+
+
+def test_rng_stream_is_consumed_like_the_reference():
+    opt, inputs, outputs, leaves = build_case("mono_iid_64x96")
+    run_oracle(opt, inputs, outputs, leaves, seed=7)
+    a = torch.randn(8, device=DEV)
+    run_ours(opt, inputs, outputs, leaves, seed=7)
+    b = torch.randn(8, device=DEV)
+    assert torch.equal(a, b)
+
+
+def test_full_size_properties_c1():
+    """BASELINE config 1 at full size (B=12, 640x192): parity plus size-independent properties."""
+    cfg = synthetic.CONFIGS["C1"]
+    opt = O.make_opt(height=cfg["height"], width=cfg["width"], batch_size=cfg["batch"], frame_ids=list(cfg["frame_ids"]))
+    inputs, outputs, leaves = synthetic.make_config("C1", seed=11, family="smooth", device=DEV)
+    S = len(opt.scales)
+    out1, l1, g1 = run_ours(opt, inputs, outputs, leaves, side="none")
+    out2, l2, g2 = run_ours(opt, inputs, outputs, leaves, side="none")
+    for k in l1:  # deterministic: two runs agree bit for bit
+        assert torch.equal(l1[k], l2[k]), k
+    for k in g1:
+        assert torch.equal(g1[k], g2[k]), k
+        assert torch.isfinite(g1[k]).all()
+    for s in opt.scales:
+        m = out1["identity_selection/%d" % s]
+        assert torch.equal(m, out2["identity_selection/%d" % s])
+        assert ((m == 0) | (m == 1)).all() and 0.0 < m.mean().item() < 1.0
+    assert ("color", -1, 0) not in out1  # side outputs are skipped in "none" mode
+    total = sum(l1["loss/%d" % s] for s in opt.scales) / S
+    assert abs(total.item() - l1["loss"].item()) <= 1e-6 * l1["loss"].item()
+    ref_out, ref_l, ref_g = run_oracle(opt, inputs, outputs, leaves)
+    for k in ref_l:
+        assert abs(l1[k].item() - ref_l[k].item()) <= 1e-6 * abs(ref_l[k].item()), k
+    for s in opt.scales:
+        assert torch.equal(out1["identity_selection/%d" % s], ref_out["identity_selection/%d" % s])
+    for k in ref_g:
+        assert ((g1[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
+
+
+def test_backward_is_linear_in_the_upstream_gradient():
+    """Every entry of the loss dict is differentiable (trainer.py:672-685), not just losses['loss']."""
+    opt, inputs, outputs, leaves = build_case("mono_iid_64x96")
+    keys = list(leaves.keys())
+
+    def grads_of(fn_ours, combo):
+        path_out = with_poses(outputs, leaves, opt.frame_ids,
+                              L.transformation_from_parameters if fn_ours else O.transformation_from_parameters)
+        torch.manual_seed(5)
+        if fn_ours:
+            losses = LossPath(make_opt(**vars(opt)), device=DEV, side_outputs="none").compute_losses(inputs, path_out)
+        else:
+            O.generate_images_pred(opt, inputs, path_out)
+            losses = O.compute_losses(opt, inputs, path_out)
+        obj = sum(w * losses[k] for k, w in combo.items())
+        return torch.autograd.grad(obj, [leaves[k] for k in keys], allow_unused=True)
+
+    combo = {"min_loss/0": 0.7, "loss/2": -1.3, "loss": 2.0, "loss/3": 0.25}
+    for a, b, k in zip(grads_of(True, combo), grads_of(False, combo), keys):
+        assert ((a - b).norm() / b.norm()).item() <= 5e-5, k
+    only0 = grads_of(True, {"min_loss/1": 1.0})
+    for gr, k in zip(only0, keys):
+        if k[0] == "disp" and k[1] != 1:
+            assert gr is None or float(gr.abs().max()) == 0.0, k
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone layers (the layers.py surface)
+# ------------------------------------------------------------------------------------------------
+def test_backproject_project_layers():
+    B, H, W = 3, 48, 80
+    gen = torch.Generator().manual_seed(0)
+    depth = (0.1 + 5 * torch.rand(B, 1, H, W, generator=gen)).to(DEV).requires_grad_(True)
+    intr = synthetic.scaled_intrinsics(synthetic.K_KITTI, H, W, 1, B)
+    K, inv_K = intr[("K", 0)].to(DEV), intr[("inv_K", 0)].to(DEV)
+    aa = (0.01 * torch.randn(B, 1, 3, generator=gen)).to(DEV).requires_grad_(True)
+    tr = (0.01 * torch.randn(B, 1, 3, generator=gen)).to(DEV).requires_grad_(True)
+
+    def chain(bp, pj, pose):
+        T = pose(aa, tr, True)
+        cam = bp(depth, inv_K)
+        pix = pj(cam, K, T)
+        w = torch.linspace(0.5, 1.5, pix.numel(), device=DEV).view_as(pix)
+        return cam, pix, torch.autograd.grad((pix * w).sum(), [depth, aa, tr])
+
+    cam, pix, g = chain(L.BackprojectDepth(B, H, W).to(DEV), L.Project3D(B, H, W).to(DEV), L.transformation_from_parameters)
+    rcam, rpix, rg = chain(O.backproject, lambda c, k, t: O.project(c, k, t, H, W), O.transformation_from_parameters)
+    assert torch.equal(cam, rcam) and torch.equal(pix, rpix)  # bit-exact forward
+    for a, b in zip(g, rg):
+        assert ((a - b).norm() / b.norm()).item() <= 2e-5
+    with pytest.raises(RuntimeError):
+        L.BackprojectDepth(B, H, W + 1)(depth, inv_K)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 33, 47), (1, 1, 2, 2), (2, 3, 192, 640)])
+def test_ssim_layer(shape):
+    gen = torch.Generator().manual_seed(1)
+    x = torch.rand(*shape, generator=gen).to(DEV).requires_grad_(True)
+    y = torch.rand(*shape, generator=gen).to(DEV).requires_grad_(True)
+    w = torch.rand(*shape, generator=gen).to(DEV)
+    out, ref = L.SSIM().to(DEV)(x, y), O.ssim(x, y)
+    assert torch.equal(out, ref)
+    g = torch.autograd.grad((out * w).sum(), [x, y])
+    rg = torch.autograd.grad((ref * w).sum(), [x, y])
+    for a, b in zip(g, rg):
+        assert ((a - b).norm() / b.norm()).item() <= 2e-5
+
+
+@pytest.mark.parametrize("no_ssim", [False, True])
+def test_compute_reprojection_loss(no_ssim):
+    gen = torch.Generator().manual_seed(2)
+    pred = torch.rand(2, 3, 64, 96, generator=gen).to(DEV).requires_grad_(True)
+    tgt = torch.rand(2, 3, 64, 96, generator=gen).to(DEV).requires_grad_(True)
+    path = LossPath(make_opt(no_ssim=no_ssim), device=DEV)
+    out, ref = path.compute_reprojection_loss(pred, tgt), O.reprojection_loss(pred, tgt, no_ssim)
+    assert out.shape == (2, 1, 64, 96) and torch.equal(out, ref)
+    w = torch.rand(2, 1, 64, 96, generator=gen).to(DEV)
+    g = torch.autograd.grad((out * w).sum(), [pred, tgt])
+    rg = torch.autograd.grad((ref * w).sum(), [pred, tgt])
+    for a, b in zip(g, rg):
+        assert ((a - b).norm() / b.norm()).item() <= 2e-5
+
+
+def test_get_smooth_loss():
+    gen = torch.Generator().manual_seed(3)
+    disp = torch.rand(3, 1, 24, 40, generator=gen).to(DEV).requires_grad_(True)
+    img = torch.rand(3, 3, 24, 40, generator=gen).to(DEV)
+    out, ref = L.get_smooth_loss(disp, img), O.smooth_loss(disp, img)
+    assert out.dim() == 0 and abs(out.item() - ref.item()) <= 1e-6 * ref.item()
+    (g,), (rg,) = torch.autograd.grad(out * 3.0, [disp]), torch.autograd.grad(ref * 3.0, [disp])
+    assert ((g - rg).norm() / rg.norm()).item() <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# error behaviour
+# ------------------------------------------------------------------------------------------------
+def test_errors_are_loud():
+    opt, inputs, outputs, leaves = build_case("mono_iid_64x96")
+    path = LossPath(make_opt(**vars(opt)), device=DEV, side_outputs="none")
+    out = with_poses(outputs, leaves, opt.frame_ids, L.transformation_from_parameters)
+    bad = dict(out)
+    bad[("disp", 1)] = out[("disp", 0)]  # wrong pyramid size
+    with pytest.raises(ValueError):
+        path.compute_losses(inputs, bad)
+    cpu_inputs = dict(inputs)
+    cpu_inputs[("color", 0, 0)] = inputs[("color", 0, 0)].cpu()
+    with pytest.raises(_lib.VslError):
+        path.compute_losses(cpu_inputs, out)
+    with pytest.raises(NotImplementedError):
+        LossPath(make_opt(avg_reprojection=True), device=DEV).generate_images_pred(inputs, out)
+    lib = _lib.load()
+    d = _lib.VslDesc()
+    assert lib.vsl_loss_forward_backward(ctypes.byref(d), None, None, 0, None) == -1

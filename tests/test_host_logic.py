@@ -1,0 +1,66 @@
+"""Host-side logic that needs no GPU: synthetic factory, pose helpers, option gating, bench model."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+from oracle import vsl_oracle as O
+from unsupervised_pose_estimation_b200 import layers as L
+from unsupervised_pose_estimation_b200 import synthetic
+from unsupervised_pose_estimation_b200.trainer import ViewSynthesisLossMixin, make_opt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_synthetic_is_deterministic_and_well_formed():
+    a = synthetic.make_batch(2, 32, 64, [0, -1, 1, "s"], seed=5)
+    b = synthetic.make_batch(2, 32, 64, [0, -1, 1, "s"], seed=5)
+    for k in a[0]:
+        assert torch.equal(a[0][k], b[0][k])
+    for k in a[2]:
+        assert torch.equal(a[2][k], b[2][k])
+    inputs = a[0]
+    assert inputs[("color", "s", 2)].shape == (2, 3, 8, 16)
+    assert inputs[("K", 1)][0, 0, 0].item() == pytest.approx(0.58 * 32)
+    assert torch.allclose(inputs[("K", 0)][0] @ inputs[("inv_K", 0)][0], torch.eye(4), atol=1e-5)
+    assert inputs["stereo_T"][0, 0, 3].item() == pytest.approx(0.1)
+
+
+@pytest.mark.parametrize("invert", [False, True])
+def test_pose_helpers_match_oracle(invert):
+    g = torch.Generator().manual_seed(0)
+    aa, tr = 0.01 * torch.randn(5, 1, 3, generator=g), 0.01 * torch.randn(5, 1, 3, generator=g)
+    assert torch.equal(L.transformation_from_parameters(aa, tr, invert), O.transformation_from_parameters(aa, tr, invert))
+    d = torch.rand(2, 1, 4, 4, generator=g)
+    for a, b in zip(L.disp_to_depth(d, 0.1, 100), O.disp_to_depth(d, 0.1, 100)):
+        assert torch.equal(a, b)
+
+
+def test_layers_reexports_reference_names():
+    for name in ["SLlog", "RMSE_log", "depth_to_disp", "disp_to_depth", "transformation_from_parameters",
+                 "get_translation_matrix", "rot_from_axisangle", "ConvBlock", "batchNorm", "Conv3x3",
+                 "BackprojectDepth", "Project3D", "upsample", "deconv", "get_smooth_loss", "SSIM",
+                 "compute_depth_errors"]:
+        assert hasattr(L, name), name
+    assert L.BackprojectDepth(2, 4, 6).batch_size == 2 and L.Project3D(2, 4, 6).eps == 1e-7
+    x = torch.rand(1, 3, 8, 8)
+    assert L.ConvBlock(3, 4)(x).shape == (1, 4, 8, 8) and L.upsample(x).shape == (1, 3, 16, 16)
+
+
+@pytest.mark.parametrize("flag", ["v1_multiscale", "avg_reprojection", "disable_automasking", "predictive_mask", "no_ssim"])
+def test_unsupported_flags_fail_loudly(flag):
+    class P(ViewSynthesisLossMixin):
+        pass
+    p = P()
+    p.opt = make_opt(**{flag: True})
+    with pytest.raises(NotImplementedError):
+        p._vsl_plan()
+
+
+def test_bench_byte_model():
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.algorithmic_bytes_per_pixel(2) == pytest.approx(50.5625)
+    assert bench.algorithmic_bytes_per_pixel(3, 2) == pytest.approx(36.59375)  # C3, bf16 images

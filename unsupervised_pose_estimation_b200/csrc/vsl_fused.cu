@@ -4,7 +4,8 @@
 //   k_smooth_mean   per-image mean of disp_s                     (trainer.py:676)
 //   k_smooth_terms  edge-aware smoothness terms + d/d(norm disp)  (layers.py:286-299)
 //   k_photometric   warp + SSIM/L1 + automask min + adjoint       (trainer.py:491-674)  <- the hot kernel
-//   k_epilogue      up-sample adjoint, smoothness chain rule, deterministic reductions, loss dict
+//   k_upsample_adjoint  d/d disp_s from d/d(up-sampled disp_s), s >= 1   (trainer.py:500-501)
+//   k_epilogue      smoothness chain rule, deterministic reductions, loss dict
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -194,6 +195,38 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Adjoint of F.interpolate(disp_s, [H,W], bilinear, align_corners=False) (trainer.py:500-501):
+// d/d disp_s[jy,jx] = sum over the 2r x 2r fine pixels whose bilinear footprint touches (jy,jx).
+// 2r lanes cooperate on one coarse pixel (one fine column each, coalesced), then a sub-warp shuffle sum.
+__global__ void __launch_bounds__(kSmallNT) k_upsample_adjoint(const SmallParams p) {
+  const int s = blockIdx.z, b = blockIdx.y;
+  if (p.identity_scale[s]) return;
+  const int h = p.hs[s], w = p.ws[s], r = p.H / h, L = 2 * r;  // L in {4, 8, 16}
+  const int gid = blockIdx.x * kSmallNT + threadIdx.x;
+  const int cp = gid / L, lane = gid - cp * L;
+  if (blockIdx.x * kSmallNT >= h * w * L) return;  // whole block past the level (uniform)
+  const bool live = cp < h * w;
+  const int jy = live ? cp / w : 0, jx = live ? cp - (cp / w) * w : 0;
+  const int ox = jx * r - r / 2 + lane;
+  float acc = 0.f;
+  if (live && ox >= 0 && ox < p.W) {
+    UpsTap tx = ups_tap(ox, w, p.scale_w[s]);
+    float wx = (tx.i0 == jx ? tx.l0 : 0.f) + (tx.i1 == jx ? tx.l1 : 0.f);
+    const float* gD = p.gD[s] + (size_t)b * p.H * p.W + ox;
+    for (int t = 0; t < L; ++t) {
+      int oy = jy * r - r / 2 + t;
+      if (oy < 0 || oy >= p.H) continue;
+      UpsTap ty = ups_tap(oy, h, p.scale_h[s]);
+      float wy = (ty.i0 == jy ? ty.l0 : 0.f) + (ty.i1 == jy ? ty.l1 : 0.f);
+      acc += wy * gD[(size_t)oy * p.W];
+    }
+    acc *= wx;
+  }
+  for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (live && lane == 0) p.gphoto[s][(size_t)b * h * w + cp] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
   __shared__ float scratch[kSmallNT / 32];
   __shared__ bool is_last;
@@ -208,12 +241,8 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
     gd = block_sum<kSmallNT>(gd, scratch);
     float corr = gd * inv * inv / (float)n;
     float* gs = p.gsmooth[s] + (size_t)b * n;
-    float* gp = p.gphoto[s] + (size_t)b * n;
-    const float* gD = p.identity_scale[s] ? nullptr : p.gD[s] + (size_t)b * p.H * p.W;
-    for (int i = chunk * kChunk + threadIdx.x; i < min(n, (chunk + 1) * kChunk); i += kSmallNT) {
+    for (int i = chunk * kChunk + threadIdx.x; i < min(n, (chunk + 1) * kChunk); i += kSmallNT)
       gs[i] = gs[i] * inv - corr;
-      if (gD) gp[i] = upsample_adjoint_pixel(gD, p.H, p.W, h, w, p.scale_h[s], p.scale_w[s], i / w, i % w);
-    }
     if (chunk == 0) {
       // photometric partials of image b, scale s: loss sum and dP, tiles in a fixed order
       const float* base = p.partials + ((size_t)b * p.tiles_per_image * p.S + s) * p.kpartial;
@@ -357,7 +386,7 @@ static bool desc_ok(const VslDesc* d) {
   if (d->num_src < 1 || d->num_src > VSL_MAX_SRC) return false;
   for (int s = 0; s < d->num_scales; ++s) {
     int e = d->scale_ids[s];
-    if (e < 0 || e > 8) return false;
+    if (e < 0 || e > 3) return false;  // up-sample adjoint uses 2*2^e <= 16 lanes per coarse pixel
     if ((d->height >> e) < 2 || (d->width >> e) < 2) return false;
     if (((d->height >> e) << e) != d->height || ((d->width >> e) << e) != d->width) return false;
   }
@@ -540,6 +569,15 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   else rc = launch_photometric<TileCfg<32, 16, 3, 256>>(pp, pl, d->batch, st);
   if (rc != VSL_OK) return rc;
   if (event_after) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after, st));
+  {
+    bool any = false;
+    for (int s = 0; s < S; ++s) any |= d->scale_ids[s] != 0;
+    if (any) {  // every non-identity level has H*W lanes of work per image (2r lanes per coarse pixel)
+      dim3 agrid((d->height * d->width + kSmallNT - 1) / kSmallNT, d->batch, S);
+      k_upsample_adjoint<<<agrid, kSmallNT, 0, st>>>(sp);
+      VSL_CUDA_OK(cudaGetLastError());
+    }
+  }
   k_epilogue<<<sgrid, kSmallNT, 0, st>>>(sp);
   VSL_CUDA_OK(cudaGetLastError());
   return VSL_OK;
