@@ -59,7 +59,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
@@ -213,8 +213,8 @@ class Workload:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C1", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--family", default="smooth", choices=["smooth", "iid"])

@@ -59,12 +59,14 @@ enum { VSL_DTYPE_F32 = 0, VSL_DTYPE_BF16 = 1 };
  * `x /= (W-1)` (a true division; CUDA multiplies by the rounded reciprocal).             */
 enum {
   VSL_ARITH_TRUE_DIV = 1 << 0,
-  VSL_ARITH_DOT_NOFMA = 1 << 1,    /* probe: un-fused dot products in bmm                   */
-  VSL_ARITH_DOT_REVERSE = 1 << 2,  /* probe: k-descending accumulation in bmm               */
+  VSL_ARITH_DOT_NOFMA = 1 << 1,    /* K=4 bmm (projection) adds un-fused products: cuBLAS, batch 1 */
+  VSL_ARITH_DOT_REVERSE = 1 << 2,  /* probe: k-descending accumulation in the K=4 bmm       */
   VSL_ARITH_UPS_RIGHT = 1 << 3,    /* probe: up-sample fuses the right-hand product         */
   VSL_ARITH_UPS_NOFMA = 1 << 4,    /* probe: up-sample without FMA contraction              */
   VSL_ARITH_TAP_NOFMA = 1 << 5,    /* probe: bilinear tap accumulation without FMA          */
-  VSL_ARITH_MEAN_DIV = 1 << 6      /* probe: channel mean as sum/3 instead of sum*(1/3)     */
+  VSL_ARITH_MEAN_DIV = 1 << 6,     /* probe: channel mean as sum/3 instead of sum*(1/3)     */
+  VSL_ARITH_DOT3_NOFMA = 1 << 7,   /* K=3 bmm (rays) adds un-fused products: cuBLAS, batch 1 */
+  VSL_ARITH_DOT3_REVERSE = 1 << 8  /* probe: k-descending accumulation in the K=3 bmm       */
 };
 
 /* Problem descriptor: what Trainer.__init__ fixes once (trainer.py:245-259, options.py). */
@@ -145,6 +147,11 @@ int vsl_warp_forward(const VslDesc* desc, int scale_index, const float* disp, co
                      const float* const P[VSL_MAX_SRC], const void* const source[VSL_MAX_SRC],
                      float* depth, float* const sample[VSL_MAX_SRC], float* const color[VSL_MAX_SRC],
                      void* stream);
+
+/* Calibration helper: out[b,i,n] = sum_k A[b,i,k] * X[b,k,n] (A [B,3,k], X [B,k,n], k = 3 or 4) with
+ * the accumulation order `arith` selects, so the host layer can find which order torch.bmm (cuBLAS)
+ * uses for a shape on this device.  Not used on the hot path. */
+int vsl_probe_bmm(int batch, int k, int n, int arith, const float* A, const float* X, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Stand-alone layers (the layers.py call surface).  fp32 only.

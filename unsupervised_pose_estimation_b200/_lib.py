@@ -28,13 +28,15 @@ ARITH_UPS_RIGHT = 1 << 3
 ARITH_UPS_NOFMA = 1 << 4
 ARITH_TAP_NOFMA = 1 << 5
 ARITH_MEAN_DIV = 1 << 6
+ARITH_DOT3_NOFMA = 1 << 7
+ARITH_DOT3_REVERSE = 1 << 8
 
 # every symbol include/vsl.h declares (tests check the shared object exports all of them)
 EXPORTED_SYMBOLS = [
     "vsl_abi_version", "vsl_status_string", "vsl_last_cuda_error",
     "vsl_loss_workspace_bytes", "vsl_loss_forward_backward", "vsl_loss_forward_backward_timed",
     "vsl_event_create", "vsl_event_destroy", "vsl_event_elapsed_ms", "vsl_loss_combine_grads",
-    "vsl_warp_forward",
+    "vsl_warp_forward", "vsl_probe_bmm",
     "vsl_backproject_forward", "vsl_backproject_backward",
     "vsl_project_forward", "vsl_project_workspace_bytes", "vsl_project_backward",
     "vsl_ssim_forward", "vsl_ssim_backward",
@@ -106,6 +108,7 @@ def load():
     lib.vsl_warp_forward.argtypes = [POINTER(VslDesc), c_int, vp, vp, POINTER(c_void_p * VSL_MAX_SRC),
                                      POINTER(c_void_p * VSL_MAX_SRC), vp, POINTER(c_void_p * VSL_MAX_SRC),
                                      POINTER(c_void_p * VSL_MAX_SRC), vp]
+    lib.vsl_probe_bmm.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp]
     lib.vsl_backproject_forward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp]
     lib.vsl_backproject_backward.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
     lib.vsl_project_forward.argtypes = [c_int, c_int, c_int, c_float, c_int, vp, vp, vp, vp]

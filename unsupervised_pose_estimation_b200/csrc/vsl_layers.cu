@@ -306,6 +306,21 @@ __global__ void __launch_bounds__(kNT) k_smooth_bwd(int B, int H, int W, const f
   gdisp[(size_t)b * n + i] = g;
 }
 
+__global__ void __launch_bounds__(kNT) k_probe_bmm(int B, int K, int N, int arith, const float* __restrict__ A,
+                                                   const float* __restrict__ X, float* __restrict__ out) {
+  size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
+  if (gid >= (size_t)B * N) return;
+  int b = (int)(gid / N), n = (int)(gid - (size_t)b * N);
+  const float* a = A + (size_t)b * 3 * K;
+  const float* x = X + (size_t)b * K * N + n;
+  for (int i = 0; i < 3; ++i) {
+    float r = (K == 3) ? dot3(a[i * 3], x[0], a[i * 3 + 1], x[N], a[i * 3 + 2], x[2 * (size_t)N], arith)
+                       : dot4(a[i * 4], x[0], a[i * 4 + 1], x[N], a[i * 4 + 2], x[2 * (size_t)N], a[i * 4 + 3],
+                              x[3 * (size_t)N], arith);
+    out[(size_t)b * 3 * N + (size_t)i * N + n] = r;
+  }
+}
+
 static unsigned blocks_for(size_t n) { return (unsigned)((n + kNT - 1) / kNT); }
 
 }  // namespace vsl
@@ -313,6 +328,14 @@ static unsigned blocks_for(size_t n) { return (unsigned)((n + kNT - 1) / kNT); }
 using namespace vsl;
 
 extern "C" {
+
+int vsl_probe_bmm(int B, int K, int N, int arith, const float* A, const float* X, float* out, void* stream) {
+  if (B < 1 || N < 1 || (K != 3 && K != 4)) return VSL_ERR_BAD_DESC;
+  if (!A || !X || !out) return VSL_ERR_NULL_POINTER;
+  k_probe_bmm<<<blocks_for((size_t)B * N), kNT, 0, (cudaStream_t)stream>>>(B, K, N, arith, A, X, out);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
 
 int vsl_backproject_forward(int B, int H, int W, int arith, const float* depth, const float* inv_K, float* cam,
                             void* stream) {

@@ -42,13 +42,17 @@ VSL_HD float fast_rcp(float a) { return 1.0f / a; }
 // arithmetic-order selectors; mirror VSL_ARITH_* in include/vsl.h
 enum : int {
   kTrueDiv = 1 << 0, kDotNoFma = 1 << 1, kDotReverse = 1 << 2, kUpsRight = 1 << 3,
-  kUpsNoFma = 1 << 4, kTapNoFma = 1 << 5, kMeanDiv = 1 << 6
+  kUpsNoFma = 1 << 4, kTapNoFma = 1 << 5, kMeanDiv = 1 << 6, kDot3NoFma = 1 << 7, kDot3Reverse = 1 << 8
 };
 
-// ---- bmm dot products (cuBLAS SGEMM with K = 3 / K = 4: one FMA chain, k ascending) ----------
+// ---- bmm dot products ----------------------------------------------------------------------------
+// cuBLAS SGEMM with K = 3 (rays, layers.py:235) / K = 4 (projection, layers.py:256).  For batch >= 2
+// it accumulates one FMA chain, k ascending (the default here).  For batch 1 at some sizes cuBLAS
+// picks a kernel that adds un-fused products; the host layer calibrates against torch.bmm once per
+// shape and selects the matching variant (functional.calibrate_arith).
 VSL_HD float dot3(float a0, float b0, float a1, float b1, float a2, float b2, int arith) {
-  if (arith & kDotNoFma) return add_rn(add_rn(mul_rn(a0, b0), mul_rn(a1, b1)), mul_rn(a2, b2));
-  if (arith & kDotReverse) return fma_rn(a0, b0, fma_rn(a1, b1, mul_rn(a2, b2)));
+  if (arith & kDot3NoFma) return add_rn(add_rn(mul_rn(a0, b0), mul_rn(a1, b1)), mul_rn(a2, b2));
+  if (arith & kDot3Reverse) return fma_rn(a0, b0, fma_rn(a1, b1, mul_rn(a2, b2)));
   return fma_rn(a2, b2, fma_rn(a1, b1, mul_rn(a0, b0)));
 }
 VSL_HD float dot4(float a0, float b0, float a1, float b1, float a2, float b2, float a3, float b3, int arith) {

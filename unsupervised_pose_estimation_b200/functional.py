@@ -30,6 +30,56 @@ def _dev(t, name):
 
 
 # --------------------------------------------------------------------------------------------------
+# rounding-order calibration
+# --------------------------------------------------------------------------------------------------
+_ARITH_CACHE = {}
+
+
+def calibrate_arith(batch, height, width, device):
+    """Which accumulation order does torch.bmm (cuBLAS) use for this shape on this device?
+
+    The reference computes rays and projections with ``torch.matmul`` (layers.py:235, :256).  cuBLAS
+    accumulates one FMA chain for batch >= 2, but for batch 1 it may select a kernel that adds un-fused
+    products.  Bit-exact projection indices need the same order, so once per (batch, H, W, device) the
+    two bmm shapes are run through torch and through ``vsl_probe_bmm`` variants; the matching
+    VSL_ARITH_* bits are returned.  Runs at plan construction only, never on the hot path."""
+    device = torch.device(device)
+    key = (batch, height, width, device.index if device.index is not None else torch.cuda.current_device())
+    if key in _ARITH_CACHE:
+        return _ARITH_CACHE[key]
+    lib = _lib.load()
+    n = height * width
+    gen = torch.Generator(device="cpu").manual_seed(1234)
+    M = torch.randn(batch, 4, 4, generator=gen).to(device)
+    bits = 0
+    for k, variants in ((3, (0, _lib.ARITH_DOT3_NOFMA, _lib.ARITH_DOT3_REVERSE)),
+                        (4, (0, _lib.ARITH_DOT_NOFMA, _lib.ARITH_DOT_REVERSE))):
+        X = torch.randn(batch, k, n, generator=gen).to(device)
+        A = M[:, :3, :k]                       # sliced like inv_K[:, :3, :3] / (K@T)[:, :3, :]
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            ref = torch.matmul(A, X)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+        Ac = A.contiguous()
+        out = torch.empty_like(ref)
+        chosen = None
+        for v in variants:
+            check(lib.vsl_probe_bmm(batch, k, n, v, Ac.data_ptr(), X.data_ptr(), out.data_ptr(), _stream()),
+                  "vsl_probe_bmm")
+            if torch.equal(out, ref):
+                chosen = v
+                break
+        if chosen is None:
+            raise _lib.VslError("could not reproduce torch.bmm's rounding for [%d,3,%d]x[%d,%d,%d] on this device; "
+                                "pass an explicit arith" % (batch, k, batch, k, n))
+        bits |= chosen
+    _ARITH_CACHE[key] = bits
+    return bits
+
+
+# --------------------------------------------------------------------------------------------------
 # fused loss
 # --------------------------------------------------------------------------------------------------
 class FusedLossPlan:
@@ -257,7 +307,9 @@ class _Backproject(torch.autograd.Function):
         return gd, None, None
 
 
-def backproject(depth, inv_K, arith=0):
+def backproject(depth, inv_K, arith="auto"):
+    if arith == "auto":
+        arith = calibrate_arith(depth.shape[0], depth.shape[2], depth.shape[3], depth.device)
     return _Backproject.apply(depth, inv_K, arith)
 
 
@@ -289,7 +341,9 @@ class _Project(torch.autograd.Function):
         return gpts, gP, None, None, None, None
 
 
-def project(points, P, height, width, eps=1e-7, arith=0):
+def project(points, P, height, width, eps=1e-7, arith="auto"):
+    if arith == "auto":
+        arith = calibrate_arith(points.shape[0], height, width, points.device)
     return _Project.apply(points, P, height, width, float(np.float32(eps)), arith)
 
 

@@ -51,7 +51,7 @@ class ViewSynthesisLossMixin:
     """Methods of reference ``Trainer`` on the view-synthesis loss path, CUDA-backed."""
 
     vsl_side_outputs = "eager"
-    vsl_arith = 0  # VSL_ARITH_* (0 = eager PyTorch-CUDA rounding order)
+    vsl_arith = "auto"  # VSL_ARITH_* bits, or "auto": calibrate against torch.bmm once per shape
 
     # -- plan ---------------------------------------------------------------------------------
     def _vsl_plan(self):
@@ -65,9 +65,12 @@ class ViewSynthesisLossMixin:
                 raise NotImplementedError(
                     "the CUDA view-synthesis path implements the reference's default loss "
                     "(automask + per-pixel min + SSIM at full resolution); not yet: " + ", ".join(bad))
+            arith = self.vsl_arith
+            if arith == "auto":
+                arith = VF.calibrate_arith(opt.batch_size, opt.height, opt.width, self.device)
             plan = (key, VF.FusedLossPlan(opt.batch_size, opt.height, opt.width, opt.scales,
                                           len(opt.frame_ids) - 1, opt.min_depth, opt.max_depth,
-                                          opt.disparity_smoothness, arith=self.vsl_arith))
+                                          opt.disparity_smoothness, arith=arith))
             self._vsl_plan_cache = plan
         return plan[1]
 
@@ -106,7 +109,7 @@ class ViewSynthesisLossMixin:
 
     def compute_reprojection_loss(self, pred, target):
         """Reference trainer.py:543-555: 0.85 * mean_c SSIM + 0.15 * mean_c L1 -> [B,1,H,W]."""
-        return VF.reprojection_loss(pred, target, no_ssim=bool(self.opt.no_ssim), arith=self.vsl_arith)
+        return VF.reprojection_loss(pred, target, no_ssim=bool(self.opt.no_ssim))
 
     def compute_losses(self, inputs, outputs):
         """Reference trainer.py:557-686: returns the loss dict, writes ``identity_selection/s``."""
@@ -137,7 +140,7 @@ class LossPath(ViewSynthesisLossMixin):
     min_depth, max_depth, disparity_smoothness and the ablation flags (options.py:59-159).
     """
 
-    def __init__(self, opt, device="cuda", side_outputs="eager", arith=0):
+    def __init__(self, opt, device="cuda", side_outputs="eager", arith="auto"):
         self.opt = opt
         self.device = torch.device(device)
         if self.device.type != "cuda":
