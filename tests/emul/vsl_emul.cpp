@@ -4,6 +4,7 @@
 // thread of k_photometric as nested host loops, so that indexing, halo handling, the reflection-pad
 // adjoint and the analytic gradients can be checked against the oracle on a machine without a GPU.
 // It is NOT part of libvsl_b200.so and nothing in the package loads it: the product has no CPU path.
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -14,7 +15,10 @@ using namespace vsl;
 
 template <class C>
 static void run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
-  std::vector<float> sm(C::kFloats);
+  std::vector<float> sm_store(C::kFloats + 4);
+  float* sm_base = sm_store.data();
+  while (reinterpret_cast<uintptr_t>(sm_base) & 15u) ++sm_base;  // CoefRec is 16-byte aligned
+  struct { float* p; float* data() const { return p; } } sm{sm_base};
   std::vector<ThreadState<C>> ts(C::NT);
   for (int b = 0; b < p.B; ++b)
     for (int ty = 0; ty < tiles_y; ++ty)
@@ -27,16 +31,16 @@ static void run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
         for (int tid = 0; tid < C::NT; ++tid) phase_target_stats<C>(p, t, sm.data(), tid);
         for (int f = 0; f < C::F; ++f) {
           for (int tid = 0; tid < C::NT; ++tid) phase_load_region<C>(p, t, p.src[f] + img_off, sm.data() + C::oX, tid);
-          for (int tid = 0; tid < C::NT; ++tid) phase_identity<C>(p, t, sm.data(), f, tid);
+          for (int tid = 0; tid < C::NT; ++tid) phase_identity<C>(p, p.g, t, sm.data(), f, tid);
         }
         for (int s = 0; s < p.S; ++s) {
           for (int tid = 0; tid < C::NT; ++tid) {
             ts[tid].loss = 0.f;
             for (int k = 0; k < C::F * 12; ++k) ts[tid].dP[k] = 0.f;
           }
-          for (int tid = 0; tid < C::NT; ++tid) phase_warp<C>(p, t, sm.data(), s, tid);
-          for (int tid = 0; tid < C::NT; ++tid) phase_windows<C>(p, t, sm.data(), s, tid, ts[tid]);
-          for (int tid = 0; tid < C::NT; ++tid) phase_backward<C>(p, t, sm.data(), s, tid, ts[tid]);
+          for (int tid = 0; tid < C::NT; ++tid) phase_warp<C>(p, p.g, t, sm.data(), s, tid);
+          for (int tid = 0; tid < C::NT; ++tid) phase_windows<C>(p, p.g, t, sm.data(), s, tid, ts[tid]);
+          for (int tid = 0; tid < C::NT; ++tid) phase_backward<C>(p, p.g, t, sm.data(), s, tid, ts[tid]);
           float* out = p.partials + ((size_t)t.cta * p.S + s) * C::kPartial;
           for (int k = 0; k < C::kPartial; ++k) out[k] = 0.f;
           for (int tid = 0; tid < C::NT; ++tid) {

@@ -142,9 +142,13 @@ __global__ void __launch_bounds__(kSmallNT) k_smooth_terms(const SmallParams p) 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <class C>
+// kFastArith: the rounding-order selectors are the compile-time default (arith == 0, PyTorch-CUDA order
+// for batch >= 2), so every variant branch in vsl_math.cuh folds away.
+template <class C, bool kFastArith>
 __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
+  GeoConst g = p.g;
+  if (kFastArith) g.arith = 0;
   TileCtx t;
   t.b = blockIdx.z;
   t.x0 = blockIdx.x * C::TW;
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
     __syncthreads();
     phase_load_region<C>(p, t, p.src[f] + img_off, sm + C::oX, tid);
     __syncthreads();
-    phase_identity<C>(p, t, sm, f, tid);
+    phase_identity<C>(p, g, t, sm, f, tid);
   }
 
   float* red = sm + C::oRed;
@@ -170,11 +174,12 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
 #pragma unroll
     for (int k = 0; k < C::F * 12; ++k) ts.dP[k] = 0.f;
     __syncthreads();
-    phase_warp<C>(p, t, sm, s, tid);
+    phase_warp<C>(p, g, t, sm, s, tid);
     __syncthreads();
-    phase_windows<C>(p, t, sm, s, tid, ts);
+    if constexpr (C::F == 2) phase_windows_paired<C>(p, g, t, sm, s, tid, ts);
+    else phase_windows<C>(p, g, t, sm, s, tid, ts);
     __syncthreads();
-    phase_backward<C>(p, t, sm, s, tid, ts);
+    phase_backward<C>(p, g, t, sm, s, tid, ts);
     // deterministic block reduction of (loss, dP) -> one partial per CTA and scale
     const int w = tid >> 5, l = tid & 31;
     float v = warp_sum(ts.loss);
@@ -430,17 +435,23 @@ static Plan make_plan(const VslDesc* d) {
   return pl;
 }
 
-template <class C>
-static int launch_photometric(const PhotoParams& pp, const Plan& pl, int batch, cudaStream_t st) {
+template <class C, bool kFastArith>
+static int launch_photometric_impl(const PhotoParams& pp, const Plan& pl, int batch, cudaStream_t st) {
   static bool attr_done = false;  // idempotent; a race only repeats the call
   if (!attr_done) {
-    VSL_CUDA_OK(cudaFuncSetAttribute(k_photometric<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kBytes));
+    VSL_CUDA_OK(cudaFuncSetAttribute(k_photometric<C, kFastArith>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::kBytes));
     attr_done = true;
   }
   dim3 grid(pl.tiles_x, pl.tiles_y, batch);
-  k_photometric<C><<<grid, C::NT, C::kBytes, st>>>(pp);
+  k_photometric<C, kFastArith><<<grid, C::NT, C::kBytes, st>>>(pp);
   VSL_CUDA_OK(cudaGetLastError());
   return VSL_OK;
+}
+template <class C>
+static int launch_photometric(const PhotoParams& pp, const Plan& pl, int batch, cudaStream_t st) {
+  return pp.g.arith == 0 ? launch_photometric_impl<C, true>(pp, pl, batch, st)
+                         : launch_photometric_impl<C, false>(pp, pl, batch, st);
 }
 
 }  // namespace vsl

@@ -188,8 +188,24 @@ VSL_HD float bilinear_value(const Taps& t, float vnw, float vne, float vsw, floa
 VSL_HD float c1f() { return (float)(0.01 * 0.01); }
 VSL_HD float c2f() { return (float)(0.03 * 0.03); }
 
-// avg_pool2d's `sum / 9` (ATen AveragePool2d.cu divides the sequential window sum by the pool size)
-VSL_HD float div9(float a) { return div_rn(a, 9.0f); }
+// avg_pool2d's `sum / 9` (ATen AveragePool2d.cu divides the sequential window sum by the pool size).
+// Correctly rounded a/9 in 3 FP instructions: q = a*RN(1/9), one Markstein correction with the exact
+// residual.  Verified against __fdiv_rn(a, 9) for EVERY float with 1e-30 <= |a| <= 1e30 on the B200
+// (tools/ubench/ubench.cu: 0 mismatches of 3,343,868,118); outside that range (and for 0) the IEEE
+// division is used.
+VSL_HD float div9(float a) {
+#if defined(__CUDA_ARCH__)
+  const float y = 1.0f / 9.0f;
+  float q = __fmul_rn(a, y);
+  float r = __fmaf_rn(-9.0f, q, a);
+  q = __fmaf_rn(r, y, q);
+  // fast result kept iff the biased exponent is in [28, 225], i.e. 2^-99 <= |a| < 2^99 (inside the verified range)
+  if (((__float_as_uint(a) & 0x7fffffffu) - 0x0e000000u) >= 0x63000000u) q = __fdiv_rn(a, 9.0f);
+  return q;
+#else
+  return div_rn(a, 9.0f);
+#endif
+}
 
 // torch.mean over the 3 channels: sequential sum times float(1/3)
 VSL_HD float mean3(float a, float b, float c, int arith) {

@@ -46,13 +46,22 @@ struct TileCfg {
   static constexpr int oTS = oT + 3 * RN;       // target mu_y, sigma_y    [6][WN]
   static constexpr int oX = oTS + 6 * WN;       // warped / source region  [F][3][RN]
   static constexpr int oId = oX + F * 3 * RN;   // identity losses         [F][WN]
-  static constexpr int oCoef = oId + F * WN;    // winner's SSIM adjoint coefficients [9][WN]
-  static constexpr int oIdx = oCoef + 9 * WN;   // winning source frame or -1 [WN] (int)
-  static constexpr int oG = oIdx + WN;          // d warped / d(ix,iy)     [F][6][IN]
+  static constexpr int oCoef = oId + F * WN;    // per window: CoefRec (winner's SSIM adjoint coefficients + winner id)
+  static constexpr int oG = oCoef + 12 * WN;    // d warped / d(ix,iy)     [F][6][IN]
   static constexpr int oRed = oG + F * 6 * IN;  // block-reduction scratch [NT/32][1 + F*12]
   static constexpr int kFloats = oRed + (NT / 32) * (1 + F * 12);
   static constexpr int kBytes = kFloats * 4;
   static constexpr int kPartial = 1 + F * 12;
+  static_assert(oCoef % 4 == 0, "CoefRec needs 16-byte alignment");
+};
+
+// One record per SSIM window: the 9 adjoint coefficients (A,B,C per channel) of the frame that won the
+// per-pixel minimum, zeros when an identity candidate won; 48 bytes so the adjoint gathers it with
+// three 128-bit shared loads.
+struct alignas(16) CoefRec {
+  float c[9];
+  float pad0, pad1;
+  int idx;  // winning source frame, or -1 (identity won / window outside the image)
 };
 
 template <class C>
@@ -145,7 +154,8 @@ VSL_HD float reproj_window(const float* __restrict__ X, const float* __restrict_
 
 // ---- phase: identity reprojection loss of source frame f (its region is staged in X[0]) ---------
 template <class C>
-VSL_HD void phase_identity(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int f, int tid) {
+VSL_HD void phase_identity(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int f,
+                           int tid) {
   const float* T = sm + C::oT;
   const float* TS = sm + C::oTS;
   const float* X = sm + C::oX;
@@ -156,7 +166,7 @@ VSL_HD void phase_identity(const PhotoParams& p, const TileCtx& t, float* __rest
     float v = 0.f;
     if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
       SsimOut so[3];
-      v = reproj_window<C>(X, T, TS, wy, wx, i, p.g.arith, so);
+      v = reproj_window<C>(X, T, TS, wy, wx, i, g.arith, so);
     }
     Id[i] = v;
   }
@@ -164,7 +174,8 @@ VSL_HD void phase_identity(const PhotoParams& p, const TileCtx& t, float* __rest
 
 // ---- phase: warp every source frame on the region for scale s -----------------------------------
 template <class C>
-VSL_HD void phase_warp(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
+VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int s,
+                       int tid) {
   float* X = sm + C::oX;
   float* G = sm + C::oG;
   const int HW = p.H * p.W;
@@ -181,13 +192,13 @@ VSL_HD void phase_warp(const PhotoParams& p, const TileCtx& t, float* __restrict
     }
     int v = reflect1(gy, p.H), u = reflect1(gx, p.W);
     float D = upsample_disp(disp, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s], p.identity_scale[s] != 0, v, u,
-                            p.g.arith);
-    Cam cam = backproject_pixel(D, invK, u, v, p.g);
+                            g.arith);
+    Cam cam = backproject_pixel(D, invK, u, v, g);
     bool interior = ry >= 2 && ry < C::TH + 2 && rx >= 2 && rx < C::TW + 2 && gy < p.H && gx < p.W;
     int j = (ry - 2) * C::TW + (rx - 2);
 #pragma unroll
     for (int f = 0; f < C::F; ++f) {
-      Proj pr = project_pixel(cam, p.P[f] + t.b * 12, p.g);
+      Proj pr = project_pixel(cam, p.P[f] + t.b * 12, g);
       Taps tp = bilinear_taps(pr, p.W, p.H);
       const float* img = p.src[f] + (size_t)t.b * 3 * HW + pr.y0 * p.W + pr.x0;
       int dx = tp.x1ok ? 1 : 0, dy = tp.y1ok ? p.W : 0;
@@ -195,7 +206,7 @@ VSL_HD void phase_warp(const PhotoParams& p, const TileCtx& t, float* __restrict
       for (int c = 0; c < 3; ++c) {
         const float* q = img + c * HW;
         float vnw = q[0], vne = q[dx], vsw = q[dy], vse = q[dy + dx];
-        X[(f * 3 + c) * C::RN + i] = bilinear_value(tp, vnw, vne, vsw, vse, p.g.arith);
+        X[(f * 3 + c) * C::RN + i] = bilinear_value(tp, vnw, vne, vsw, vse, g.arith);
         if (interior) {
           // grid_sampler_2d_backward's d out / d(ix, iy); zero where the border clip is active
           float ddx = pr.inx ? ((vne - vnw) * tp.wy1 + (vse - vsw) * tp.wy0) : 0.f;
@@ -209,60 +220,78 @@ VSL_HD void phase_warp(const PhotoParams& p, const TileCtx& t, float* __restrict
 }
 
 // ---- phase: per-window losses, auto-mask arg-min, adjoint coefficients ---------------------------
+// adjoint coefficients of one frame's SSIM at a window: A (d/d mu_x), B (d/d E[x^2]), C (d/d E[xy]) per
+// channel, pre-scaled by the pixel weight, 0.85/3, the clamp mask, -1/2 and the 1/9 of the mean filter
+VSL_HD void window_coefs(const SsimOut so[3], const float* __restrict__ TS, int WN, int i, float kc, float coef[9]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float dmu, dexx, dexy;
+    ssim_r_grads(so[c], TS[c * WN + i], dmu, dexx, dexy);
+    float k = so[c].live ? kc : 0.f;
+    coef[c] = k * dmu;
+    coef[3 + c] = k * dexx;
+    coef[6 + c] = k * dexy;
+  }
+}
+
+VSL_HD void store_rec(CoefRec* __restrict__ rec, const float coef[9], int idx) {
+  CoefRec r;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.c[k] = coef[k];
+  r.pad0 = 0.f; r.pad1 = 0.f; r.idx = idx;
+  *rec = r;
+}
+
+// best identity candidate (trainer.py:654-659: identity + 1e-5 * randn, identity channels first)
 template <class C>
-VSL_HD void phase_windows(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid,
-                          ThreadState<C>& ts) {
+VSL_HD void identity_candidates(const PhotoParams& p, const TileCtx& t, const float* __restrict__ Id, int s, int i,
+                                int gy, int gx, float& best, int& bidx) {
+  const int HW = p.H * p.W;
+  const float* nz = p.noise[s] + (size_t)t.b * C::F * HW + gy * p.W + gx;
+  best = INFINITY;
+  bidx = -1;
+#pragma unroll
+  for (int f = 0; f < C::F; ++f) {
+    float cand = add_rn(Id[f * C::WN + i], mul_rn(nz[f * HW], 1e-5f));
+    if (cand < best) { best = cand; bidx = f; }
+  }
+}
+
+template <class C>
+VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int s,
+                          int tid, ThreadState<C>& ts) {
   const float* T = sm + C::oT;
   const float* TS = sm + C::oTS;
   const float* X = sm + C::oX;
   const float* Id = sm + C::oId;
-  float* Coef = sm + C::oCoef;
-  int* Idx = reinterpret_cast<int*>(sm + C::oIdx);
+  CoefRec* Rec = reinterpret_cast<CoefRec*>(sm + C::oCoef);
   const int HW = p.H * p.W;
   const float kc = p.wpix * (0.85f / 3.0f) * (-0.5f) * (1.0f / 9.0f);
   for (int i = tid; i < C::WN; i += C::NT) {
     int wy = i / C::WW, wx = i - wy * C::WW;
     int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
-    if (!(gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)) {
-      Idx[i] = -1;
-      continue;
-    }
-    // identity candidates first (trainer.py:659: cat(identity, reprojection)), ties keep the lower index
-    float best = INFINITY;
-    int bidx = -1;
-    const float* nz = p.noise[s] + (size_t)t.b * C::F * HW + gy * p.W + gx;
-#pragma unroll
-    for (int f = 0; f < C::F; ++f) {
-      float cand = add_rn(Id[f * C::WN + i], mul_rn(nz[f * HW], 1e-5f));
-      if (cand < best) { best = cand; bidx = f; }
-    }
     float coef[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) coef[k] = 0.f;
+    if (!(gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)) {
+      store_rec(Rec + i, coef, -1);
+      continue;
+    }
+    float best;
+    int bidx;
+    identity_candidates<C>(p, t, Id, s, i, gy, gx, best, bidx);
 #pragma unroll
     for (int f = 0; f < C::F; ++f) {
       SsimOut so[3];
-      float l = reproj_window<C>(X + f * 3 * C::RN, T, TS, wy, wx, i, p.g.arith, so);
-      if (l < best) {
+      float l = reproj_window<C>(X + f * 3 * C::RN, T, TS, wy, wx, i, g.arith, so);
+      if (l < best) {  // strict: ties keep the lower index, like torch.min
         best = l;
         bidx = C::F + f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float dmu, dexx, dexy;
-          ssim_r_grads(so[c], TS[c * C::WN + i], dmu, dexx, dexy);
-          float k = so[c].live ? kc : 0.f;
-          coef[c] = k * dmu;
-          coef[3 + c] = k * dexx;
-          coef[6 + c] = k * dexy;
-        }
+        window_coefs(so, TS, C::WN, i, kc, coef);
       }
     }
     bool warped = bidx >= C::F;
-    Idx[i] = warped ? bidx - C::F : -1;
-    if (warped) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) Coef[k * C::WN + i] = coef[k];
-    }
+    store_rec(Rec + i, coef, warped ? bidx - C::F : -1);
     bool interior = wy >= 1 && wy <= C::TH && wx >= 1 && wx <= C::TW;
     if (interior) {
       ts.loss += best;
@@ -271,14 +300,72 @@ VSL_HD void phase_windows(const PhotoParams& p, const TileCtx& t, float* __restr
   }
 }
 
+#if defined(__CUDACC__)
+// Two-source-frame variant (frames [0,-1,1], the reference default): lanes 2k / 2k+1 evaluate frame 0 / 1
+// of the same window and exchange the losses by shuffle, so the 2*WN (window, frame) items fill the CTA's
+// threads evenly (95 % of the slots instead of 80 %).  Same decisions as phase_windows.
+template <class C>
+__device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const GeoConst& g, const TileCtx& t,
+                                                     float* __restrict__ sm, int s, int tid, ThreadState<C>& ts) {
+  static_assert(C::F == 2, "paired variant is for two source frames");
+  const float* T = sm + C::oT;
+  const float* TS = sm + C::oTS;
+  const float* X = sm + C::oX;
+  const float* Id = sm + C::oId;
+  CoefRec* Rec = reinterpret_cast<CoefRec*>(sm + C::oCoef);
+  const int HW = p.H * p.W;
+  const float kc = p.wpix * (0.85f / 3.0f) * (-0.5f) * (1.0f / 9.0f);
+  for (int base = 0; base < 2 * C::WN; base += C::NT) {  // uniform trip count: every lane reaches the shuffle
+    const int item = base + tid;
+    const int i = item >> 1, f = item & 1;
+    const bool live = item < 2 * C::WN;
+    int wy = i / C::WW, wx = i - wy * C::WW;
+    int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
+    const bool inside = live && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+    float best = INFINITY, l = INFINITY;
+    int bidx = -1;
+    SsimOut so[3];
+    if (inside) {
+      identity_candidates<C>(p, t, Id, s, i, gy, gx, best, bidx);
+      l = reproj_window<C>(X + f * 3 * C::RN, T, TS, wy, wx, i, g.arith, so);
+    }
+    const float other = __shfl_xor_sync(0xffffffffu, l, 1);
+    if (!live) continue;
+    // arg-min over (identity..., frame 0, frame 1) with ties to the lower index
+    const float l0 = f == 0 ? l : other, l1 = f == 0 ? other : l;
+    int win = -1;
+    float m = best;
+    if (inside) {
+      if (l0 < m) { m = l0; win = 0; }
+      if (l1 < m) { m = l1; win = 1; }
+    }
+    float coef[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) coef[k] = 0.f;
+    if (win == f) {
+      window_coefs(so, TS, C::WN, i, kc, coef);
+      store_rec(Rec + i, coef, f);
+    } else if (win < 0 && f == 0) {
+      store_rec(Rec + i, coef, -1);
+    }
+    if (f == 0 && inside) {
+      bool interior = wy >= 1 && wy <= C::TH && wx >= 1 && wx <= C::TW;
+      if (interior) {
+        ts.loss += m;
+        if (p.mask[s]) p.mask[s][(size_t)t.b * HW + gy * p.W + gx] = win >= 0 ? 1.f : 0.f;
+      }
+    }
+  }
+}
+#endif
+
 // ---- phase: adjoint for the interior pixels of scale s -------------------------------------------
 template <class C>
-VSL_HD void phase_backward(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid,
-                           ThreadState<C>& ts) {
+VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int s,
+                           int tid, ThreadState<C>& ts) {
   const float* T = sm + C::oT;
   const float* X = sm + C::oX;
-  const float* Coef = sm + C::oCoef;
-  const int* Idx = reinterpret_cast<const int*>(sm + C::oIdx);
+  const CoefRec* Rec = reinterpret_cast<const CoefRec*>(sm + C::oCoef);
   const float* G = sm + C::oG;
   const int HW = p.H * p.W;
   const float* invK = p.invK + t.b * 16;
@@ -301,17 +388,15 @@ VSL_HD void phase_backward(const PhotoParams& p, const TileCtx& t, float* __rest
 #pragma unroll
       for (int dx = -1; dx <= 1; ++dx) {
         float cx = ((dx == -1 && gx == 1) || (dx == 1 && gx == p.W - 2)) ? 2.f : 1.f;
-        int w = (iy + 1 + dy) * C::WW + (ix + 1 + dx);
-        int idx = Idx[w];
-        if (idx < 0) continue;
-        used |= 1u << idx;
-        float cnt = cy * cx;
+        const CoefRec rec = Rec[(iy + 1 + dy) * C::WW + (ix + 1 + dx)];  // 3 x 128-bit shared loads
+        if (rec.idx >= 0) used |= 1u << rec.idx;
+        const float cnt = cy * cx;
 #pragma unroll
-        for (int f = 0; f < C::F; ++f)
-          if (idx == f) {
+        for (int f = 0; f < C::F; ++f) {
+          const float cf = rec.idx == f ? cnt : 0.f;  // records of lost windows hold zeros
 #pragma unroll
-            for (int k = 0; k < 9; ++k) acc[f][k] += cnt * Coef[k * C::WN + w];
-          }
+          for (int k = 0; k < 9; ++k) acc[f][k] = fmaf(cf, rec.c[k], acc[f][k]);
+        }
       }
     }
     float gz = 0.f;
@@ -319,10 +404,10 @@ VSL_HD void phase_backward(const PhotoParams& p, const TileCtx& t, float* __rest
     cam.z = 0.f;
     if (used) {
       float D = upsample_disp(disp, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s], p.identity_scale[s] != 0, gy,
-                              gx, p.g.arith);
-      cam = backproject_pixel(D, invK, gx, gy, p.g);
+                              gx, g.arith);
+      cam = backproject_pixel(D, invK, gx, gy, g);
       const int center = (iy + 2) * C::RW + (ix + 2);
-      const int own = Idx[(iy + 1) * C::WW + (ix + 1)];
+      const int own = Rec[(iy + 1) * C::WW + (ix + 1)].idx;
 #pragma unroll
       for (int f = 0; f < C::F; ++f) {
         if (!(used & (1u << f))) continue;
@@ -339,7 +424,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const TileCtx& t, float* __rest
         float c0 = P[0] * cam.X + P[1] * cam.Y + P[2] * cam.Z + P[3];
         float c1 = P[4] * cam.X + P[5] * cam.Y + P[6] * cam.Z + P[7];
         float c2 = P[8] * cam.X + P[9] * cam.Y + P[10] * cam.Z + P[11];
-        float iz = fast_rcp(c2 + p.g.eps);
+        float iz = fast_rcp(c2 + g.eps);
         float g0 = gix * iz, g1 = giy * iz;
         float g2 = -(g0 * c0 + g1 * c1) * iz;
         float* dP = ts.dP + f * 12;
@@ -353,7 +438,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const TileCtx& t, float* __rest
       }
     }
     // z = 1/(min_disp + range*D)  ->  dz/dD = -range * z^2
-    p.gD[s][(size_t)t.b * HW + gy * p.W + gx] = -gz * p.g.disp_range * cam.z * cam.z;
+    p.gD[s][(size_t)t.b * HW + gy * p.W + gx] = -gz * g.disp_range * cam.z * cam.z;
   }
 }
 
