@@ -232,6 +232,35 @@ def test_backward_is_linear_in_the_upstream_gradient():
             assert gr is None or float(gr.abs().max()) == 0.0, k
 
 
+def test_graph_replay_equals_eager():
+    """The captured step (graph.py) is the eager step: same losses, masks, gradients and RNG consumption."""
+    from unsupervised_pose_estimation_b200.graph import GraphedLossStep
+    opt, inputs, outputs, _ = build_case("mono_iid_64x96")
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in outputs.items() if k[0] == "disp"}
+    for f in opt.frame_ids[1:]:
+        T = L.transformation_from_parameters(outputs[("axisangle", 0, f)][:, 0].detach(),
+                                             outputs[("translation", 0, f)][:, 0].detach(), f < 0)
+        leaves[("cam_T_cam", 0, f)] = T.clone().requires_grad_(True)
+    path = LossPath(make_opt(**vars(opt)), device=DEV, side_outputs="none")
+    step = GraphedLossStep(path, inputs, leaves)
+    for trial in range(2):
+        torch.manual_seed(100 + trial)
+        out = dict(leaves)
+        eager = path.compute_losses(inputs, out)
+        eg = torch.autograd.grad(eager["loss"], list(leaves.values()))
+        after_eager = torch.randn(4, device=DEV)
+        torch.manual_seed(100 + trial)
+        losses, grads = step.replay()
+        after_graph = torch.randn(4, device=DEV)
+        for k in eager:
+            assert torch.equal(eager[k], losses[k]), k
+        for s in opt.scales:
+            assert torch.equal(out["identity_selection/%d" % s], step.outputs["identity_selection/%d" % s])
+        for g, k in zip(eg, leaves):
+            assert torch.equal(g, grads[k]), k
+        assert torch.equal(after_eager, after_graph)
+
+
 # ------------------------------------------------------------------------------------------------
 # stand-alone layers (the layers.py surface)
 # ------------------------------------------------------------------------------------------------
