@@ -160,12 +160,9 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
   phase_load_region<C>(p, t, p.tgt + img_off, sm + C::oT, tid);
   __syncthreads();
   phase_target_stats<C>(p, t, sm, tid);
-  for (int f = 0; f < C::F; ++f) {
-    __syncthreads();
-    phase_load_region<C>(p, t, p.src[f] + img_off, sm + C::oX, tid);
-    __syncthreads();
-    phase_identity<C>(p, g, t, sm, f, tid);
-  }
+  phase_load_sources<C>(p, t, sm, tid);
+  __syncthreads();
+  phase_identity<C>(p, g, t, sm, tid);
 
   float* red = sm + C::oRed;
   for (int s = 0; s < p.S; ++s) {
@@ -400,7 +397,7 @@ static bool desc_ok(const VslDesc* d) {
 
 static GeoConst make_geo(const VslDesc* d) {
   GeoConst g;
-  g.min_disp = d->min_disp; g.disp_range = d->disp_range; g.eps = d->eps;
+  g.min_disp = d->min_disp; g.disp_range = d->disp_range; g.eps = d->eps; g.one = 1.0f;
   g.W = d->width; g.H = d->height;
   g.wm1 = (float)(d->width - 1); g.hm1 = (float)(d->height - 1);
   g.inv_wm1 = 1.0f / g.wm1; g.inv_hm1 = 1.0f / g.hm1;

@@ -39,6 +39,37 @@ VSL_HD float rcp_rn(float a) { volatile float r = 1.0f / a; return r; }
 VSL_HD float fast_rcp(float a) { return 1.0f / a; }
 #endif
 
+// ---- packed pairs: two independent fp32 values per operation -------------------------------------
+// sm_100 issues add/mul/fma on fp32 PAIRS as one instruction (FADD2 / FMUL2 / FFMA2), each half rounded
+// to nearest like the scalar op.  The kernel is issue-bound, so evaluating two source frames of one SSIM
+// window in the two halves nearly halves the instruction count of the hot loop at identical bits.
+#if defined(__CUDA_ARCH__)
+typedef float2 F2;
+VSL_HD F2 f2(float x, float y) { return make_float2(x, y); }
+VSL_HD F2 add2(F2 a, F2 b) { return __fadd2_rn(a, b); }
+VSL_HD F2 fma2(F2 a, F2 b, F2 c) { return __ffma2_rn(a, b, c); }
+// NOTE: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 although both carry .rn — even
+// when the product is written fma(a, b, -0) — which it never does for the scalar forms.  Products that
+// feed an add or subtract are therefore formed by two scalar __fmul_rn (mul2); only sums, explicit FMAs
+// and products that are not added to anything (mul2_packed) use the packed instructions.  Checked bit
+// for bit against the scalar chain on the B200 (tools/ubench/pairtest.cu).
+VSL_HD F2 mul2(F2 a, F2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+VSL_HD F2 mul2_packed(F2 a, F2 b) { return __fmul2_rn(a, b); }
+#else
+struct F2 { float x, y; };
+VSL_HD F2 f2(float x, float y) { F2 r; r.x = x; r.y = y; return r; }
+VSL_HD F2 add2(F2 a, F2 b) { return f2(add_rn(a.x, b.x), add_rn(a.y, b.y)); }
+VSL_HD F2 mul2(F2 a, F2 b) { return f2(mul_rn(a.x, b.x), mul_rn(a.y, b.y)); }
+VSL_HD F2 fma2(F2 a, F2 b, F2 c) { return f2(fma_rn(a.x, b.x, c.x), fma_rn(a.y, b.y, c.y)); }
+VSL_HD F2 mul2_packed(F2 a, F2 b) { return mul2(a, b); }
+#endif
+VSL_HD F2 splat(float v) { return f2(v, v); }
+// s + a*b with the product rounded first (two roundings, like add_rn(s, mul_rn(a, b))), all packed:
+// the product feeds only the MULTIPLICAND of an FMA whose other factor is a run-time 1.0 (GeoConst::one),
+// so neither nvcc nor ptxas can contract or simplify it.  p*1 is exact, so the FMA rounds p + s once.
+VSL_HD F2 addp(F2 s, F2 a, F2 b, F2 one) { return fma2(mul2_packed(a, b), one, s); }
+VSL_HD F2 sub2(F2 a, F2 b) { return add2(a, f2(-b.x, -b.y)); }  // a + (-b) rounds exactly like a - b
+
 // arithmetic-order selectors; mirror VSL_ARITH_* in include/vsl.h
 enum : int {
   kTrueDiv = 1 << 0, kDotNoFma = 1 << 1, kDotReverse = 1 << 2, kUpsRight = 1 << 3,
@@ -96,6 +127,7 @@ VSL_HD float upsample_disp(const float* __restrict__ disp, int hs, int ws, float
 // ---- geometry ---------------------------------------------------------------------------------
 struct GeoConst {  // per call
   float min_disp, disp_range, eps;
+  float one;               // 1.0f, deliberately a run-time value (see addp)
   float wm1, hm1;          // (float)(W-1), (float)(H-1)
   float inv_wm1, inv_hm1;  // 1.0f/(W-1), 1.0f/(H-1) rounded (PyTorch-CUDA divides by a CPU scalar this way)
   int W, H, arith;
@@ -207,6 +239,29 @@ VSL_HD float div9(float a) {
 #endif
 }
 
+VSL_HD bool div9_fast_ok(float a) {
+#if defined(__CUDA_ARCH__)
+  return ((__float_as_uint(a) & 0x7fffffffu) - 0x0e000000u) < 0x63000000u;
+#else
+  (void)a;
+  return false;
+#endif
+}
+// both halves of a pair divided by 9 (same sequence and guard as div9)
+VSL_HD F2 div9_2(F2 a) {
+#if defined(__CUDA_ARCH__)
+  const F2 y = splat(1.0f / 9.0f);
+  F2 q = mul2_packed(a, y);  // q is only ever an FMA operand below, never the input of a plain add
+  F2 r = fma2(splat(-9.0f), q, a);
+  q = fma2(r, y, q);
+  if (!div9_fast_ok(a.x)) q.x = __fdiv_rn(a.x, 9.0f);
+  if (!div9_fast_ok(a.y)) q.y = __fdiv_rn(a.y, 9.0f);
+  return q;
+#else
+  return f2(div_rn(a.x, 9.0f), div_rn(a.y, 9.0f));
+#endif
+}
+
 // torch.mean over the 3 channels: sequential sum times float(1/3)
 VSL_HD float mean3(float a, float b, float c, int arith) {
   float s = add_rn(add_rn(a, b), c);
@@ -235,6 +290,30 @@ VSL_HD SsimOut ssim_from_sums(float sx, float sxx, float sxy, float mu_y, float 
   o.live = (t >= 0.f) && (t <= 1.f);
   o.val = fminf(fmaxf(t, 0.f), 1.f);
   return o;
+}
+
+// The same SSIM value for two x-images against one y (the two halves are two source frames); op for op
+// the chain of ssim_from_sums, so each half is bit-identical to the scalar evaluation.
+VSL_HD F2 ssim_val2(F2 sx, F2 sxx, F2 sxy, float mu_y, float sig_y, F2 one) {
+  const F2 muy = splat(mu_y), c1 = splat(c1f()), c2 = splat(c2f());
+  const F2 mone = f2(-one.x, -one.y);
+  F2 mu_x = div9_2(sx);
+  F2 mu_x2 = mul2_packed(mu_x, mu_x);                       // consumed through FMAs by `one` only
+  F2 sig_x = fma2(mu_x2, mone, div9_2(sxx));                // E[x^2] - mu_x^2
+  F2 sig_xy = fma2(mul2_packed(mu_x, muy), mone, div9_2(sxy));
+  F2 n1 = addp(c1, add2(mu_x, mu_x), muy, one);             // (2 mu_x) mu_y + C1  (2 mu_x is exact)
+  F2 n2 = add2(add2(sig_xy, sig_xy), c2);                   // 2 sigma_xy + C2
+  F2 d1 = add2(fma2(mu_x2, one, splat(mul_rn(mu_y, mu_y))), c1);
+  F2 d2 = add2(add2(sig_x, splat(sig_y)), c2);
+  F2 n = mul2_packed(n1, n2), d = mul2_packed(d1, d2);
+  F2 r = f2(div_rn(n.x, d.x), div_rn(n.y, d.y));
+  F2 t = mul2_packed(sub2(splat(1.0f), r), splat(0.5f));
+  return f2(fminf(fmaxf(t.x, 0.f), 1.f), fminf(fmaxf(t.y, 0.f), 1.f));
+}
+VSL_HD F2 mean3_2(F2 a, F2 b, F2 c, int arith) {
+  F2 s = add2(add2(a, b), c);
+  if (arith & kMeanDiv) return f2(div_rn(s.x, 3.0f), div_rn(s.y, 3.0f));
+  return mul2_packed(s, splat(1.0f / 3.0f));  // callers combine it through addp, never a plain add
 }
 
 // d r / d(mu_x, E[x^2], E[xy]) of r = n1 n2 / (d1 d2)  

@@ -122,23 +122,39 @@ VSL_HD void phase_target_stats(const PhotoParams& p, const TileCtx& t, float* __
   }
 }
 
-// SSIM + L1 of one window for one image buffer X (3 channels, region layout); returns the
-// reprojection loss (trainer.py:546-553) and leaves the per-channel SSIM state in `so`.
+// ---- warped / source pixel storage -----------------------------------------------------------------
+// Source frames are kept in PAIRS: frames 2k and 2k+1 interleaved as one fp32 pair per (channel, pixel),
+// so the SSIM window loop loads and processes both with packed instructions.  An odd last frame is stored
+// on its own.  Float offsets relative to sm + C::oX:
 template <class C>
-VSL_HD float reproj_window(const float* __restrict__ X, const float* __restrict__ T,
+struct XLayout {
+  static constexpr int NP = C::F / 2;           // pairs
+  static constexpr int R = C::F % 2;            // leftover single frame
+  VSL_HD static int pair_base(int pr, int c) { return (pr * 3 + c) * 2 * C::RN; }  // F2 array [RN]
+  VSL_HD static int single_base(int c) { return NP * 6 * C::RN + c * C::RN; }      // float array [RN]
+  VSL_HD static int at(int f, int c, int pos) {
+    return f < 2 * NP ? pair_base(f >> 1, c) + 2 * pos + (f & 1) : single_base(c) + pos;
+  }
+};
+
+// SSIM + L1 of one window for one frame X (3 channels `cs` floats apart, pixels XS floats apart: XS = 1
+// for a single-frame buffer, 2 for one half of a pair buffer); returns the reprojection loss
+// (trainer.py:546-553) and leaves the per-channel SSIM state in `so`.
+template <class C, int XS = 1>
+VSL_HD float reproj_window(const float* __restrict__ X, int cs, const float* __restrict__ T,
                            const float* __restrict__ TS, int wy, int wx, int widx, int arith, SsimOut so[3]) {
   float ss[3], l1[3];
   const int center = (wy + 1) * C::RW + (wx + 1);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float* x = X + c * C::RN + center;
+    const float* x = X + c * cs + XS * center;
     const float* y = T + c * C::RN + center;
     float sx = 0.f, sxx = 0.f, sxy = 0.f;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
       for (int dx = -1; dx <= 1; ++dx) {
-        float xv = x[dy * C::RW + dx], yv = y[dy * C::RW + dx];
+        float xv = x[XS * (dy * C::RW + dx)], yv = y[dy * C::RW + dx];
         sx = add_rn(sx, xv);
         sxx = add_rn(sxx, mul_rn(xv, xv));
         sxy = add_rn(sxy, mul_rn(xv, yv));
@@ -152,23 +168,99 @@ VSL_HD float reproj_window(const float* __restrict__ X, const float* __restrict_
   return add_rn(mul_rn(0.85f, ms), mul_rn(0.15f, ml));
 }
 
-// ---- phase: identity reprojection loss of source frame f (its region is staged in X[0]) ---------
+// The same for a PAIR of frames at once (X2: pair storage of channel 0, channels 2*RN apart).  Returns
+// both losses; `sums` keeps the window sums (sx, sxx, sxy per channel) so the caller can rebuild the
+// SSIM state of whichever frame wins without holding both in registers.
+struct PairSums { F2 sx[3], sxx[3], sxy[3]; };
 template <class C>
-VSL_HD void phase_identity(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int f,
-                           int tid) {
+VSL_HD F2 reproj_window_pair(const float* __restrict__ X2, const float* __restrict__ T,
+                             const float* __restrict__ TS, int wy, int wx, int widx, int arith, float onef,
+                             PairSums& sums) {
+  F2 ss[3], l1[3];
+  const F2 one = splat(onef);
+  const int center = (wy + 1) * C::RW + (wx + 1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const F2* x = reinterpret_cast<const F2*>(X2 + c * 2 * C::RN) + center;
+    const float* y = T + c * C::RN + center;
+    F2 sx = splat(0.f), sxx = splat(0.f), sxy = splat(0.f);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        F2 xv = x[dy * C::RW + dx];
+        F2 yv = splat(y[dy * C::RW + dx]);
+        sx = add2(sx, xv);
+        sxx = addp(sxx, xv, xv, one);
+        sxy = addp(sxy, xv, yv, one);
+      }
+    sums.sx[c] = sx; sums.sxx[c] = sxx; sums.sxy[c] = sxy;
+    ss[c] = ssim_val2(sx, sxx, sxy, TS[c * C::WN + widx], TS[(3 + c) * C::WN + widx], one);
+    F2 d = sub2(splat(y[0]), x[0]);
+    l1[c] = f2(fabsf(d.x), fabsf(d.y));
+  }
+  F2 ms = mean3_2(ss[0], ss[1], ss[2], arith);
+  F2 ml = mean3_2(l1[0], l1[1], l1[2], arith);
+  return addp(mul2_packed(splat(0.15f), ml), splat(0.85f), ms, one);  // 0.85 ms + 0.15 ml, each product rounded
+}
+
+// ---- phase: stage every source frame's tile (+2 halo, reflect-mapped) in the X storage -----------
+template <class C>
+VSL_HD void phase_load_sources(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int tid) {
+  using XL = XLayout<C>;
+  float* X = sm + C::oX;
+  const int HW = p.H * p.W;
+  const size_t img_off = (size_t)t.b * 3 * HW;
+  for (int i = tid; i < C::RN; i += C::NT) {
+    int ry = i / C::RW, rx = i - ry * C::RW;
+    int gy = t.y0 - 2 + ry, gx = t.x0 - 2 + rx;
+    bool valid = gy >= -1 && gy <= p.H && gx >= -1 && gx <= p.W;
+    int o = reflect1(gy, p.H) * p.W + reflect1(gx, p.W);
+#pragma unroll
+    for (int pr = 0; pr < XL::NP; ++pr)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        F2 v = splat(0.f);
+        if (valid) v = f2(p.src[2 * pr][img_off + c * HW + o], p.src[2 * pr + 1][img_off + c * HW + o]);
+        reinterpret_cast<F2*>(X + XL::pair_base(pr, c))[i] = v;
+      }
+    if (XL::R) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) X[XL::single_base(c) + i] = valid ? p.src[C::F - 1][img_off + c * HW + o] : 0.f;
+    }
+  }
+}
+
+// ---- phase: identity reprojection losses of all source frames (trainer.py:620-633) --------------
+template <class C>
+VSL_HD void phase_identity(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int tid) {
+  using XL = XLayout<C>;
   const float* T = sm + C::oT;
   const float* TS = sm + C::oTS;
   const float* X = sm + C::oX;
-  float* Id = sm + C::oId + f * C::WN;
+  float* Id = sm + C::oId;
   for (int i = tid; i < C::WN; i += C::NT) {
     int wy = i / C::WW, wx = i - wy * C::WW;
     int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
-    float v = 0.f;
-    if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-      SsimOut so[3];
-      v = reproj_window<C>(X, T, TS, wy, wx, i, g.arith, so);
+    bool inside = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+#pragma unroll
+    for (int pr = 0; pr < XL::NP; ++pr) {
+      F2 v = splat(0.f);
+      if (inside) {
+        PairSums sums;
+        v = reproj_window_pair<C>(X + XL::pair_base(pr, 0), T, TS, wy, wx, i, g.arith, g.one, sums);
+      }
+      Id[(2 * pr) * C::WN + i] = v.x;
+      Id[(2 * pr + 1) * C::WN + i] = v.y;
     }
-    Id[i] = v;
+    if (XL::R) {
+      float v = 0.f;
+      if (inside) {
+        SsimOut so[3];
+        v = reproj_window<C>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so);
+      }
+      Id[(C::F - 1) * C::WN + i] = v;
+    }
   }
 }
 
@@ -176,6 +268,7 @@ VSL_HD void phase_identity(const PhotoParams& p, const GeoConst& g, const TileCt
 template <class C>
 VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int s,
                        int tid) {
+  using XL = XLayout<C>;
   float* X = sm + C::oX;
   float* G = sm + C::oG;
   const int HW = p.H * p.W;
@@ -185,36 +278,47 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
     int ry = i / C::RW, rx = i - ry * C::RW;
     int gy = t.y0 - 2 + ry, gx = t.x0 - 2 + rx;
     bool valid = gy >= -1 && gy <= p.H && gx >= -1 && gx <= p.W;
-    if (!valid) {
+    float val[C::F][3];
 #pragma unroll
-      for (int k = 0; k < C::F * 3; ++k) X[k * C::RN + i] = 0.f;
-      continue;
-    }
-    int v = reflect1(gy, p.H), u = reflect1(gx, p.W);
-    float D = upsample_disp(disp, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s], p.identity_scale[s] != 0, v, u,
-                            g.arith);
-    Cam cam = backproject_pixel(D, invK, u, v, g);
-    bool interior = ry >= 2 && ry < C::TH + 2 && rx >= 2 && rx < C::TW + 2 && gy < p.H && gx < p.W;
-    int j = (ry - 2) * C::TW + (rx - 2);
+    for (int f = 0; f < C::F; ++f)
 #pragma unroll
-    for (int f = 0; f < C::F; ++f) {
-      Proj pr = project_pixel(cam, p.P[f] + t.b * 12, g);
-      Taps tp = bilinear_taps(pr, p.W, p.H);
-      const float* img = p.src[f] + (size_t)t.b * 3 * HW + pr.y0 * p.W + pr.x0;
-      int dx = tp.x1ok ? 1 : 0, dy = tp.y1ok ? p.W : 0;
+      for (int c = 0; c < 3; ++c) val[f][c] = 0.f;
+    if (valid) {
+      int v = reflect1(gy, p.H), u = reflect1(gx, p.W);
+      float D = upsample_disp(disp, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s], p.identity_scale[s] != 0, v, u,
+                              g.arith);
+      Cam cam = backproject_pixel(D, invK, u, v, g);
+      bool interior = ry >= 2 && ry < C::TH + 2 && rx >= 2 && rx < C::TW + 2 && gy < p.H && gx < p.W;
+      int j = (ry - 2) * C::TW + (rx - 2);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* q = img + c * HW;
-        float vnw = q[0], vne = q[dx], vsw = q[dy], vse = q[dy + dx];
-        X[(f * 3 + c) * C::RN + i] = bilinear_value(tp, vnw, vne, vsw, vse, g.arith);
-        if (interior) {
-          // grid_sampler_2d_backward's d out / d(ix, iy); zero where the border clip is active
-          float ddx = pr.inx ? ((vne - vnw) * tp.wy1 + (vse - vsw) * tp.wy0) : 0.f;
-          float ddy = pr.iny ? ((vsw - vnw) * tp.wx1 + (vse - vne) * tp.wx0) : 0.f;
-          G[(f * 6 + c) * C::IN + j] = ddx;
-          G[(f * 6 + 3 + c) * C::IN + j] = ddy;
+      for (int f = 0; f < C::F; ++f) {
+        Proj pr = project_pixel(cam, p.P[f] + t.b * 12, g);
+        Taps tp = bilinear_taps(pr, p.W, p.H);
+        const float* img = p.src[f] + (size_t)t.b * 3 * HW + pr.y0 * p.W + pr.x0;
+        int dx = tp.x1ok ? 1 : 0, dy = tp.y1ok ? p.W : 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* q = img + c * HW;
+          float vnw = q[0], vne = q[dx], vsw = q[dy], vse = q[dy + dx];
+          val[f][c] = bilinear_value(tp, vnw, vne, vsw, vse, g.arith);
+          if (interior) {
+            // grid_sampler_2d_backward's d out / d(ix, iy); zero where the border clip is active
+            float ddx = pr.inx ? ((vne - vnw) * tp.wy1 + (vse - vsw) * tp.wy0) : 0.f;
+            float ddy = pr.iny ? ((vsw - vnw) * tp.wx1 + (vse - vne) * tp.wx0) : 0.f;
+            G[(f * 6 + c) * C::IN + j] = ddx;
+            G[(f * 6 + 3 + c) * C::IN + j] = ddy;
+          }
         }
       }
+    }
+#pragma unroll
+    for (int pr = 0; pr < XL::NP; ++pr)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        reinterpret_cast<F2*>(X + XL::pair_base(pr, c))[i] = f2(val[2 * pr][c], val[2 * pr + 1][c]);
+    if (XL::R) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) X[XL::single_base(c) + i] = val[C::F - 1][c];
     }
   }
 }
@@ -242,24 +346,10 @@ VSL_HD void store_rec(CoefRec* __restrict__ rec, const float coef[9], int idx) {
   *rec = r;
 }
 
-// best identity candidate (trainer.py:654-659: identity + 1e-5 * randn, identity channels first)
-template <class C>
-VSL_HD void identity_candidates(const PhotoParams& p, const TileCtx& t, const float* __restrict__ Id, int s, int i,
-                                int gy, int gx, float& best, int& bidx) {
-  const int HW = p.H * p.W;
-  const float* nz = p.noise[s] + (size_t)t.b * C::F * HW + gy * p.W + gx;
-  best = INFINITY;
-  bidx = -1;
-#pragma unroll
-  for (int f = 0; f < C::F; ++f) {
-    float cand = add_rn(Id[f * C::WN + i], mul_rn(nz[f * HW], 1e-5f));
-    if (cand < best) { best = cand; bidx = f; }
-  }
-}
-
 template <class C>
 VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int s,
                           int tid, ThreadState<C>& ts) {
+  using XL = XLayout<C>;
   const float* T = sm + C::oT;
   const float* TS = sm + C::oTS;
   const float* X = sm + C::oX;
@@ -277,16 +367,39 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
       store_rec(Rec + i, coef, -1);
       continue;
     }
-    float best;
-    int bidx;
-    identity_candidates<C>(p, t, Id, s, i, gy, gx, best, bidx);
+    // identity candidates first (trainer.py:654-659: identity + 1e-5 * randn; cat(identity, reprojection));
+    // strict '<' everywhere: ties keep the lower index, like torch.min
+    float best = INFINITY;
+    int bidx = -1;
+    const float* nz = p.noise[s] + (size_t)t.b * C::F * HW + gy * p.W + gx;
 #pragma unroll
     for (int f = 0; f < C::F; ++f) {
+      float cand = add_rn(Id[f * C::WN + i], mul_rn(nz[f * HW], 1e-5f));
+      if (cand < best) { best = cand; bidx = f; }
+    }
+#pragma unroll
+    for (int pr = 0; pr < XL::NP; ++pr) {
+      PairSums sums;
+      F2 l = reproj_window_pair<C>(X + XL::pair_base(pr, 0), T, TS, wy, wx, i, g.arith, g.one, sums);
+      int win = -1;
+      if (l.x < best) { best = l.x; win = 0; }
+      if (l.y < best) { best = l.y; win = 1; }
+      if (win >= 0) {  // rebuild the winner's SSIM state from its window sums (same ops, same bits)
+        bidx = C::F + 2 * pr + win;
+        SsimOut so[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          so[c] = win == 0 ? ssim_from_sums(sums.sx[c].x, sums.sxx[c].x, sums.sxy[c].x, TS[c * C::WN + i], TS[(3 + c) * C::WN + i])
+                           : ssim_from_sums(sums.sx[c].y, sums.sxx[c].y, sums.sxy[c].y, TS[c * C::WN + i], TS[(3 + c) * C::WN + i]);
+        window_coefs(so, TS, C::WN, i, kc, coef);
+      }
+    }
+    if (XL::R) {
       SsimOut so[3];
-      float l = reproj_window<C>(X + f * 3 * C::RN, T, TS, wy, wx, i, g.arith, so);
-      if (l < best) {  // strict: ties keep the lower index, like torch.min
+      float l = reproj_window<C>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so);
+      if (l < best) {
         best = l;
-        bidx = C::F + f;
+        bidx = 2 * C::F - 1;
         window_coefs(so, TS, C::WN, i, kc, coef);
       }
     }
@@ -302,12 +415,14 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
 
 #if defined(__CUDACC__)
 // Two-source-frame variant (frames [0,-1,1], the reference default): lanes 2k / 2k+1 evaluate frame 0 / 1
-// of the same window and exchange the losses by shuffle, so the 2*WN (window, frame) items fill the CTA's
-// threads evenly (95 % of the slots instead of 80 %).  Same decisions as phase_windows.
+// of the same window (the two halves of the pair storage) and exchange the losses by shuffle, so the
+// 2*WN (window, frame) items fill the CTA's threads evenly (95 % of the slots instead of 80 %).  Same
+// decisions as phase_windows; measured faster than the packed-pair evaluation for F = 2.
 template <class C>
 __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const GeoConst& g, const TileCtx& t,
                                                      float* __restrict__ sm, int s, int tid, ThreadState<C>& ts) {
   static_assert(C::F == 2, "paired variant is for two source frames");
+  using XL = XLayout<C>;
   const float* T = sm + C::oT;
   const float* TS = sm + C::oTS;
   const float* X = sm + C::oX;
@@ -323,11 +438,13 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
     int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
     const bool inside = live && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
     float best = INFINITY, l = INFINITY;
-    int bidx = -1;
     SsimOut so[3];
     if (inside) {
-      identity_candidates<C>(p, t, Id, s, i, gy, gx, best, bidx);
-      l = reproj_window<C>(X + f * 3 * C::RN, T, TS, wy, wx, i, g.arith, so);
+      const float* nz = p.noise[s] + (size_t)t.b * 2 * HW + gy * p.W + gx;
+      float c0 = add_rn(Id[i], mul_rn(nz[0], 1e-5f));
+      float c1 = add_rn(Id[C::WN + i], mul_rn(nz[HW], 1e-5f));
+      best = c1 < c0 ? c1 : c0;
+      l = reproj_window<C, 2>(X + XL::pair_base(0, 0) + f, 2 * C::RN, T, TS, wy, wx, i, g.arith, so);
     }
     const float other = __shfl_xor_sync(0xffffffffu, l, 1);
     if (!live) continue;
@@ -363,6 +480,7 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
 template <class C>
 VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int s,
                            int tid, ThreadState<C>& ts) {
+  using XL = XLayout<C>;
   const float* T = sm + C::oT;
   const float* X = sm + C::oX;
   const CoefRec* Rec = reinterpret_cast<const CoefRec*>(sm + C::oCoef);
@@ -414,11 +532,11 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
         float gix = 0.f, giy = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float xq = X[(f * 3 + c) * C::RN + center], yq = T[c * C::RN + center];
-          float g = acc[f][c] + 2.f * xq * acc[f][3 + c] + yq * acc[f][6 + c];
-          if (own == f) g += (xq > yq) ? kl1 : ((xq < yq) ? -kl1 : 0.f);
-          gix += g * G[(f * 6 + c) * C::IN + j];
-          giy += g * G[(f * 6 + 3 + c) * C::IN + j];
+          float xq = X[XL::at(f, c, center)], yq = T[c * C::RN + center];
+          float gc = acc[f][c] + 2.f * xq * acc[f][3 + c] + yq * acc[f][6 + c];
+          if (own == f) gc += (xq > yq) ? kl1 : ((xq < yq) ? -kl1 : 0.f);
+          gix += gc * G[(f * 6 + c) * C::IN + j];
+          giy += gc * G[(f * 6 + 3 + c) * C::IN + j];
         }
         const float* P = p.P[f] + t.b * 12;
         float c0 = P[0] * cam.X + P[1] * cam.Y + P[2] * cam.Z + P[3];
