@@ -27,7 +27,7 @@ static void run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
         t.b = b; t.x0 = tx * C::TW; t.y0 = ty * C::TH;
         t.cta = (b * tiles_y + ty) * tiles_x + tx;
         size_t img_off = (size_t)b * 3 * p.H * p.W;
-        for (int tid = 0; tid < C::NT; ++tid) phase_load_region<C>(p, t, p.tgt + img_off, sm.data() + C::oT, tid);
+        for (int tid = 0; tid < C::NT; ++tid) phase_load_region<C>(p, t, (const float*)p.tgt + img_off, sm.data() + C::oT, tid);
         for (int tid = 0; tid < C::NT; ++tid) phase_target_stats<C>(p, t, sm.data(), tid);
         for (int tid = 0; tid < C::NT; ++tid) phase_load_sources<C>(p, t, sm.data(), tid);
         for (int tid = 0; tid < C::NT; ++tid) phase_identity<C>(p, p.g, t, sm.data(), tid);
@@ -57,7 +57,7 @@ extern "C" int vsl_emul_photometric(int B, int H, int W, int S, int F, const int
   PhotoParams p;
   std::memset(&p, 0, sizeof(p));
   p.tgt = tgt; p.invK = invK; p.B = B; p.H = H; p.W = W; p.S = S; p.F = F;
-  p.g.one = 1.0f; p.g.min_disp = min_disp; p.g.disp_range = disp_range; p.g.eps = eps; p.g.W = W; p.g.H = H;
+  p.g.one = 1.0f; p.automask = 1; p.no_ssim = 0; p.g.min_disp = min_disp; p.g.disp_range = disp_range; p.g.eps = eps; p.g.W = W; p.g.H = H;
   p.g.wm1 = (float)(W - 1); p.g.hm1 = (float)(H - 1);
   p.g.inv_wm1 = 1.0f / p.g.wm1; p.g.inv_hm1 = 1.0f / p.g.hm1; p.g.arith = arith;
   p.wpix = 1.0f / ((float)B * H * W);

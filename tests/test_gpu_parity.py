@@ -80,6 +80,12 @@ CASES = {
     "ragged_tiles_40x72": (3, 40, 72, [0, -1, 1], synthetic.K_LUNG, "iid", 6, {}),   # not a multiple of the 32x16 tile
     "two_scales": (2, 64, 96, [0, 1], synthetic.K_KITTI, "smooth", 7, {"scales": [0, 2]}),
     "single_scale": (1, 32, 64, [0, -1, 1], synthetic.K_KITTI, "iid", 8, {"scales": [0]}),
+    "kitti_hires_c4_b2": (2, 320, 1024, [0, -1, 1], synthetic.K_KITTI, "smooth", 9, {}),
+    "no_ssim": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "iid", 10, {"no_ssim": True}),
+    "no_ssim_stereo": (2, 64, 96, [0, -1, 1, "s"], synthetic.K_KITTI, "smooth", 11, {"no_ssim": True}),
+    "no_automask": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "iid", 12, {"disable_automasking": True}),
+    "no_automask_one_frame": (2, 64, 96, [0, 1], synthetic.K_KITTI, "smooth", 13, {"disable_automasking": True}),
+    "no_automask_stereo": (2, 64, 96, [0, -1, 1, "s"], synthetic.K_KITTI, "iid", 14, {"disable_automasking": True}),
 }
 
 
@@ -106,9 +112,13 @@ def test_fused_path_matches_oracle(name):
             a, b = tap_indices(out[("sample", f, s)], H, W), tap_indices(ref_out[("sample", f, s)], H, W)
             assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
             assert torch.equal(out[("color", f, s)], ref_out[("color", f, s)]), ("color", f, s)
-            assert out[("color_identity", f, s)] is inputs[("color", f, 0)]
+            if not opt.disable_automasking:
+                assert out[("color_identity", f, s)] is inputs[("color", f, 0)]
         k = "identity_selection/%d" % s
-        assert torch.equal(out[k], ref_out[k]), k
+        if opt.disable_automasking:  # the reference writes no mask then (trainer.py:668-670)
+            assert k not in out and k not in ref_out
+        else:
+            assert torch.equal(out[k], ref_out[k]), k
     assert set(losses) == set(ref_losses)
     for k in ref_losses:  # 1e-6 relative (north_star asks 1e-5)
         assert abs(losses[k].item() - ref_losses[k].item()) <= 1e-6 * abs(ref_losses[k].item()), k
@@ -166,6 +176,32 @@ def test_golden_fixtures(case):
         assert list(g["grads"].keys()) == list(leaves.keys())
         err = ((got - ref).norm() / ref.norm()).item()
         assert err <= 2e-2, (k, err)  # flips of ~1e-4 of the arg-min / floor decisions move the gradient by ~1 %
+
+
+@pytest.mark.parametrize("frames", [[0, -1, 1, "s"], [0, -1, 1]])
+def test_bf16_image_storage(frames):
+    """BASELINE config 3: colour images stored as bf16, every arithmetic step in fp32.  The oracle gets the
+    same bf16-rounded images up-cast to fp32, so results must match like the fp32 path."""
+    B, H, W = 2, 192, 640
+    opt = O.make_opt(height=H, width=W, batch_size=B, frame_ids=list(frames))
+    inputs, outputs, leaves = synthetic.make_batch(B, H, W, frames, seed=21, family="smooth", device=DEV)
+    in16 = {k: (v.bfloat16() if k[0] == "color" else v) for k, v in inputs.items()}
+    in32 = {k: (v.float() if k[0] == "color" else v) for k, v in in16.items()}
+    ref_out, ref_losses, ref_g = run_oracle(opt, in32, outputs, leaves)
+    out, losses, g = run_ours(opt, in16, outputs, leaves)
+    for s in opt.scales:
+        for f in frames[1:]:
+            assert torch.equal(out[("sample", f, s)], ref_out[("sample", f, s)])
+            assert torch.equal(out[("color", f, s)], ref_out[("color", f, s)])
+        assert torch.equal(out["identity_selection/%d" % s], ref_out["identity_selection/%d" % s])
+    for k in ref_losses:
+        assert abs(losses[k].item() - ref_losses[k].item()) <= 1e-6 * abs(ref_losses[k].item()), k
+    for k in ref_g:  # north_star allows 1e-2 in bf16 mode; with identical inputs the fp32 bound holds
+        assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
+    with pytest.raises(TypeError):  # mixed storage types are rejected
+        mixed = dict(in16)
+        mixed[("color", -1, 0)] = inputs[("color", -1, 0)]
+        run_ours(opt, mixed, outputs, leaves)
 
 
 def test_rng_stream_is_consumed_like_the_reference():
@@ -343,8 +379,9 @@ def test_errors_are_loud():
     cpu_inputs[("color", 0, 0)] = inputs[("color", 0, 0)].cpu()
     with pytest.raises(_lib.VslError):
         path.compute_losses(cpu_inputs, out)
-    with pytest.raises(NotImplementedError):
-        LossPath(make_opt(avg_reprojection=True), device=DEV).generate_images_pred(inputs, out)
+    for flag in ("avg_reprojection", "v1_multiscale", "predictive_mask"):
+        with pytest.raises(NotImplementedError):
+            LossPath(make_opt(**{flag: True}), device=DEV).generate_images_pred(inputs, out)
     lib = _lib.load()
     d = _lib.VslDesc()
     assert lib.vsl_loss_forward_backward(ctypes.byref(d), None, None, 0, None) == -1

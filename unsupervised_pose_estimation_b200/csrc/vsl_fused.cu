@@ -30,7 +30,7 @@ constexpr int kSmallNT = 256;
 
 struct SmallParams {  // smoothness + epilogue
   const float* disp[kMaxScales];
-  const float* img[kMaxScales];   // target pyramid
+  const void* img[kMaxScales];    // target pyramid (fp32 or bf16)
   float* gsmooth[kMaxScales];     // d smooth_s / d disp_s
   float* gphoto[kMaxScales];      // d min_loss_s / d disp_s
   const float* gD[kMaxScales];    // full-res adjoint input (null for identity scales)
@@ -91,12 +91,15 @@ __device__ __forceinline__ float image_mean(const SmallParams& p, int s, int b, 
 }
 
 // edge weight exp(-mean_c |img(a) - img(b)|)  (layers.py:293-297)
-__device__ __forceinline__ float edge_weight(const float* img, int n, int ia, int ib) {
-  float g = fabsf(img[ia] - img[ib]) + fabsf(img[n + ia] - img[n + ib]) + fabsf(img[2 * n + ia] - img[2 * n + ib]);
+template <class Img>
+__device__ __forceinline__ float edge_weight(const Img* img, int n, int ia, int ib) {
+  float g = fabsf(ldimg(img, ia) - ldimg(img, ib)) + fabsf(ldimg(img, n + ia) - ldimg(img, n + ib)) +
+            fabsf(ldimg(img, 2 * n + ia) - ldimg(img, 2 * n + ib));
   return expf(-g * (1.0f / 3.0f));
 }
 __device__ __forceinline__ float sgnf(float t) { return t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f); }
 
+template <class Img>
 __global__ void __launch_bounds__(kSmallNT) k_smooth_terms(const SmallParams p) {
   __shared__ float scratch[kSmallNT / 32];
   int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kSmallNT) k_smooth_terms(const SmallParams p) 
   if (chunk * kChunk >= n) return;
   float inv = 1.0f / (image_mean(p, s, b, scratch) + 1e-7f);
   const float* d = p.disp[s] + (size_t)b * n;
-  const float* img = p.img[s] + (size_t)b * 3 * n;
+  const Img* img = (const Img*)p.img[s] + (size_t)b * 3 * n;
   float* g_out = p.gsmooth[s] + (size_t)b * n;
   float cx = 1.0f / ((float)p.B * h * (w - 1)), cy = 1.0f / ((float)p.B * (h - 1) * w);
   float sx = 0.f, sy = 0.f, sgd = 0.f;
@@ -157,12 +160,14 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
   const int tid = threadIdx.x;
   const size_t img_off = (size_t)t.b * 3 * p.H * p.W;
 
-  phase_load_region<C>(p, t, p.tgt + img_off, sm + C::oT, tid);
+  phase_load_region<C>(p, t, (const typename C::Img*)p.tgt + img_off, sm + C::oT, tid);
   __syncthreads();
   phase_target_stats<C>(p, t, sm, tid);
-  phase_load_sources<C>(p, t, sm, tid);
-  __syncthreads();
-  phase_identity<C>(p, g, t, sm, tid);
+  if (p.automask) {
+    phase_load_sources<C>(p, t, sm, tid);
+    __syncthreads();
+    phase_identity<C>(p, g, t, sm, tid);
+  }
 
   float* red = sm + C::oRed;
   for (int s = 0; s < p.S; ++s) {
@@ -344,13 +349,14 @@ __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
 // ---------------------------------------------------------------------------------------------
 // side outputs of generate_images_pred for one scale (trainer.py:500-537)
 struct WarpParams {
-  const float* disp; const float* invK; const float* P[kMaxSrc]; const float* src[kMaxSrc];
+  const float* disp; const float* invK; const float* P[kMaxSrc]; const void* src[kMaxSrc];
   float* depth; float* sample[kMaxSrc]; float* color[kMaxSrc];
   int B, H, W, F, hs, ws, identity;
   float scale_h, scale_w;
   GeoConst g;
 };
 
+template <class Img>
 __global__ void __launch_bounds__(256) k_warp_forward(const WarpParams p) {
   int HW = p.H * p.W;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -369,11 +375,12 @@ __global__ void __launch_bounds__(256) k_warp_forward(const WarpParams p) {
     }
     if (p.color[f]) {
       Taps tp = bilinear_taps(pr, p.W, p.H);
-      const float* img = p.src[f] + (size_t)b * 3 * HW + pr.y0 * p.W + pr.x0;
+      const Img* img = (const Img*)p.src[f] + (size_t)b * 3 * HW + pr.y0 * p.W + pr.x0;
       int dx = tp.x1ok ? 1 : 0, dy = tp.y1ok ? p.W : 0;
       for (int c = 0; c < 3; ++c) {
-        const float* q = img + c * HW;
-        p.color[f][(size_t)b * 3 * HW + c * HW + i] = bilinear_value(tp, q[0], q[dx], q[dy], q[dy + dx], p.g.arith);
+        const Img* q = img + c * HW;
+        p.color[f][(size_t)b * 3 * HW + c * HW + i] =
+            bilinear_value(tp, ldimg(q, 0), ldimg(q, dx), ldimg(q, dy), ldimg(q, dy + dx), p.g.arith);
       }
     }
   }
@@ -507,16 +514,18 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
                                     size_t workspace_bytes, void* stream, void* event_before, void* event_after) {
   if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
   if (!buf || !workspace) return VSL_ERR_NULL_POINTER;
-  if (d->flags != VSL_FLAG_AUTOMASK) return VSL_ERR_UNSUPPORTED;   // default reference flags only
-  if (d->image_dtype != VSL_DTYPE_F32) return VSL_ERR_UNSUPPORTED;
+  if (d->flags & ~(VSL_FLAG_AUTOMASK | VSL_FLAG_NO_SSIM)) return VSL_ERR_UNSUPPORTED;  // avg / v1: not in this kernel
+  if (d->image_dtype != VSL_DTYPE_F32 && d->image_dtype != VSL_DTYPE_BF16) return VSL_ERR_UNSUPPORTED;
   if (d->num_src > 3) return VSL_ERR_UNSUPPORTED;
+  const bool automask = (d->flags & VSL_FLAG_AUTOMASK) != 0;
   const int S = d->num_scales, F = d->num_src;
   Plan pl = make_plan(d);
   if (workspace_bytes < pl.total) return VSL_ERR_WORKSPACE;
   if (((uintptr_t)workspace & 15u) != 0) return VSL_ERR_MISALIGNED;
   if (!buf->inv_K || !buf->losses || !buf->grad_P) return VSL_ERR_NULL_POINTER;
   for (int s = 0; s < S; ++s)
-    if (!buf->target[s] || !buf->disp[s] || !buf->noise[s] || !buf->grad_disp_photo[s] || !buf->grad_disp_smooth[s])
+    if (!buf->target[s] || !buf->disp[s] || (automask && !buf->noise[s]) || !buf->grad_disp_photo[s] ||
+        !buf->grad_disp_smooth[s])
       return VSL_ERR_NULL_POINTER;
   for (int f = 0; f < F; ++f)
     if (!buf->source[f] || !buf->P[f]) return VSL_ERR_NULL_POINTER;
@@ -527,13 +536,15 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
 
   SmallParams sp = {};
   PhotoParams pp = {};
-  pp.tgt = (const float*)buf->target[0];
+  pp.tgt = buf->target[0];
+  pp.automask = automask ? 1 : 0;
+  pp.no_ssim = (d->flags & VSL_FLAG_NO_SSIM) ? 1 : 0;
   pp.invK = buf->inv_K;
   pp.B = sp.B = d->batch; pp.H = sp.H = d->height; pp.W = sp.W = d->width; pp.S = sp.S = S; pp.F = sp.F = F;
   pp.g = make_geo(d);
   pp.wpix = 1.0f / ((float)d->batch * d->height * d->width);
   pp.partials = ws + pl.off_partials;
-  for (int f = 0; f < F; ++f) { pp.src[f] = (const float*)buf->source[f]; pp.P[f] = buf->P[f]; }
+  for (int f = 0; f < F; ++f) { pp.src[f] = buf->source[f]; pp.P[f] = buf->P[f]; }
   for (int s = 0; s < S; ++s) {
     int e = d->scale_ids[s];
     int hs = d->height >> e, wsz = d->width >> e;
@@ -543,10 +554,10 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     pp.identity_scale[s] = sp.identity_scale[s] = (e == 0);
     pp.disp[s] = sp.disp[s] = buf->disp[s];
     pp.noise[s] = buf->noise[s];
-    pp.mask[s] = buf->mask[s];
+    pp.mask[s] = automask ? buf->mask[s] : nullptr;
     pp.gD[s] = (e == 0) ? buf->grad_disp_photo[s] : ws + pl.off_gD[s];
     sp.gD[s] = (e == 0) ? nullptr : ws + pl.off_gD[s];
-    sp.img[s] = (const float*)buf->target[s];
+    sp.img[s] = buf->target[s];
     sp.gsmooth[s] = buf->grad_disp_smooth[s];
     sp.gphoto[s] = buf->grad_disp_photo[s];
     sp.scale_id[s] = e;
@@ -568,13 +579,20 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   dim3 sgrid(pl.chunks0, d->batch, S);
   k_smooth_mean<<<sgrid, kSmallNT, 0, st>>>(sp);
   VSL_CUDA_OK(cudaGetLastError());
-  k_smooth_terms<<<sgrid, kSmallNT, 0, st>>>(sp);
+  if (d->image_dtype == VSL_DTYPE_BF16) k_smooth_terms<bf16_t><<<sgrid, kSmallNT, 0, st>>>(sp);
+  else k_smooth_terms<float><<<sgrid, kSmallNT, 0, st>>>(sp);
   VSL_CUDA_OK(cudaGetLastError());
   if (event_before) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_before, st));
   int rc;
-  if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256>>(pp, pl, d->batch, st);
-  else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256>>(pp, pl, d->batch, st);
-  else rc = launch_photometric<TileCfg<32, 16, 3, 256>>(pp, pl, d->batch, st);
+  if (d->image_dtype == VSL_DTYPE_BF16) {
+    if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256, bf16_t>>(pp, pl, d->batch, st);
+    else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, bf16_t>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, 16, 3, 256, bf16_t>>(pp, pl, d->batch, st);
+  } else {
+    if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256>>(pp, pl, d->batch, st);
+    else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, 16, 3, 256>>(pp, pl, d->batch, st);
+  }
   if (rc != VSL_OK) return rc;
   if (event_after) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after, st));
   {
@@ -619,7 +637,8 @@ int vsl_warp_forward(const VslDesc* d, int scale_index, const float* disp, const
                      float* const sample[VSL_MAX_SRC], float* const color[VSL_MAX_SRC], void* stream) {
   if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
   if (scale_index < 0 || scale_index >= d->num_scales) return VSL_ERR_BAD_DESC;
-  if (d->image_dtype != VSL_DTYPE_F32 || (d->flags & VSL_FLAG_V1_MULTISCALE)) return VSL_ERR_UNSUPPORTED;
+  if ((d->image_dtype != VSL_DTYPE_F32 && d->image_dtype != VSL_DTYPE_BF16) || (d->flags & VSL_FLAG_V1_MULTISCALE))
+    return VSL_ERR_UNSUPPORTED;
   if (!disp || !inv_K || !P || !source) return VSL_ERR_NULL_POINTER;
   WarpParams wp = {};
   int e = d->scale_ids[scale_index];
@@ -631,13 +650,14 @@ int vsl_warp_forward(const VslDesc* d, int scale_index, const float* disp, const
   for (int f = 0; f < d->num_src; ++f) {
     if (!P[f]) return VSL_ERR_NULL_POINTER;
     wp.P[f] = P[f];
-    wp.src[f] = (const float*)source[f];
+    wp.src[f] = source[f];
     wp.sample[f] = sample ? sample[f] : nullptr;
     wp.color[f] = color ? color[f] : nullptr;
     if (wp.color[f] && !wp.src[f]) return VSL_ERR_NULL_POINTER;
   }
   size_t n = (size_t)d->batch * d->height * d->width;
-  k_warp_forward<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wp);
+  if (d->image_dtype == VSL_DTYPE_BF16) k_warp_forward<bf16_t><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wp);
+  else k_warp_forward<float><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wp);
   VSL_CUDA_OK(cudaGetLastError());
   return VSL_OK;
 }

@@ -39,6 +39,19 @@ VSL_HD float rcp_rn(float a) { volatile float r = 1.0f / a; return r; }
 VSL_HD float fast_rcp(float a) { return 1.0f / a; }
 #endif
 
+// ---- image storage: fp32 or bf16 (arithmetic is always fp32; bf16 -> fp32 is exact) ---------------
+struct bf16_t { uint16_t bits; };
+VSL_HD float ldimg(const float* __restrict__ p, size_t i) { return p[i]; }
+VSL_HD float ldimg(const bf16_t* __restrict__ p, size_t i) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float((uint32_t)p[i].bits << 16);
+#else
+  union { uint32_t u; float f; } c;
+  c.u = (uint32_t)p[i].bits << 16;
+  return c.f;
+#endif
+}
+
 // ---- packed pairs: two independent fp32 values per operation -------------------------------------
 // sm_100 issues add/mul/fma on fp32 PAIRS as one instruction (FADD2 / FMUL2 / FFMA2), each half rounded
 // to nearest like the scalar op.  The kernel is issue-bound, so evaluating two source frames of one SSIM

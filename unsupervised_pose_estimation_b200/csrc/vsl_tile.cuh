@@ -18,8 +18,8 @@ constexpr int kMaxScales = 4;
 constexpr int kMaxSrc = 4;
 
 struct PhotoParams {
-  const float* tgt;               // [B,3,H,W]
-  const float* src[kMaxSrc];      // [B,3,H,W]
+  const void* tgt;                // [B,3,H,W]  fp32 or bf16 (TileCfg::Img)
+  const void* src[kMaxSrc];       // [B,3,H,W]
   const float* disp[kMaxScales];  // [B,1,hs,ws]
   const float* invK;              // [B,4,4]
   const float* P[kMaxSrc];        // [B,3,4]
@@ -33,10 +33,13 @@ struct PhotoParams {
   int identity_scale[kMaxScales];  // up-sample is the identity (level size == H x W)
   GeoConst g;
   float wpix;                     // 1 / (B*H*W): weight of one pixel in min_loss/s
+  int automask;                   // 0: --disable_automasking (no identity candidates, no noise, no mask)
+  int no_ssim;                    // 1: --no_ssim (reprojection loss = mean_c L1)
 };
 
-template <int TW_, int TH_, int F_, int NT_>
+template <int TW_, int TH_, int F_, int NT_, class Img_ = float>
 struct TileCfg {
+  typedef Img_ Img;  // storage type of the colour images
   static constexpr int TW = TW_, TH = TH_, F = F_, NT = NT_;
   static constexpr int RW = TW + 4, RH = TH + 4, RN = RW * RH;  // region: tile + 2 halo (warped / target pixels)
   static constexpr int WW = TW + 2, WH = TH + 2, WN = WW * WH;  // windows: tile + 1 halo (SSIM centres)
@@ -77,7 +80,7 @@ struct TileCtx {
 
 // ---- phase: load an image tile + 2 halo into a region buffer, reflect-mapped --------------------
 template <class C>
-VSL_HD void phase_load_region(const PhotoParams& p, const TileCtx& t, const float* __restrict__ img_b,
+VSL_HD void phase_load_region(const PhotoParams& p, const TileCtx& t, const typename C::Img* __restrict__ img_b,
                               float* __restrict__ dst, int tid) {
   const int HW = p.H * p.W;
   for (int i = tid; i < C::RN; i += C::NT) {
@@ -86,7 +89,7 @@ VSL_HD void phase_load_region(const PhotoParams& p, const TileCtx& t, const floa
     bool valid = gy >= -1 && gy <= p.H && gx >= -1 && gx <= p.W;
     int o = reflect1(gy, p.H) * p.W + reflect1(gx, p.W);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) dst[c * C::RN + i] = valid ? img_b[c * HW + o] : 0.f;
+    for (int c = 0; c < 3; ++c) dst[c * C::RN + i] = valid ? ldimg(img_b, (size_t)c * HW + o) : 0.f;
   }
 }
 
@@ -142,9 +145,18 @@ struct XLayout {
 // (trainer.py:546-553) and leaves the per-channel SSIM state in `so`.
 template <class C, int XS = 1>
 VSL_HD float reproj_window(const float* __restrict__ X, int cs, const float* __restrict__ T,
-                           const float* __restrict__ TS, int wy, int wx, int widx, int arith, SsimOut so[3]) {
+                           const float* __restrict__ TS, int wy, int wx, int widx, int arith, SsimOut so[3],
+                           bool no_ssim = false) {
   float ss[3], l1[3];
   const int center = (wy + 1) * C::RW + (wx + 1);
+  if (no_ssim) {  // trainer.py:549-550: reprojection loss = mean_c |target - pred|
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      l1[c] = fabsf(sub_rn(T[c * C::RN + center], X[c * cs + XS * center]));
+      so[c].live = false;
+    }
+    return mean3(l1[0], l1[1], l1[2], arith);
+  }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float* x = X + c * cs + XS * center;
@@ -175,10 +187,18 @@ struct PairSums { F2 sx[3], sxx[3], sxy[3]; };
 template <class C>
 VSL_HD F2 reproj_window_pair(const float* __restrict__ X2, const float* __restrict__ T,
                              const float* __restrict__ TS, int wy, int wx, int widx, int arith, float onef,
-                             PairSums& sums) {
+                             PairSums& sums, bool no_ssim = false) {
   F2 ss[3], l1[3];
   const F2 one = splat(onef);
   const int center = (wy + 1) * C::RW + (wx + 1);
+  if (no_ssim) {  // trainer.py:549-550
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      F2 d = sub2(splat(T[c * C::RN + center]), reinterpret_cast<const F2*>(X2 + c * 2 * C::RN)[center]);
+      l1[c] = f2(fabsf(d.x), fabsf(d.y));
+    }
+    return mean3_2(l1[0], l1[1], l1[2], arith);
+  }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const F2* x = reinterpret_cast<const F2*>(X2 + c * 2 * C::RN) + center;
@@ -221,12 +241,14 @@ VSL_HD void phase_load_sources(const PhotoParams& p, const TileCtx& t, float* __
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         F2 v = splat(0.f);
-        if (valid) v = f2(p.src[2 * pr][img_off + c * HW + o], p.src[2 * pr + 1][img_off + c * HW + o]);
+        if (valid) v = f2(ldimg((const typename C::Img*)p.src[2 * pr], img_off + c * HW + o),
+                          ldimg((const typename C::Img*)p.src[2 * pr + 1], img_off + c * HW + o));
         reinterpret_cast<F2*>(X + XL::pair_base(pr, c))[i] = v;
       }
     if (XL::R) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) X[XL::single_base(c) + i] = valid ? p.src[C::F - 1][img_off + c * HW + o] : 0.f;
+      for (int c = 0; c < 3; ++c)
+        X[XL::single_base(c) + i] = valid ? ldimg((const typename C::Img*)p.src[C::F - 1], img_off + c * HW + o) : 0.f;
     }
   }
 }
@@ -248,7 +270,7 @@ VSL_HD void phase_identity(const PhotoParams& p, const GeoConst& g, const TileCt
       F2 v = splat(0.f);
       if (inside) {
         PairSums sums;
-        v = reproj_window_pair<C>(X + XL::pair_base(pr, 0), T, TS, wy, wx, i, g.arith, g.one, sums);
+        v = reproj_window_pair<C>(X + XL::pair_base(pr, 0), T, TS, wy, wx, i, g.arith, g.one, sums, p.no_ssim != 0);
       }
       Id[(2 * pr) * C::WN + i] = v.x;
       Id[(2 * pr + 1) * C::WN + i] = v.y;
@@ -257,7 +279,7 @@ VSL_HD void phase_identity(const PhotoParams& p, const GeoConst& g, const TileCt
       float v = 0.f;
       if (inside) {
         SsimOut so[3];
-        v = reproj_window<C>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so);
+        v = reproj_window<C>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
       }
       Id[(C::F - 1) * C::WN + i] = v;
     }
@@ -294,12 +316,12 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
       for (int f = 0; f < C::F; ++f) {
         Proj pr = project_pixel(cam, p.P[f] + t.b * 12, g);
         Taps tp = bilinear_taps(pr, p.W, p.H);
-        const float* img = p.src[f] + (size_t)t.b * 3 * HW + pr.y0 * p.W + pr.x0;
+        const typename C::Img* img = (const typename C::Img*)p.src[f] + (size_t)t.b * 3 * HW + pr.y0 * p.W + pr.x0;
         int dx = tp.x1ok ? 1 : 0, dy = tp.y1ok ? p.W : 0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float* q = img + c * HW;
-          float vnw = q[0], vne = q[dx], vsw = q[dy], vse = q[dy + dx];
+          const typename C::Img* q = img + c * HW;
+          float vnw = ldimg(q, 0), vne = ldimg(q, dx), vsw = ldimg(q, dy), vse = ldimg(q, dy + dx);
           val[f][c] = bilinear_value(tp, vnw, vne, vsw, vse, g.arith);
           if (interior) {
             // grid_sampler_2d_backward's d out / d(ix, iy); zero where the border clip is active
@@ -371,21 +393,23 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
     // strict '<' everywhere: ties keep the lower index, like torch.min
     float best = INFINITY;
     int bidx = -1;
-    const float* nz = p.noise[s] + (size_t)t.b * C::F * HW + gy * p.W + gx;
+    if (p.automask) {
+      const float* nz = p.noise[s] + (size_t)t.b * C::F * HW + gy * p.W + gx;
 #pragma unroll
-    for (int f = 0; f < C::F; ++f) {
-      float cand = add_rn(Id[f * C::WN + i], mul_rn(nz[f * HW], 1e-5f));
-      if (cand < best) { best = cand; bidx = f; }
+      for (int f = 0; f < C::F; ++f) {
+        float cand = add_rn(Id[f * C::WN + i], mul_rn(nz[f * HW], 1e-5f));
+        if (cand < best) { best = cand; bidx = f; }
+      }
     }
 #pragma unroll
     for (int pr = 0; pr < XL::NP; ++pr) {
       PairSums sums;
-      F2 l = reproj_window_pair<C>(X + XL::pair_base(pr, 0), T, TS, wy, wx, i, g.arith, g.one, sums);
+      F2 l = reproj_window_pair<C>(X + XL::pair_base(pr, 0), T, TS, wy, wx, i, g.arith, g.one, sums, p.no_ssim != 0);
       int win = -1;
       if (l.x < best) { best = l.x; win = 0; }
       if (l.y < best) { best = l.y; win = 1; }
-      if (win >= 0) {  // rebuild the winner's SSIM state from its window sums (same ops, same bits)
-        bidx = C::F + 2 * pr + win;
+      if (win >= 0) bidx = C::F + 2 * pr + win;
+      if (win >= 0 && !p.no_ssim) {  // rebuild the winner's SSIM state from its window sums (same ops, same bits)
         SsimOut so[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
@@ -396,11 +420,13 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
     }
     if (XL::R) {
       SsimOut so[3];
-      float l = reproj_window<C>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so);
+      float l = reproj_window<C>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
       if (l < best) {
         best = l;
         bidx = 2 * C::F - 1;
-        window_coefs(so, TS, C::WN, i, kc, coef);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) coef[k] = 0.f;  // a pair frame may have set them before losing to this one
+        if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc, coef);
       }
     }
     bool warped = bidx >= C::F;
@@ -440,11 +466,13 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
     float best = INFINITY, l = INFINITY;
     SsimOut so[3];
     if (inside) {
-      const float* nz = p.noise[s] + (size_t)t.b * 2 * HW + gy * p.W + gx;
-      float c0 = add_rn(Id[i], mul_rn(nz[0], 1e-5f));
-      float c1 = add_rn(Id[C::WN + i], mul_rn(nz[HW], 1e-5f));
-      best = c1 < c0 ? c1 : c0;
-      l = reproj_window<C, 2>(X + XL::pair_base(0, 0) + f, 2 * C::RN, T, TS, wy, wx, i, g.arith, so);
+      if (p.automask) {
+        const float* nz = p.noise[s] + (size_t)t.b * 2 * HW + gy * p.W + gx;
+        float c0 = add_rn(Id[i], mul_rn(nz[0], 1e-5f));
+        float c1 = add_rn(Id[C::WN + i], mul_rn(nz[HW], 1e-5f));
+        best = c1 < c0 ? c1 : c0;
+      }
+      l = reproj_window<C, 2>(X + XL::pair_base(0, 0) + f, 2 * C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
     }
     const float other = __shfl_xor_sync(0xffffffffu, l, 1);
     if (!live) continue;
@@ -460,7 +488,7 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
 #pragma unroll
     for (int k = 0; k < 9; ++k) coef[k] = 0.f;
     if (win == f) {
-      window_coefs(so, TS, C::WN, i, kc, coef);
+      if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc, coef);
       store_rec(Rec + i, coef, f);
     } else if (win < 0 && f == 0) {
       store_rec(Rec + i, coef, -1);
@@ -488,7 +516,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
   const int HW = p.H * p.W;
   const float* invK = p.invK + t.b * 16;
   const float* disp = p.disp[s] + (size_t)t.b * p.hs[s] * p.ws[s];
-  const float kl1 = p.wpix * (0.15f / 3.0f);
+  const float kl1 = p.no_ssim ? p.wpix * (1.0f / 3.0f) : p.wpix * (0.15f / 3.0f);
   for (int j = tid; j < C::IN; j += C::NT) {
     int iy = j / C::TW, ix = j - iy * C::TW;
     int gy = t.y0 + iy, gx = t.x0 + ix;

@@ -18,14 +18,14 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _dev(t, name):
+def _dev(t, name, dtype=torch.float32):
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a tensor" % name)
     if not t.is_cuda:
         raise _lib.VslError(
             "%s is on %s: the view-synthesis loss path only runs on CUDA (no CPU fallback)" % (name, t.device))
-    if t.dtype != torch.float32:
-        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
     return t.contiguous()
 
 
@@ -88,7 +88,7 @@ class FusedLossPlan:
     per plan (calls are stream-ordered)."""
 
     def __init__(self, batch, height, width, scales, num_src, min_depth, max_depth,
-                 disparity_smoothness, flags=_lib.FLAG_AUTOMASK, arith=0):
+                 disparity_smoothness, flags=_lib.FLAG_AUTOMASK, arith=0, image_dtype=torch.float32):
         scales = list(scales)
         if not (1 <= len(scales) <= VSL_MAX_SCALES):
             raise ValueError("1..%d scales supported" % VSL_MAX_SCALES)
@@ -104,7 +104,11 @@ class FusedLossPlan:
             d.scale_ids[i] = int(s)
         d.num_src = self.num_src
         d.flags = int(flags)
-        d.image_dtype = _lib.DTYPE_F32
+        if image_dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("colour images must be stored as float32 or bfloat16")
+        self.image_dtype = image_dtype
+        self.automask = bool(flags & _lib.FLAG_AUTOMASK)
+        d.image_dtype = _lib.DTYPE_BF16 if image_dtype == torch.bfloat16 else _lib.DTYPE_F32
         d.arith = int(arith)
         # Python-double scalars rounded to fp32 at the op, as PyTorch does (layers.py:90-93)
         d.min_disp = float(np.float32(1.0 / max_depth))
@@ -167,19 +171,22 @@ class _FusedLoss(torch.autograd.Function):
         buf = VslLossBuffers()
         keep = []
         for s in range(S):
-            t = _dev(targets[s], "target[%d]" % s)
+            t = _dev(targets[s], "target[%d]" % s, plan.image_dtype)
             d = _dev(disps[s], "disp[%d]" % s)
-            z = _dev(noise[s], "noise[%d]" % s)
             if tuple(d.shape) != plan.level_shapes[s]:
                 raise ValueError("disp[%d] has shape %s, plan expects %s" % (s, tuple(d.shape), plan.level_shapes[s]))
             if tuple(t.shape) != (B, 3, H >> plan.scales[s], W >> plan.scales[s]):
                 raise ValueError("target[%d] has shape %s" % (s, tuple(t.shape)))
-            if tuple(z.shape) != (B, F, H, W):
-                raise ValueError("noise[%d] has shape %s, expected %s" % (s, tuple(z.shape), (B, F, H, W)))
-            buf.target[s], buf.disp[s], buf.noise[s] = t.data_ptr(), d.data_ptr(), z.data_ptr()
-            keep += [t, d, z]
+            buf.target[s], buf.disp[s] = t.data_ptr(), d.data_ptr()
+            keep += [t, d]
+            if plan.automask:
+                z = _dev(noise[s], "noise[%d]" % s)
+                if tuple(z.shape) != (B, F, H, W):
+                    raise ValueError("noise[%d] has shape %s, expected %s" % (s, tuple(z.shape), (B, F, H, W)))
+                buf.noise[s] = z.data_ptr()
+                keep.append(z)
         for f in range(F):
-            src = _dev(sources[f], "source[%d]" % f)
+            src = _dev(sources[f], "source[%d]" % f, plan.image_dtype)
             P = _dev(Ps[f], "P[%d]" % f)
             if tuple(src.shape) != (B, 3, H, W) or tuple(P.shape) != (B, 3, 4):
                 raise ValueError("source/P[%d] have shapes %s / %s" % (f, tuple(src.shape), tuple(P.shape)))
@@ -203,7 +210,7 @@ class _FusedLoss(torch.autograd.Function):
         for s in range(S):
             buf.grad_disp_photo[s] = gphoto[s].data_ptr()
             buf.grad_disp_smooth[s] = gsmooth[s].data_ptr()
-            if want_mask:
+            if want_mask and plan.automask:
                 m = torch.empty(B, H, W, dtype=torch.float32, device=dev)
                 buf.mask[s] = m.data_ptr()
                 masks.append(m)
@@ -245,7 +252,7 @@ def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True):
     loss_vector order: min_loss/s for every scale, loss/s for every scale, loss
     (reference trainer.py:672-685).  Gradients flow to ``disps`` and ``Ps``.
     """
-    res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise), bool(want_mask),
+    res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise or []), bool(want_mask),
                            *(list(disps) + list(Ps)))
     return res[0], list(res[1:])
 
@@ -265,7 +272,7 @@ def warp_side_outputs(plan, scale_index, disp, inv_K, Ps, sources, want_depth=Tr
     keep, samples, colors = [], [], []
     for f in range(F):
         P = _dev(Ps[f].detach(), "P")
-        src = _dev(sources[f], "source")
+        src = _dev(sources[f], "source", plan.image_dtype)
         keep += [P, src]
         Pp[f], Sp[f] = P.data_ptr(), src.data_ptr()
         if want_sample:

@@ -34,12 +34,8 @@ def _unsupported(opt):
         bad.append("--v1_multiscale")
     if getattr(opt, "avg_reprojection", False):
         bad.append("--avg_reprojection")
-    if getattr(opt, "disable_automasking", False):
-        bad.append("--disable_automasking")
     if getattr(opt, "predictive_mask", False):
         bad.append("--predictive_mask")
-    if getattr(opt, "no_ssim", False):
-        bad.append("--no_ssim")
     if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn":
         bad.append("--pose_model_type posecnn")
     if getattr(opt, "pre_trained_generator", False):
@@ -54,10 +50,19 @@ class ViewSynthesisLossMixin:
     vsl_arith = "auto"  # VSL_ARITH_* bits, or "auto": calibrate against torch.bmm once per shape
 
     # -- plan ---------------------------------------------------------------------------------
-    def _vsl_plan(self):
+    vsl_image_dtype = torch.float32  # storage of the colour images: torch.float32 or torch.bfloat16
+
+    def _vsl_plan(self, image_dtype=None):
         opt = self.opt
+        if image_dtype is not None:
+            self.vsl_image_dtype = image_dtype
+        flags = 0
+        if not getattr(opt, "disable_automasking", False):
+            flags |= _lib.FLAG_AUTOMASK
+        if getattr(opt, "no_ssim", False):
+            flags |= _lib.FLAG_NO_SSIM
         key = (opt.batch_size, opt.height, opt.width, tuple(opt.scales), len(opt.frame_ids) - 1,
-               opt.min_depth, opt.max_depth, opt.disparity_smoothness, self.vsl_arith)
+               opt.min_depth, opt.max_depth, opt.disparity_smoothness, self.vsl_arith, flags, self.vsl_image_dtype)
         plan = getattr(self, "_vsl_plan_cache", None)
         if plan is None or plan[0] != key:
             bad = _unsupported(opt)
@@ -70,7 +75,8 @@ class ViewSynthesisLossMixin:
                 arith = VF.calibrate_arith(opt.batch_size, opt.height, opt.width, self.device)
             plan = (key, VF.FusedLossPlan(opt.batch_size, opt.height, opt.width, opt.scales,
                                           len(opt.frame_ids) - 1, opt.min_depth, opt.max_depth,
-                                          opt.disparity_smoothness, arith=arith))
+                                          opt.disparity_smoothness, flags=flags, arith=arith,
+                                          image_dtype=self.vsl_image_dtype))
             self._vsl_plan_cache = plan
         return plan[1]
 
@@ -86,7 +92,7 @@ class ViewSynthesisLossMixin:
     # -- reference surface ----------------------------------------------------------------------
     def generate_images_pred(self, inputs, outputs):
         """Reference trainer.py:491-541.  See the module docstring for ``vsl_side_outputs``."""
-        self._vsl_plan()  # validates the options early, like the reference would fail early
+        self._vsl_plan(inputs[("color", 0, 0)].dtype)  # validates the options early, like the reference would
         if self.vsl_side_outputs == "eager":
             self.materialize_side_outputs(inputs, outputs)
         elif self.vsl_side_outputs != "none":
@@ -105,7 +111,8 @@ class ViewSynthesisLossMixin:
                 for fi, frame_id in enumerate(self.opt.frame_ids[1:]):
                     outputs[("sample", frame_id, scale)] = samples[fi]
                     outputs[("color", frame_id, scale)] = colors[fi]
-                    outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, 0)]
+                    if plan.automask:  # trainer.py:539-541
+                        outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, 0)]
 
     def compute_reprojection_loss(self, pred, target):
         """Reference trainer.py:543-555: 0.85 * mean_c SSIM + 0.15 * mean_c L1 -> [B,1,H,W]."""
@@ -114,7 +121,7 @@ class ViewSynthesisLossMixin:
     def compute_losses(self, inputs, outputs):
         """Reference trainer.py:557-686: returns the loss dict, writes ``identity_selection/s``."""
         opt = self.opt
-        plan = self._vsl_plan()
+        plan = self._vsl_plan(inputs[("color", 0, 0)].dtype)
         S, F = len(opt.scales), len(opt.frame_ids) - 1
         targets = [inputs[("color", 0, s)] for s in opt.scales]
         sources = [inputs[("color", f, 0)] for f in opt.frame_ids[1:]]
@@ -122,13 +129,16 @@ class ViewSynthesisLossMixin:
         Ps = self._vsl_projections(inputs, outputs)
         dev = disps[0].device
         # one draw per scale, same shape/order/device as trainer.py:656-657
-        noise = [torch.randn((opt.batch_size, F, opt.height, opt.width), device=dev) for _ in opt.scales]
+        noise = None
+        if plan.automask:
+            noise = [torch.randn((opt.batch_size, F, opt.height, opt.width), device=dev) for _ in opt.scales]
         vec, masks = VF.fused_loss(plan, targets, sources, disps, inputs[("inv_K", 0)], Ps, noise)
         losses = {}
         for si, scale in enumerate(opt.scales):
             losses["min_loss/{}".format(scale)] = vec[si]
             losses["loss/{}".format(scale)] = vec[S + si]
-            outputs["identity_selection/{}".format(scale)] = masks[si]
+            if plan.automask:  # the reference writes the mask only with automasking on (trainer.py:668-670)
+                outputs["identity_selection/{}".format(scale)] = masks[si]
         losses["loss"] = vec[2 * S]
         return losses
 
