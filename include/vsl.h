@@ -84,6 +84,8 @@ typedef struct VslDesc {
   float disp_range;               /* float32(1/min_depth - 1/max_depth) (layers.py:92)      */
   float eps;                      /* Project3D eps, 1e-7                (layers.py:245)     */
   float smooth_weight;            /* opt.disparity_smoothness           (trainer.py:680)    */
+  int32_t smooth_level_bias;      /* smoothness is divided by 2^(scale_id + bias) (trainer.py:680); non-zero
+                                     only for --v1_multiscale, where each level runs as its own problem  */
 } VslDesc;
 
 /* ------------------------------------------------------------------------------------ */

@@ -86,6 +86,8 @@ CASES = {
     "no_automask": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "iid", 12, {"disable_automasking": True}),
     "no_automask_one_frame": (2, 64, 96, [0, 1], synthetic.K_KITTI, "smooth", 13, {"disable_automasking": True}),
     "no_automask_stereo": (2, 64, 96, [0, -1, 1, "s"], synthetic.K_KITTI, "iid", 14, {"disable_automasking": True}),
+    "v1_multiscale": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "iid", 15, {"v1_multiscale": True}),
+    "v1_multiscale_c1_b2": (2, 192, 640, [0, -1, 1, "s"], synthetic.K_KITTI, "smooth", 16, {"v1_multiscale": True}),
 }
 
 
@@ -109,11 +111,13 @@ def test_fused_path_matches_oracle(name):
         assert torch.equal(out[("depth", 0, s)], ref_out[("depth", 0, s)]), ("depth", s)
         for f in opt.frame_ids[1:]:
             assert torch.equal(out[("sample", f, s)], ref_out[("sample", f, s)]), ("sample", f, s)
+            if opt.v1_multiscale:
+                H, W = opt.height >> s, opt.width >> s
             a, b = tap_indices(out[("sample", f, s)], H, W), tap_indices(ref_out[("sample", f, s)], H, W)
             assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
             assert torch.equal(out[("color", f, s)], ref_out[("color", f, s)]), ("color", f, s)
             if not opt.disable_automasking:
-                assert out[("color_identity", f, s)] is inputs[("color", f, 0)]
+                assert out[("color_identity", f, s)] is inputs[("color", f, s if opt.v1_multiscale else 0)]
         k = "identity_selection/%d" % s
         if opt.disable_automasking:  # the reference writes no mask then (trainer.py:668-670)
             assert k not in out and k not in ref_out
@@ -379,7 +383,7 @@ def test_errors_are_loud():
     cpu_inputs[("color", 0, 0)] = inputs[("color", 0, 0)].cpu()
     with pytest.raises(_lib.VslError):
         path.compute_losses(cpu_inputs, out)
-    for flag in ("avg_reprojection", "v1_multiscale", "predictive_mask"):
+    for flag in ("avg_reprojection", "predictive_mask"):
         with pytest.raises(NotImplementedError):
             LossPath(make_opt(**{flag: True}), device=DEV).generate_images_pred(inputs, out)
     lib = _lib.load()

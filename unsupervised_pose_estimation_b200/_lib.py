@@ -51,6 +51,7 @@ class VslDesc(Structure):
         ("num_scales", c_int32), ("scale_ids", c_int32 * VSL_MAX_SCALES), ("num_src", c_int32),
         ("flags", c_int32), ("image_dtype", c_int32), ("arith", c_int32),
         ("min_disp", c_float), ("disp_range", c_float), ("eps", c_float), ("smooth_weight", c_float),
+        ("smooth_level_bias", c_int32),
     ]
 
 

@@ -396,6 +396,7 @@ static bool desc_ok(const VslDesc* d) {
   for (int s = 0; s < d->num_scales; ++s) {
     int e = d->scale_ids[s];
     if (e < 0 || e > 3) return false;  // up-sample adjoint uses 2*2^e <= 16 lanes per coarse pixel
+    if (e + d->smooth_level_bias < 0 || e + d->smooth_level_bias > 16) return false;
     if ((d->height >> e) < 2 || (d->width >> e) < 2) return false;
     if (((d->height >> e) << e) != d->height || ((d->width >> e) << e) != d->width) return false;
   }
@@ -560,7 +561,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     sp.img[s] = buf->target[s];
     sp.gsmooth[s] = buf->grad_disp_smooth[s];
     sp.gphoto[s] = buf->grad_disp_photo[s];
-    sp.scale_id[s] = e;
+    sp.scale_id[s] = e + d->smooth_level_bias;
   }
   sp.mean_part = ws + pl.off_mean;
   sp.smooth_part = ws + pl.off_smooth;
@@ -622,7 +623,7 @@ int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLos
     if (!buf->grad_disp_photo[s] || !buf->grad_disp_smooth[s] || !grad_disp[s]) return VSL_ERR_NULL_POINTER;
     int e = d->scale_ids[s];
     cp.n[s] = (d->height >> e) * (d->width >> e);
-    cp.scale_id[s] = e;
+    cp.scale_id[s] = e + d->smooth_level_bias;
     cp.gphoto[s] = buf->grad_disp_photo[s]; cp.gsmooth[s] = buf->grad_disp_smooth[s]; cp.out[s] = grad_disp[s];
   }
   if (grad_P_out && !buf->grad_P) return VSL_ERR_NULL_POINTER;

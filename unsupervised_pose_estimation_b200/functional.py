@@ -88,7 +88,8 @@ class FusedLossPlan:
     per plan (calls are stream-ordered)."""
 
     def __init__(self, batch, height, width, scales, num_src, min_depth, max_depth,
-                 disparity_smoothness, flags=_lib.FLAG_AUTOMASK, arith=0, image_dtype=torch.float32):
+                 disparity_smoothness, flags=_lib.FLAG_AUTOMASK, arith=0, image_dtype=torch.float32,
+                 smooth_level_bias=0):
         scales = list(scales)
         if not (1 <= len(scales) <= VSL_MAX_SCALES):
             raise ValueError("1..%d scales supported" % VSL_MAX_SCALES)
@@ -115,6 +116,7 @@ class FusedLossPlan:
         d.disp_range = float(np.float32(1.0 / min_depth - 1.0 / max_depth))
         d.eps = float(np.float32(1e-7))
         d.smooth_weight = float(disparity_smoothness)
+        d.smooth_level_bias = int(smooth_level_bias)
         self.desc = d
         self.lib = _lib.load()
         self.ws_bytes = self.lib.vsl_loss_workspace_bytes(ctypes.byref(d))

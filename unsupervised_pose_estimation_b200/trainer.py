@@ -30,8 +30,6 @@ from . import functional as VF
 
 def _unsupported(opt):
     bad = []
-    if getattr(opt, "v1_multiscale", False):
-        bad.append("--v1_multiscale")
     if getattr(opt, "avg_reprojection", False):
         bad.append("--avg_reprojection")
     if getattr(opt, "predictive_mask", False):
@@ -61,8 +59,9 @@ class ViewSynthesisLossMixin:
             flags |= _lib.FLAG_AUTOMASK
         if getattr(opt, "no_ssim", False):
             flags |= _lib.FLAG_NO_SSIM
+        v1 = bool(getattr(opt, "v1_multiscale", False))
         key = (opt.batch_size, opt.height, opt.width, tuple(opt.scales), len(opt.frame_ids) - 1,
-               opt.min_depth, opt.max_depth, opt.disparity_smoothness, self.vsl_arith, flags, self.vsl_image_dtype)
+               opt.min_depth, opt.max_depth, opt.disparity_smoothness, self.vsl_arith, flags, self.vsl_image_dtype, v1)
         plan = getattr(self, "_vsl_plan_cache", None)
         if plan is None or plan[0] != key:
             bad = _unsupported(opt)
@@ -70,19 +69,32 @@ class ViewSynthesisLossMixin:
                 raise NotImplementedError(
                     "the CUDA view-synthesis path implements the reference's default loss "
                     "(automask + per-pixel min + SSIM at full resolution); not yet: " + ", ".join(bad))
-            arith = self.vsl_arith
-            if arith == "auto":
-                arith = VF.calibrate_arith(opt.batch_size, opt.height, opt.width, self.device)
-            plan = (key, VF.FusedLossPlan(opt.batch_size, opt.height, opt.width, opt.scales,
-                                          len(opt.frame_ids) - 1, opt.min_depth, opt.max_depth,
-                                          opt.disparity_smoothness, flags=flags, arith=arith,
-                                          image_dtype=self.vsl_image_dtype))
+            def make(h, w, scales, bias):
+                arith = self.vsl_arith
+                if arith == "auto":
+                    arith = VF.calibrate_arith(opt.batch_size, h, w, self.device)
+                return VF.FusedLossPlan(opt.batch_size, h, w, scales, len(opt.frame_ids) - 1, opt.min_depth,
+                                        opt.max_depth, opt.disparity_smoothness, flags=flags, arith=arith,
+                                        image_dtype=self.vsl_image_dtype, smooth_level_bias=bias)
+            if v1:
+                # --v1_multiscale (trainer.py:497-498, 604-605): every level is warped and scored at its own
+                # resolution with its own K / images, i.e. S independent single-level problems
+                plan = (key, [make(opt.height >> s, opt.width >> s, [0], s) for s in opt.scales])
+            else:
+                plan = (key, make(opt.height, opt.width, opt.scales, 0))
             self._vsl_plan_cache = plan
         return plan[1]
 
-    def _vsl_projections(self, inputs, outputs):
+    def _vsl_level_plans(self, image_dtype=None):
+        """[(plan, scale_index_in_plan, source_scale)] per entry of opt.scales."""
+        plan = self._vsl_plan(image_dtype)
+        if isinstance(plan, list):
+            return [(pl, 0, s) for pl, s in zip(plan, self.opt.scales)]
+        return [(plan, si, 0) for si, _ in enumerate(self.opt.scales)]
+
+    def _vsl_projections(self, inputs, outputs, source_scale=0):
         """P_f = (K @ T_f)[:, :3, :] per source frame (reference layers.py:254; T as trainer.py:510-513)."""
-        K = inputs[("K", 0)]
+        K = inputs[("K", source_scale)]
         Ps = []
         for frame_id in self.opt.frame_ids[1:]:
             T = inputs["stereo_T"] if frame_id == "s" else outputs[("cam_T_cam", 0, frame_id)]
@@ -100,19 +112,18 @@ class ViewSynthesisLossMixin:
 
     def materialize_side_outputs(self, inputs, outputs):
         """Write ("depth",0,s), ("sample",f,s), ("color",f,s), ("color_identity",f,s) into ``outputs``."""
-        plan = self._vsl_plan()
         with torch.no_grad():
-            Ps = self._vsl_projections(inputs, outputs)
-            sources = [inputs[("color", f, 0)] for f in self.opt.frame_ids[1:]]
-            for si, scale in enumerate(self.opt.scales):
+            for (plan, si, src_scale), scale in zip(self._vsl_level_plans(inputs[("color", 0, 0)].dtype), self.opt.scales):
+                Ps = self._vsl_projections(inputs, outputs, src_scale)
+                sources = [inputs[("color", f, src_scale)] for f in self.opt.frame_ids[1:]]
                 depth, samples, colors = VF.warp_side_outputs(
-                    plan, si, outputs[("disp", scale)], inputs[("inv_K", 0)], Ps, sources)
+                    plan, si, outputs[("disp", scale)], inputs[("inv_K", src_scale)], Ps, sources)
                 outputs[("depth", 0, scale)] = depth
                 for fi, frame_id in enumerate(self.opt.frame_ids[1:]):
                     outputs[("sample", frame_id, scale)] = samples[fi]
                     outputs[("color", frame_id, scale)] = colors[fi]
                     if plan.automask:  # trainer.py:539-541
-                        outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, 0)]
+                        outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, src_scale)]
 
     def compute_reprojection_loss(self, pred, target):
         """Reference trainer.py:543-555: 0.85 * mean_c SSIM + 0.15 * mean_c L1 -> [B,1,H,W]."""
@@ -122,6 +133,8 @@ class ViewSynthesisLossMixin:
         """Reference trainer.py:557-686: returns the loss dict, writes ``identity_selection/s``."""
         opt = self.opt
         plan = self._vsl_plan(inputs[("color", 0, 0)].dtype)
+        if isinstance(plan, list):
+            return self._compute_losses_v1(inputs, outputs, plan)
         S, F = len(opt.scales), len(opt.frame_ids) - 1
         targets = [inputs[("color", 0, s)] for s in opt.scales]
         sources = [inputs[("color", f, 0)] for f in opt.frame_ids[1:]]
@@ -140,6 +153,28 @@ class ViewSynthesisLossMixin:
             if plan.automask:  # the reference writes the mask only with automasking on (trainer.py:668-670)
                 outputs["identity_selection/{}".format(scale)] = masks[si]
         losses["loss"] = vec[2 * S]
+        return losses
+
+
+    def _compute_losses_v1(self, inputs, outputs, plans):
+        """--v1_multiscale: one fused launch per level at that level's resolution (trainer.py:604-605)."""
+        opt = self.opt
+        F = len(opt.frame_ids) - 1
+        losses, total = {}, 0
+        for plan, scale in zip(plans, opt.scales):
+            disp = outputs[("disp", scale)]
+            noise = None
+            if plan.automask:
+                noise = [torch.randn((opt.batch_size, F, plan.height, plan.width), device=disp.device)]
+            vec, masks = VF.fused_loss(plan, [inputs[("color", 0, scale)]],
+                                       [inputs[("color", f, scale)] for f in opt.frame_ids[1:]], [disp],
+                                       inputs[("inv_K", scale)], self._vsl_projections(inputs, outputs, scale), noise)
+            losses["min_loss/{}".format(scale)] = vec[0]
+            losses["loss/{}".format(scale)] = vec[1]
+            if plan.automask:
+                outputs["identity_selection/{}".format(scale)] = masks[0]
+            total = total + vec[1]
+        losses["loss"] = total / self.num_scales if hasattr(self, "num_scales") else total / len(opt.scales)
         return losses
 
 
