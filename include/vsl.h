@@ -113,7 +113,9 @@ typedef struct VslLossBuffers {
   float* losses;                        /* [3*S+1]: min_loss/s (S), loss/s (S), loss, smooth/s (S)    */
   float* mask[VSL_MAX_SCALES];          /* outputs["identity_selection/s"] [B,H,W]; may be null       */
   float* grad_disp_photo[VSL_MAX_SCALES];  /* d(min_loss/s)/d disp_s   [B,1,H>>s,W>>s]                */
-  float* grad_disp_smooth[VSL_MAX_SCALES]; /* d(smooth_s)/d disp_s     [B,1,H>>s,W>>s]                */
+  float* grad_disp_smooth[VSL_MAX_SCALES]; /* d(smooth_s)/d(norm disp_s) [B,1,H>>s,W>>s]; combine_grads applies
+                                              the chain through the per-image mean with smooth_norm        */
+  float* smooth_norm;                   /* [S][B][2] per-image normalisation terms for the backward          */
   float* grad_P;                        /* d(min_loss/s)/d P_f  [S][F][B][12]                         */
 } VslLossBuffers;
 

@@ -39,6 +39,10 @@ static void run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
           for (int tid = 0; tid < C::NT; ++tid) phase_warp<C>(p, p.g, t, sm.data(), s, tid);
           for (int tid = 0; tid < C::NT; ++tid) phase_windows<C>(p, p.g, t, sm.data(), s, tid, ts[tid]);
           for (int tid = 0; tid < C::NT; ++tid) phase_backward<C>(p, p.g, t, sm.data(), s, tid, ts[tid]);
+          if (!p.identity_scale[s]) {
+            for (int tid = 0; tid < C::NT; ++tid) phase_adjoint_rows<C>(p, t, sm.data(), s, tid);
+            for (int tid = 0; tid < C::NT; ++tid) phase_adjoint_cols<C>(p, t, sm.data(), s, tid);
+          }
           float* out = p.partials + ((size_t)t.cta * p.S + s) * C::kPartial;
           for (int k = 0; k < C::kPartial; ++k) out[k] = 0.f;
           for (int tid = 0; tid < C::NT; ++tid) {
@@ -61,7 +65,8 @@ extern "C" int vsl_emul_photometric(int B, int H, int W, int S, int F, const int
   p.g.wm1 = (float)(W - 1); p.g.hm1 = (float)(H - 1);
   p.g.inv_wm1 = 1.0f / p.g.wm1; p.g.inv_hm1 = 1.0f / p.g.hm1; p.g.arith = arith;
   p.wpix = 1.0f / ((float)B * H * W);
-  std::vector<std::vector<float>> gD(S);
+  std::vector<std::vector<float>> gD(S), gpart(S);
+  const int tiles_x0 = (W + tw - 1) / tw, tiles_y0 = (H + th - 1) / th;
   for (int f = 0; f < F; ++f) { p.src[f] = src[f]; p.P[f] = P[f]; }
   for (int s = 0; s < S; ++s) {
     int e = scale_ids[s];
@@ -71,6 +76,9 @@ extern "C" int vsl_emul_photometric(int B, int H, int W, int S, int F, const int
     p.disp[s] = disp[s]; p.noise[s] = noise[s]; p.mask[s] = mask[s];
     gD[s].assign((size_t)B * H * W, 0.f);
     p.gD[s] = gD[s].data();
+    int r = 1 << e;
+    gpart[s].assign((size_t)tiles_x0 * tiles_y0 * B * (tw / r + 2) * (th / r + 2), 0.f);
+    p.gpart[s] = gpart[s].data();
   }
   int tiles_x = (W + tw - 1) / tw, tiles_y = (H + th - 1) / th;
   int kpartial = 1 + F * 12;
@@ -95,8 +103,7 @@ extern "C" int vsl_emul_photometric(int B, int H, int W, int S, int F, const int
       for (int i = 0; i < hs * ws; ++i)
         gdisp[s][(size_t)b * hs * ws + i] =
             p.identity_scale[s] ? gD[s][(size_t)b * H * W + i]
-                                : upsample_adjoint_pixel(gD[s].data() + (size_t)b * H * W, H, W, hs, ws, p.scale_h[s],
-                                                         p.scale_w[s], i / ws, i % ws);
+                                : gather_adjoint_partials(gpart[s].data(), b, i / ws, i % ws, W / ws, tw, th, tiles_x, tiles_y);
     }
   }
   return 0;

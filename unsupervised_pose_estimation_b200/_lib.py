@@ -62,7 +62,7 @@ class VslLossBuffers(Structure):
         ("noise", c_void_p * VSL_MAX_SCALES),
         ("losses", c_void_p), ("mask", c_void_p * VSL_MAX_SCALES),
         ("grad_disp_photo", c_void_p * VSL_MAX_SCALES), ("grad_disp_smooth", c_void_p * VSL_MAX_SCALES),
-        ("grad_P", c_void_p),
+        ("smooth_norm", c_void_p), ("grad_P", c_void_p),
     ]
 
 

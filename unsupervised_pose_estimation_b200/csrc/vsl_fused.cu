@@ -4,8 +4,9 @@
 //   k_smooth_mean   per-image mean of disp_s                     (trainer.py:676)
 //   k_smooth_terms  edge-aware smoothness terms + d/d(norm disp)  (layers.py:286-299)
 //   k_photometric   warp + SSIM/L1 + automask min + adjoint       (trainer.py:491-674)  <- the hot kernel
-//   k_upsample_adjoint  d/d disp_s from d/d(up-sampled disp_s), s >= 1   (trainer.py:500-501)
-//   k_epilogue      smoothness chain rule, deterministic reductions, loss dict
+//   k_epilogue      sums the tiles' up-sample-adjoint partials (s >= 1), deterministic reductions, loss dict
+// and of vsl_loss_combine_grads (the backward):
+//   k_combine       smoothness chain rule through the per-image mean + upstream weights
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,7 +34,9 @@ struct SmallParams {  // smoothness + epilogue
   const void* img[kMaxScales];    // target pyramid (fp32 or bf16)
   float* gsmooth[kMaxScales];     // d smooth_s / d disp_s
   float* gphoto[kMaxScales];      // d min_loss_s / d disp_s
-  const float* gD[kMaxScales];    // full-res adjoint input (null for identity scales)
+  const float* gpart[kMaxScales]; // per-CTA partial up-sample adjoints (null for identity scales)
+  float* norm;                    // [S][B][2]: 1/(mean disp + 1e-7), sum(g*d) * inv^2 / n   (for k_combine)
+  int tw, th, tiles_x, tiles_y;
   float* mean_part;               // [S][B][chunks0]
   float* smooth_part;             // [S][B][chunks0][3]  (sum_x, sum_y, sum g*d)
   const float* partials;          // photometric partials [numCTA][S][kPartial]
@@ -198,39 +201,12 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
       for (int i = 0; i < C::NT / 32; ++i) r += red[i * C::kPartial + tid];
       p.partials[((size_t)t.cta * p.S + s) * C::kPartial + tid] = r;
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Adjoint of F.interpolate(disp_s, [H,W], bilinear, align_corners=False) (trainer.py:500-501):
-// d/d disp_s[jy,jx] = sum over the 2r x 2r fine pixels whose bilinear footprint touches (jy,jx).
-// 2r lanes cooperate on one coarse pixel (one fine column each, coalesced), then a sub-warp shuffle sum.
-__global__ void __launch_bounds__(kSmallNT) k_upsample_adjoint(const SmallParams p) {
-  const int s = blockIdx.z, b = blockIdx.y;
-  if (p.identity_scale[s]) return;
-  const int h = p.hs[s], w = p.ws[s], r = p.H / h, L = 2 * r;  // L in {4, 8, 16}
-  const int gid = blockIdx.x * kSmallNT + threadIdx.x;
-  const int cp = gid / L, lane = gid - cp * L;
-  if (blockIdx.x * kSmallNT >= h * w * L) return;  // whole block past the level (uniform)
-  const bool live = cp < h * w;
-  const int jy = live ? cp / w : 0, jx = live ? cp - (cp / w) * w : 0;
-  const int ox = jx * r - r / 2 + lane;
-  float acc = 0.f;
-  if (live && ox >= 0 && ox < p.W) {
-    UpsTap tx = ups_tap(ox, w, p.scale_w[s]);
-    float wx = (tx.i0 == jx ? tx.l0 : 0.f) + (tx.i1 == jx ? tx.l1 : 0.f);
-    const float* gD = p.gD[s] + (size_t)b * p.H * p.W + ox;
-    for (int t = 0; t < L; ++t) {
-      int oy = jy * r - r / 2 + t;
-      if (oy < 0 || oy >= p.H) continue;
-      UpsTap ty = ups_tap(oy, h, p.scale_h[s]);
-      float wy = (ty.i0 == jy ? ty.l0 : 0.f) + (ty.i1 == jy ? ty.l1 : 0.f);
-      acc += wy * gD[(size_t)oy * p.W];
+    if (!p.identity_scale[s]) {  // block-uniform; the tile's d/d(up-sampled disp) is complete (sync above)
+      phase_adjoint_rows<C>(p, t, sm, s, tid);
+      __syncthreads();
+      phase_adjoint_cols<C>(p, t, sm, s, tid);
     }
-    acc *= wx;
   }
-  for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (live && lane == 0) p.gphoto[s][(size_t)b * h * w + cp] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -240,38 +216,38 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
   int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   int h = p.hs[s], w = p.ws[s], n = h * w;
   int nchunk = (n + kChunk - 1) / kChunk;
-  if (chunk < nchunk) {
-    float inv = 1.0f / (image_mean(p, s, b, scratch) + 1e-7f);
-    float gd = 0.f;
-    for (int i = threadIdx.x; i < nchunk; i += kSmallNT)
-      gd += p.smooth_part[((size_t)(s * p.B + b) * p.chunks0 + i) * 3 + 2];
-    gd = block_sum<kSmallNT>(gd, scratch);
-    float corr = gd * inv * inv / (float)n;
-    float* gs = p.gsmooth[s] + (size_t)b * n;
+  if (chunk < nchunk && !p.identity_scale[s]) {
+    // d(min_loss/s)/d disp_s: add the (<= 4) tile partials of every coarse pixel, tiles in a fixed order
+    float* gp = p.gphoto[s] + (size_t)b * n;
+    const int r = p.W / w;
     for (int i = chunk * kChunk + threadIdx.x; i < min(n, (chunk + 1) * kChunk); i += kSmallNT)
-      gs[i] = gs[i] * inv - corr;
-    if (chunk == 0) {
-      // photometric partials of image b, scale s: loss sum and dP, tiles in a fixed order
-      const float* base = p.partials + ((size_t)b * p.tiles_per_image * p.S + s) * p.kpartial;
-      for (int k = threadIdx.x; k < p.kpartial; k += kSmallNT) {
-        double acc = 0.0;
-        for (int tl = 0; tl < p.tiles_per_image; ++tl) acc += (double)base[(size_t)tl * p.S * p.kpartial + k];
-        if (k == 0) p.lossb[s * p.B + b] = (float)acc;
-        else {
-          int f = (k - 1) / 12, e = (k - 1) % 12;
-          p.gradP[((size_t)(s * p.F + f) * p.B + b) * 12 + e] = (float)acc;
-        }
-      }
-      float sx = 0.f, sy = 0.f;
-      for (int i = threadIdx.x; i < nchunk; i += kSmallNT) {
-        const float* sp = p.smooth_part + ((size_t)(s * p.B + b) * p.chunks0 + i) * 3;
-        sx += sp[0]; sy += sp[1];
-      }
-      sx = block_sum<kSmallNT>(sx, scratch);
-      sy = block_sum<kSmallNT>(sy, scratch);
-      if (threadIdx.x == 0) {
-        p.smoothb[(s * p.B + b) * 2] = sx;
-        p.smoothb[(s * p.B + b) * 2 + 1] = sy;
+      gp[i] = gather_adjoint_partials(p.gpart[s], b, i / w, i % w, r, p.tw, p.th, p.tiles_x, p.tiles_y);
+  }
+  if (chunk == 0) {
+    // per (scale, image): smoothness normalisation for the backward, photometric partials, smoothness sums
+    float inv = 1.0f / (image_mean(p, s, b, scratch) + 1e-7f);
+    float gd = 0.f, sx = 0.f, sy = 0.f;
+    for (int i = threadIdx.x; i < nchunk; i += kSmallNT) {
+      const float* sp = p.smooth_part + ((size_t)(s * p.B + b) * p.chunks0 + i) * 3;
+      sx += sp[0]; sy += sp[1]; gd += sp[2];
+    }
+    gd = block_sum<kSmallNT>(gd, scratch);
+    sx = block_sum<kSmallNT>(sx, scratch);
+    sy = block_sum<kSmallNT>(sy, scratch);
+    if (threadIdx.x == 0) {
+      p.norm[(s * p.B + b) * 2] = inv;
+      p.norm[(s * p.B + b) * 2 + 1] = gd * inv * inv / (float)n;
+      p.smoothb[(s * p.B + b) * 2] = sx;
+      p.smoothb[(s * p.B + b) * 2 + 1] = sy;
+    }
+    const float* base = p.partials + ((size_t)b * p.tiles_per_image * p.S + s) * p.kpartial;
+    for (int k = threadIdx.x; k < p.kpartial; k += kSmallNT) {
+      double acc = 0.0;
+      for (int tl = 0; tl < p.tiles_per_image; ++tl) acc += (double)base[(size_t)tl * p.S * p.kpartial + k];
+      if (k == 0) p.lossb[s * p.B + b] = (float)acc;
+      else {
+        int f = (k - 1) / 12, e = (k - 1) % 12;
+        p.gradP[((size_t)(s * p.F + f) * p.B + b) * 12 + e] = (float)acc;
       }
     }
   }
@@ -316,6 +292,7 @@ struct CombineParams {
   float* out[kMaxScales];
   const float* gradP;  // [S][F][B][12]
   float* gradP_out;    // [F][B][12]
+  const float* norm;   // [S][B][2]
   int B, S, F, chunks0;
   int n[kMaxScales], scale_id[kMaxScales];
   float smooth_weight;
@@ -330,8 +307,10 @@ __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
     const float* gp = p.gphoto[s] + (size_t)b * p.n[s];
     const float* gs = p.gsmooth[s] + (size_t)b * p.n[s];
     float* o = p.out[s] + (size_t)b * p.n[s];
+    // d smooth_s/d disp = g * inv - sum(g d) inv^2 / n  (chain through norm_disp = disp / (mean + 1e-7), trainer.py:676-677)
+    const float inv = p.norm[(s * p.B + b) * 2], corr = p.norm[(s * p.B + b) * 2 + 1];
     for (int i = chunk * kChunk + threadIdx.x; i < min(p.n[s], (chunk + 1) * kChunk); i += kSmallNT)
-      o[i] = a * gp[i] + bb * gs[i];
+      o[i] = a * gp[i] + bb * (gs[i] * inv - corr);
   }
   if (chunk == 0 && s == 0 && p.gradP_out) {
     for (int k = threadIdx.x; k < p.F * 12; k += kSmallNT) {
@@ -415,7 +394,7 @@ static GeoConst make_geo(const VslDesc* d) {
 
 struct Plan {  // sizes derived from the descriptor; identical in workspace_bytes() and the launcher
   int tw, th, tiles_x, tiles_y, num_cta, kpartial, chunks0;
-  size_t off_partials, off_gD[kMaxScales], off_mean, off_smooth, off_lossb, off_smoothb, off_counter, total;
+  size_t off_partials, off_gpart[kMaxScales], off_mean, off_smooth, off_lossb, off_smoothb, off_counter, total;
 };
 
 static Plan make_plan(const VslDesc* d) {
@@ -429,8 +408,10 @@ static Plan make_plan(const VslDesc* d) {
   size_t off = 0;
   auto take = [&](size_t floats) { size_t o = off; off += (floats + 63) / 64 * 64; return o; };
   pl.off_partials = take((size_t)pl.num_cta * d->num_scales * pl.kpartial);
-  for (int s = 0; s < d->num_scales; ++s)
-    pl.off_gD[s] = d->scale_ids[s] == 0 ? 0 : take((size_t)d->batch * d->height * d->width);
+  for (int s = 0; s < d->num_scales; ++s) {
+    int r = 1 << d->scale_ids[s];
+    pl.off_gpart[s] = r == 1 ? 0 : take((size_t)pl.num_cta * (pl.tw / r + 2) * (pl.th / r + 2));
+  }
   pl.off_mean = take((size_t)d->num_scales * d->batch * pl.chunks0);
   pl.off_smooth = take((size_t)d->num_scales * d->batch * pl.chunks0 * 3);
   pl.off_lossb = take((size_t)d->num_scales * d->batch);
@@ -523,7 +504,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   Plan pl = make_plan(d);
   if (workspace_bytes < pl.total) return VSL_ERR_WORKSPACE;
   if (((uintptr_t)workspace & 15u) != 0) return VSL_ERR_MISALIGNED;
-  if (!buf->inv_K || !buf->losses || !buf->grad_P) return VSL_ERR_NULL_POINTER;
+  if (!buf->inv_K || !buf->losses || !buf->grad_P || !buf->smooth_norm) return VSL_ERR_NULL_POINTER;
   for (int s = 0; s < S; ++s)
     if (!buf->target[s] || !buf->disp[s] || (automask && !buf->noise[s]) || !buf->grad_disp_photo[s] ||
         !buf->grad_disp_smooth[s])
@@ -556,8 +537,9 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     pp.disp[s] = sp.disp[s] = buf->disp[s];
     pp.noise[s] = buf->noise[s];
     pp.mask[s] = automask ? buf->mask[s] : nullptr;
-    pp.gD[s] = (e == 0) ? buf->grad_disp_photo[s] : ws + pl.off_gD[s];
-    sp.gD[s] = (e == 0) ? nullptr : ws + pl.off_gD[s];
+    pp.gD[s] = (e == 0) ? buf->grad_disp_photo[s] : nullptr;
+    pp.gpart[s] = (e == 0) ? nullptr : ws + pl.off_gpart[s];
+    sp.gpart[s] = pp.gpart[s];
     sp.img[s] = buf->target[s];
     sp.gsmooth[s] = buf->grad_disp_smooth[s];
     sp.gphoto[s] = buf->grad_disp_photo[s];
@@ -569,6 +551,8 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   sp.lossb = ws + pl.off_lossb;
   sp.smoothb = ws + pl.off_smoothb;
   sp.gradP = buf->grad_P;
+  sp.norm = buf->smooth_norm;
+  sp.tw = pl.tw; sp.th = pl.th; sp.tiles_x = pl.tiles_x; sp.tiles_y = pl.tiles_y;
   sp.losses = buf->losses;
   sp.counter = (unsigned*)(ws + pl.off_counter);
   sp.chunks0 = pl.chunks0;
@@ -596,15 +580,6 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   }
   if (rc != VSL_OK) return rc;
   if (event_after) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after, st));
-  {
-    bool any = false;
-    for (int s = 0; s < S; ++s) any |= d->scale_ids[s] != 0;
-    if (any) {  // every non-identity level has H*W lanes of work per image (2r lanes per coarse pixel)
-      dim3 agrid((d->height * d->width + kSmallNT - 1) / kSmallNT, d->batch, S);
-      k_upsample_adjoint<<<agrid, kSmallNT, 0, st>>>(sp);
-      VSL_CUDA_OK(cudaGetLastError());
-    }
-  }
   k_epilogue<<<sgrid, kSmallNT, 0, st>>>(sp);
   VSL_CUDA_OK(cudaGetLastError());
   return VSL_OK;
@@ -619,6 +594,8 @@ int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLos
   cp.chunks0 = (d->height * d->width + kChunk - 1) / kChunk;
   cp.smooth_weight = d->smooth_weight;
   cp.gradP = buf->grad_P; cp.gradP_out = grad_P_out;
+  cp.norm = buf->smooth_norm;
+  if (!cp.norm) return VSL_ERR_NULL_POINTER;
   for (int s = 0; s < d->num_scales; ++s) {
     if (!buf->grad_disp_photo[s] || !buf->grad_disp_smooth[s] || !grad_disp[s]) return VSL_ERR_NULL_POINTER;
     int e = d->scale_ids[s];

@@ -25,7 +25,8 @@ struct PhotoParams {
   const float* P[kMaxSrc];        // [B,3,4]
   const float* noise[kMaxScales]; // [B,F,H,W]
   float* mask[kMaxScales];        // [B,H,W] or null
-  float* gD[kMaxScales];          // [B,H,W]: d(min_loss/s)/d(up-sampled disp_s)
+  float* gD[kMaxScales];          // identity levels: [B,H,W] d(min_loss/s)/d disp_s, written directly
+  float* gpart[kMaxScales];       // other levels: per-CTA partial up-sample adjoints [numCTA][ncy][ncx]
   float* partials;                // [numCTA][S][1 + F*12]
   int B, H, W, S, F;
   int hs[kMaxScales], ws[kMaxScales];
@@ -52,7 +53,9 @@ struct TileCfg {
   static constexpr int oCoef = oId + F * WN;    // per window: CoefRec (winner's SSIM adjoint coefficients + winner id)
   static constexpr int oG = oCoef + 12 * WN;    // d warped / d(ix,iy)     [F][6][IN]
   static constexpr int oRed = oG + F * 6 * IN;  // block-reduction scratch [NT/32][1 + F*12]
-  static constexpr int kFloats = oRed + (NT / 32) * (1 + F * 12);
+  static constexpr int oGD = oRed + (NT / 32) * (1 + F * 12);  // d/d(up-sampled disp) of the tile [IN]
+  static constexpr int oH = oGD + IN;           // row-reduced adjoint [TH][TW/2 + 2]
+  static constexpr int kFloats = oH + TH * (TW / 2 + 2);
   static constexpr int kBytes = kFloats * 4;
   static constexpr int kPartial = 1 + F * 12;
   static_assert(oCoef % 4 == 0, "CoefRec needs 16-byte alignment");
@@ -520,7 +523,10 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
   for (int j = tid; j < C::IN; j += C::NT) {
     int iy = j / C::TW, ix = j - iy * C::TW;
     int gy = t.y0 + iy, gx = t.x0 + ix;
-    if (gy >= p.H || gx >= p.W) continue;
+    if (gy >= p.H || gx >= p.W) {
+      sm[C::oGD + j] = 0.f;
+      continue;
+    }
     // masked 3x3 gather of the winners' coefficients; reflected border rows/cols count twice
     float acc[C::F][9];
 #pragma unroll
@@ -584,34 +590,99 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
       }
     }
     // z = 1/(min_disp + range*D)  ->  dz/dD = -range * z^2
-    p.gD[s][(size_t)t.b * HW + gy * p.W + gx] = -gz * g.disp_range * cam.z * cam.z;
+    const float gDv = -gz * g.disp_range * cam.z * cam.z;
+    if (p.identity_scale[s]) p.gD[s][(size_t)t.b * HW + gy * p.W + gx] = gDv;
+    else sm[C::oGD + j] = gDv;  // folded into d/d disp_s by phase_adjoint_rows / _cols
   }
 }
 
-// ---- bilinear up-sample adjoint: d/d disp_s from d/d(up-sampled disp) (trainer.py:500-501) -------
-// gather form for one coarse pixel (jy, jx) of a [hs, ws] level; gD: one full-res plane [H, W]
-VSL_HD float upsample_adjoint_pixel(const float* __restrict__ gD, int H, int W, int hs, int ws, float scale_h,
-                                    float scale_w, int jy, int jx) {
-  int ry = H / hs, rx = W / ws;  // integer ratios (levels are exact halvings)
-  int oy0 = jy * ry - ry / 2 - 1, oy1 = jy * ry + (3 * ry) / 2 + 1;
-  int ox0 = jx * rx - rx / 2 - 1, ox1 = jx * rx + (3 * rx) / 2 + 1;
-  if (oy0 < 0) oy0 = 0;
-  if (ox0 < 0) ox0 = 0;
-  if (oy1 > H) oy1 = H;
-  if (ox1 > W) ox1 = W;
-  float acc = 0.f;
-  for (int oy = oy0; oy < oy1; ++oy) {
-    UpsTap ty = ups_tap(oy, hs, scale_h);
-    float wy = (ty.i0 == jy ? ty.l0 : 0.f) + (ty.i1 == jy ? ty.l1 : 0.f);
-    if (wy == 0.f) continue;
-    float row = 0.f;
-    for (int ox = ox0; ox < ox1; ++ox) {
-      UpsTap tx = ups_tap(ox, ws, scale_w);
-      float wx = (tx.i0 == jx ? tx.l0 : 0.f) + (tx.i1 == jx ? tx.l1 : 0.f);
-      row += wx * gD[oy * W + ox];
+// ---- phases: adjoint of the bilinear up-sample of disp_s (trainer.py:500-501), tile-local part -----
+// d/d disp_s[jy,jx] = sum over fine pixels o of wy(oy,jy) wx(ox,jx) gD[o]; the footprint of a coarse pixel is
+// [r j - r/2, r j + 3r/2) per axis, so a TW x TH tile touches (TW/r + 2) x (TH/r + 2) coarse pixels.  The tile
+// reduces its own fine pixels separably (rows, then columns) and stores one partial per touched coarse
+// pixel; k_epilogue adds the <= 4 partials of every coarse pixel in a fixed order (no atomics).
+// weight of fine pixel o in coarse pixel j for ratio R = 2^e: a triangle over the footprint
+// t = o - (R j - R/2) in [0, 2R): (t + 0.5)/R rising, (2R - t - 0.5)/R falling — exactly the weights
+// ups_tap() produces (all values are multiples of 2^-(e+1)) — except at the two borders, where the
+// clamped source index gives the whole weight to the edge pixel.
+template <int R>
+VSL_HD float ups_weight(int o, int j, int size) {
+  const int t = o - (R * j - R / 2);
+  float w = ((t < R ? t : 2 * R - 1 - t) + 0.5f) * (1.0f / R);
+  if (j == 0 && t < R) w = 1.0f;           // o < R/2: source index clamped to 0
+  if (j == size - 1 && t >= R) w = 1.0f;   // last coarse pixel: no right/bottom neighbour
+  return w;
+}
+template <class C, int R>
+VSL_HD void adjoint_rows_r(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
+  const float* GD = sm + C::oGD;
+  float* Hs = sm + C::oH;
+  constexpr int ncx = C::TW / R + 2;
+  for (int item = tid; item < ncx * C::TH; item += C::NT) {
+    const int y = item / ncx, cj = item - y * ncx;
+    const int jx = t.x0 / R - 1 + cj;
+    float acc = 0.f;
+    if (jx >= 0 && jx < p.ws[s]) {
+      const int base = R * jx - R / 2 - t.x0;  // footprint start in tile coordinates
+#pragma unroll
+      for (int k = 0; k < 2 * R; ++k) {
+        const int x = base + k;
+        if (x >= 0 && x < C::TW) acc += ups_weight<R>(t.x0 + x, jx, p.ws[s]) * GD[y * C::TW + x];
+      }
     }
-    acc += wy * row;
+    Hs[item] = acc;
   }
+}
+template <class C, int R>
+VSL_HD void adjoint_cols_r(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
+  const float* Hs = sm + C::oH;
+  constexpr int ncx = C::TW / R + 2, ncy = C::TH / R + 2;
+  float* out = p.gpart[s] + (size_t)t.cta * ncx * ncy;
+  for (int item = tid; item < ncx * ncy; item += C::NT) {
+    const int cjy = item / ncx, cj = item - cjy * ncx;
+    const int jy = t.y0 / R - 1 + cjy;
+    float acc = 0.f;
+    if (jy >= 0 && jy < p.hs[s]) {
+      const int base = R * jy - R / 2 - t.y0;
+#pragma unroll
+      for (int k = 0; k < 2 * R; ++k) {
+        const int y = base + k;
+        if (y >= 0 && y < C::TH) acc += ups_weight<R>(t.y0 + y, jy, p.hs[s]) * Hs[y * ncx + cj];
+      }
+    }
+    out[item] = acc;
+  }
+}
+template <class C>
+VSL_HD void phase_adjoint_rows(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
+  const int r = p.W / p.ws[s];
+  if (r == 2) adjoint_rows_r<C, 2>(p, t, sm, s, tid);
+  else if (r == 4) adjoint_rows_r<C, 4>(p, t, sm, s, tid);
+  else adjoint_rows_r<C, 8>(p, t, sm, s, tid);
+}
+template <class C>
+VSL_HD void phase_adjoint_cols(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
+  const int r = p.W / p.ws[s];
+  if (r == 2) adjoint_cols_r<C, 2>(p, t, sm, s, tid);
+  else if (r == 4) adjoint_cols_r<C, 4>(p, t, sm, s, tid);
+  else adjoint_cols_r<C, 8>(p, t, sm, s, tid);
+}
+
+// sum of the tile partials that touch coarse pixel (jy, jx) of image b; tiles in row-major order
+VSL_HD float gather_adjoint_partials(const float* __restrict__ gpart, int b, int jy, int jx, int r, int tw, int th,
+                                     int tiles_x, int tiles_y) {
+  const int cw = tw / r, ch = th / r, ncx = cw + 2, ncy = ch + 2;
+  int ty_hi = (jy + 1) / ch, tx_hi = (jx + 1) / cw;
+  int ty_lo = jy - ch <= 0 ? 0 : (jy - ch + ch - 1) / ch, tx_lo = jx - cw <= 0 ? 0 : (jx - cw + cw - 1) / cw;
+  if (ty_hi >= tiles_y) ty_hi = tiles_y - 1;
+  if (tx_hi >= tiles_x) tx_hi = tiles_x - 1;
+  float acc = 0.f;
+  for (int ty = ty_lo; ty <= ty_hi; ++ty)
+    for (int tx = tx_lo; tx <= tx_hi; ++tx) {
+      int cjy = jy - (ty * ch - 1), cjx = jx - (tx * cw - 1);
+      size_t cta = ((size_t)b * tiles_y + ty) * tiles_x + tx;
+      acc += gpart[(cta * ncy + cjy) * ncx + cjx];
+    }
   return acc;
 }
 

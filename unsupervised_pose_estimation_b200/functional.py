@@ -202,12 +202,12 @@ class _FusedLoss(torch.autograd.Function):
 
         # one flat allocation for everything the backward keeps
         n_levels = [B * (H >> s) * (W >> s) for s in plan.scales]
-        sizes = [3 * S + 1, S * F * B * 12] + n_levels + n_levels
+        sizes = [3 * S + 1, S * F * B * 12, S * B * 2] + n_levels + n_levels
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         parts = torch.split(flat, sizes)
-        losses, gradP = parts[0], parts[1]
-        gphoto, gsmooth = parts[2:2 + S], parts[2 + S:2 + 2 * S]
-        buf.losses, buf.grad_P = losses.data_ptr(), gradP.data_ptr()
+        losses, gradP, norm = parts[0], parts[1], parts[2]
+        gphoto, gsmooth = parts[3:3 + S], parts[3 + S:3 + 2 * S]
+        buf.losses, buf.grad_P, buf.smooth_norm = losses.data_ptr(), gradP.data_ptr(), norm.data_ptr()
         masks = []
         for s in range(S):
             buf.grad_disp_photo[s] = gphoto[s].data_ptr()
