@@ -240,14 +240,29 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
       p.smoothb[(s * p.B + b) * 2] = sx;
       p.smoothb[(s * p.B + b) * 2 + 1] = sy;
     }
+    // photometric partials (loss sum, dL/dP) of image b at scale s: 8 lane-groups each add every 8th tile
+    // (independent loads, so they pipeline), then the 8 group sums are added in a fixed order
+    __shared__ double gsum[kSmallNT / 32][40];
     const float* base = p.partials + ((size_t)b * p.tiles_per_image * p.S + s) * p.kpartial;
-    for (int k = threadIdx.x; k < p.kpartial; k += kSmallNT) {
+    const int grp = threadIdx.x >> 5, k = threadIdx.x & 31;
+    for (int k0 = 0; k0 < p.kpartial; k0 += 32) {  // kpartial = 1 + 12 F <= 37
       double acc = 0.0;
-      for (int tl = 0; tl < p.tiles_per_image; ++tl) acc += (double)base[(size_t)tl * p.S * p.kpartial + k];
-      if (k == 0) p.lossb[s * p.B + b] = (float)acc;
-      else {
-        int f = (k - 1) / 12, e = (k - 1) % 12;
-        p.gradP[((size_t)(s * p.F + f) * p.B + b) * 12 + e] = (float)acc;
+      if (k0 + k < p.kpartial)
+        for (int tl = grp; tl < p.tiles_per_image; tl += kSmallNT / 32)
+          acc += (double)base[(size_t)tl * p.S * p.kpartial + k0 + k];
+      __syncthreads();
+      gsum[grp][k] = acc;
+      __syncthreads();
+      if (grp == 0 && k0 + k < p.kpartial) {
+        double tot = 0.0;
+#pragma unroll
+        for (int gi = 0; gi < kSmallNT / 32; ++gi) tot += gsum[gi][k];
+        const int kk = k0 + k;
+        if (kk == 0) p.lossb[s * p.B + b] = (float)tot;
+        else {
+          int f = (kk - 1) / 12, e = (kk - 1) % 12;
+          p.gradP[((size_t)(s * p.F + f) * p.B + b) * 12 + e] = (float)tot;
+        }
       }
     }
   }
