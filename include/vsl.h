@@ -108,7 +108,8 @@ typedef struct VslLossBuffers {
   const float* disp[VSL_MAX_SCALES];    /* outputs[("disp",s)]    [B,1,H>>s,W>>s]                     */
   const float* inv_K;                   /* inputs[("inv_K",0)]    [B,4,4]                             */
   const float* P[VSL_MAX_SRC];          /* (K @ T_f)[:, :3, :]    [B,3,4]  (layers.py:254)            */
-  const float* noise[VSL_MAX_SCALES];   /* torch.randn draw of trainer.py:656 per scale [B,F,H,W]     */
+  const float* noise[VSL_MAX_SCALES];   /* torch.randn draw of trainer.py:656 per scale [B,F,H,W]
+                                           ([B,1,H,W] with VSL_FLAG_AVG_REPROJECTION); unused without automask */
   /* outputs */
   float* losses;                        /* [3*S+1]: min_loss/s (S), loss/s (S), loss, smooth/s (S)    */
   float* mask[VSL_MAX_SCALES];          /* outputs["identity_selection/s"] [B,H,W]; may be null       */

@@ -57,7 +57,7 @@ def test_descriptor_validation_without_gpu():
     assert rc == -1
     rc = lib.vsl_loss_forward_backward(ctypes.byref(make_desc()), None, ws, 64, None)
     assert rc == -2
-    rc = lib.vsl_loss_forward_backward(ctypes.byref(make_desc(flags=_lib.FLAG_AUTOMASK | _lib.FLAG_AVG_REPROJECTION)),
+    rc = lib.vsl_loss_forward_backward(ctypes.byref(make_desc(flags=_lib.FLAG_AUTOMASK | _lib.FLAG_V1_MULTISCALE)),
                                        ctypes.byref(buf), ws, 64, None)
     assert rc == -4
     rc = lib.vsl_loss_forward_backward(ctypes.byref(make_desc()), ctypes.byref(buf), ws, 64, None)

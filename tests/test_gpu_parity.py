@@ -86,6 +86,11 @@ CASES = {
     "no_automask": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "iid", 12, {"disable_automasking": True}),
     "no_automask_one_frame": (2, 64, 96, [0, 1], synthetic.K_KITTI, "smooth", 13, {"disable_automasking": True}),
     "no_automask_stereo": (2, 64, 96, [0, -1, 1, "s"], synthetic.K_KITTI, "iid", 14, {"disable_automasking": True}),
+    "avg_reprojection": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "iid", 17, {"avg_reprojection": True}),
+    "avg_reprojection_c1_stereo": (2, 192, 640, [0, -1, 1, "s"], synthetic.K_KITTI, "smooth", 18, {"avg_reprojection": True}),
+    "avg_no_automask": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "smooth", 19,
+                        {"avg_reprojection": True, "disable_automasking": True}),
+    "avg_one_frame": (2, 64, 96, [0, 1], synthetic.K_KITTI, "iid", 20, {"avg_reprojection": True}),
     "v1_multiscale": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "iid", 15, {"v1_multiscale": True}),
     "v1_multiscale_c1_b2": (2, 192, 640, [0, -1, 1, "s"], synthetic.K_KITTI, "smooth", 16, {"v1_multiscale": True}),
 }
@@ -383,7 +388,7 @@ def test_errors_are_loud():
     cpu_inputs[("color", 0, 0)] = inputs[("color", 0, 0)].cpu()
     with pytest.raises(_lib.VslError):
         path.compute_losses(cpu_inputs, out)
-    for flag in ("avg_reprojection", "predictive_mask"):
+    for flag in ("predictive_mask", "pre_trained_generator"):
         with pytest.raises(NotImplementedError):
             LossPath(make_opt(**{flag: True}), device=DEV).generate_images_pred(inputs, out)
     lib = _lib.load()

@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
     __syncthreads();
     phase_warp<C>(p, g, t, sm, s, tid);
     __syncthreads();
-    if constexpr (C::F == 2) phase_windows_paired<C>(p, g, t, sm, s, tid, ts);
+    if constexpr (C::AVG) phase_windows_avg<C>(p, g, t, sm, s, tid, ts);
+    else if constexpr (C::F == 2) phase_windows_paired<C>(p, g, t, sm, s, tid, ts);
     else phase_windows<C>(p, g, t, sm, s, tid, ts);
     __syncthreads();
     phase_backward<C>(p, g, t, sm, s, tid, ts);
@@ -511,7 +512,9 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
                                     size_t workspace_bytes, void* stream, void* event_before, void* event_after) {
   if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
   if (!buf || !workspace) return VSL_ERR_NULL_POINTER;
-  if (d->flags & ~(VSL_FLAG_AUTOMASK | VSL_FLAG_NO_SSIM)) return VSL_ERR_UNSUPPORTED;  // avg / v1: not in this kernel
+  if (d->flags & ~(VSL_FLAG_AUTOMASK | VSL_FLAG_NO_SSIM | VSL_FLAG_AVG_REPROJECTION)) return VSL_ERR_UNSUPPORTED;
+  const bool avg = (d->flags & VSL_FLAG_AVG_REPROJECTION) && d->num_src > 1;  // the mean of one frame is the frame
+  if (avg && d->image_dtype != VSL_DTYPE_F32) return VSL_ERR_UNSUPPORTED;   // avg + bf16 storage: not instantiated
   if (d->image_dtype != VSL_DTYPE_F32 && d->image_dtype != VSL_DTYPE_BF16) return VSL_ERR_UNSUPPORTED;
   if (d->num_src > 3) return VSL_ERR_UNSUPPORTED;
   const bool automask = (d->flags & VSL_FLAG_AUTOMASK) != 0;
@@ -584,7 +587,10 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   VSL_CUDA_OK(cudaGetLastError());
   if (event_before) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_before, st));
   int rc;
-  if (d->image_dtype == VSL_DTYPE_BF16) {
+  if (avg) {
+    if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, float, true>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, 16, 3, 256, float, true>>(pp, pl, d->batch, st);
+  } else if (d->image_dtype == VSL_DTYPE_BF16) {
     if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256, bf16_t>>(pp, pl, d->batch, st);
     else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, bf16_t>>(pp, pl, d->batch, st);
     else rc = launch_photometric<TileCfg<32, 16, 3, 256, bf16_t>>(pp, pl, d->batch, st);

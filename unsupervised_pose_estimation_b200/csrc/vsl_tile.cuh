@@ -38,10 +38,14 @@ struct PhotoParams {
   int no_ssim;                    // 1: --no_ssim (reprojection loss = mean_c L1)
 };
 
-template <int TW_, int TH_, int F_, int NT_, class Img_ = float>
+template <int TW_, int TH_, int F_, int NT_, class Img_ = float, bool AVG_ = false>
 struct TileCfg {
   typedef Img_ Img;  // storage type of the colour images
   static constexpr int TW = TW_, TH = TH_, F = F_, NT = NT_;
+  // --avg_reprojection (trainer.py:629-630, 649-650): the frames' losses are averaged before the minimum,
+  // so when the warped average wins EVERY frame receives gradient: one coefficient record per frame
+  static constexpr bool AVG = AVG_;
+  static constexpr int NREC = AVG_ ? F_ : 1;
   static constexpr int RW = TW + 4, RH = TH + 4, RN = RW * RH;  // region: tile + 2 halo (warped / target pixels)
   static constexpr int WW = TW + 2, WH = TH + 2, WN = WW * WH;  // windows: tile + 1 halo (SSIM centres)
   static constexpr int IN = TW * TH;                            // interior
@@ -51,7 +55,7 @@ struct TileCfg {
   static constexpr int oX = oTS + 6 * WN;       // warped / source region  [F][3][RN]
   static constexpr int oId = oX + F * 3 * RN;   // identity losses         [F][WN]
   static constexpr int oCoef = oId + F * WN;    // per window: CoefRec (winner's SSIM adjoint coefficients + winner id)
-  static constexpr int oG = oCoef + 12 * WN;    // d warped / d(ix,iy)     [F][6][IN]
+  static constexpr int oG = oCoef + 12 * WN * NREC;  // d warped / d(ix,iy)  [F][6][IN]
   static constexpr int oRed = oG + F * 6 * IN;  // block-reduction scratch [NT/32][1 + F*12]
   static constexpr int oGD = oRed + (NT / 32) * (1 + F * 12);  // d/d(up-sampled disp) of the tile [IN]
   static constexpr int oH = oGD + IN;           // row-reduced adjoint [TH][TW/2 + 2]
@@ -371,6 +375,74 @@ VSL_HD void store_rec(CoefRec* __restrict__ rec, const float coef[9], int idx) {
   *rec = r;
 }
 
+// torch.mean over the frame dimension (sequential sum times float(1/F)), trainer.py:629-630, 649-650
+template <int F>
+VSL_HD float mean_frames(const float* l) {
+  float acc = l[0];
+#pragma unroll
+  for (int f = 1; f < F; ++f) acc = add_rn(acc, l[f]);
+  return mul_rn(acc, 1.0f / (float)F);
+}
+
+// --avg_reprojection: candidates are (mean_f identity_f + noise, mean_f reprojection_f); when the warped
+// mean wins, every frame's record is live with its coefficients scaled by 1/F.
+template <class C>
+VSL_HD void phase_windows_avg(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int s,
+                              int tid, ThreadState<C>& ts) {
+  using XL = XLayout<C>;
+  const float* T = sm + C::oT;
+  const float* TS = sm + C::oTS;
+  const float* X = sm + C::oX;
+  const float* Id = sm + C::oId;
+  CoefRec* Rec = reinterpret_cast<CoefRec*>(sm + C::oCoef);
+  const int HW = p.H * p.W;
+  const float kc = p.wpix * (0.85f / 3.0f) * (-0.5f) * (1.0f / 9.0f) * (1.0f / (float)C::F);
+  for (int i = tid; i < C::WN; i += C::NT) {
+    int wy = i / C::WW, wx = i - wy * C::WW;
+    int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
+    float coef[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) coef[k] = 0.f;
+    if (!(gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)) {
+#pragma unroll
+      for (int f = 0; f < C::F; ++f) store_rec(Rec + f * C::WN + i, coef, -1);
+      continue;
+    }
+    float best = INFINITY;
+    if (p.automask) {
+      float idl[C::F];
+#pragma unroll
+      for (int f = 0; f < C::F; ++f) idl[f] = Id[f * C::WN + i];
+      best = add_rn(mean_frames<C::F>(idl), mul_rn(p.noise[s][(size_t)t.b * HW + gy * p.W + gx], 1e-5f));
+    }
+    float l[C::F];
+#pragma unroll
+    for (int f = 0; f < C::F; ++f) {
+      SsimOut so[3];
+      if (f < 2 * XL::NP)  // one half of a pair buffer (pixel stride 2) or the un-paired odd last frame
+        l[f] = reproj_window<C, 2>(X + XL::pair_base(f >> 1, 0) + (f & 1), 2 * C::RN, T, TS, wy, wx, i, g.arith, so,
+                                   p.no_ssim != 0);
+      else
+        l[f] = reproj_window<C, 1>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) coef[k] = 0.f;
+      if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc, coef);
+      store_rec(Rec + f * C::WN + i, coef, f);
+    }
+    const float avg = mean_frames<C::F>(l);
+    const bool warped = avg < best;  // identity first: ties keep the identity channel
+    if (!warped) {
+#pragma unroll
+      for (int f = 0; f < C::F; ++f) Rec[f * C::WN + i].idx = -1;
+    }
+    bool interior = wy >= 1 && wy <= C::TH && wx >= 1 && wx <= C::TW;
+    if (interior) {
+      ts.loss += warped ? avg : best;
+      if (p.mask[s]) p.mask[s][(size_t)t.b * HW + gy * p.W + gx] = warped ? 1.f : 0.f;
+    }
+  }
+}
+
 template <class C>
 VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int s,
                           int tid, ThreadState<C>& ts) {
@@ -519,7 +591,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
   const int HW = p.H * p.W;
   const float* invK = p.invK + t.b * 16;
   const float* disp = p.disp[s] + (size_t)t.b * p.hs[s] * p.ws[s];
-  const float kl1 = p.no_ssim ? p.wpix * (1.0f / 3.0f) : p.wpix * (0.15f / 3.0f);
+  const float kl1 = (p.no_ssim ? p.wpix * (1.0f / 3.0f) : p.wpix * (0.15f / 3.0f)) / (float)(C::AVG ? C::F : 1);
   for (int j = tid; j < C::IN; j += C::NT) {
     int iy = j / C::TW, ix = j - iy * C::TW;
     int gy = t.y0 + iy, gx = t.x0 + ix;
@@ -540,14 +612,17 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
 #pragma unroll
       for (int dx = -1; dx <= 1; ++dx) {
         float cx = ((dx == -1 && gx == 1) || (dx == 1 && gx == p.W - 2)) ? 2.f : 1.f;
-        const CoefRec rec = Rec[(iy + 1 + dy) * C::WW + (ix + 1 + dx)];  // 3 x 128-bit shared loads
-        if (rec.idx >= 0) used |= 1u << rec.idx;
         const float cnt = cy * cx;
 #pragma unroll
-        for (int f = 0; f < C::F; ++f) {
-          const float cf = rec.idx == f ? cnt : 0.f;  // records of lost windows hold zeros
+        for (int rr = 0; rr < C::NREC; ++rr) {
+          const CoefRec rec = Rec[rr * C::WN + (iy + 1 + dy) * C::WW + (ix + 1 + dx)];  // 3 x 128-bit shared loads
+          if (rec.idx >= 0) used |= 1u << rec.idx;
 #pragma unroll
-          for (int k = 0; k < 9; ++k) acc[f][k] = fmaf(cf, rec.c[k], acc[f][k]);
+          for (int f = 0; f < C::F; ++f) {
+            const float cf = rec.idx == f ? cnt : 0.f;  // records of lost windows hold zeros / idx -1
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[f][k] = fmaf(cf, rec.c[k], acc[f][k]);
+          }
         }
       }
     }
@@ -559,7 +634,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
                               gx, g.arith);
       cam = backproject_pixel(D, invK, gx, gy, g);
       const int center = (iy + 2) * C::RW + (ix + 2);
-      const int own = Rec[(iy + 1) * C::WW + (ix + 1)].idx;
+      const int own = Rec[(iy + 1) * C::WW + (ix + 1)].idx;  // AVG: record 0 is live iff the warped mean won
 #pragma unroll
       for (int f = 0; f < C::F; ++f) {
         if (!(used & (1u << f))) continue;
@@ -568,7 +643,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
         for (int c = 0; c < 3; ++c) {
           float xq = X[XL::at(f, c, center)], yq = T[c * C::RN + center];
           float gc = acc[f][c] + 2.f * xq * acc[f][3 + c] + yq * acc[f][6 + c];
-          if (own == f) gc += (xq > yq) ? kl1 : ((xq < yq) ? -kl1 : 0.f);
+          if (C::AVG ? own >= 0 : own == f) gc += (xq > yq) ? kl1 : ((xq < yq) ? -kl1 : 0.f);
           gix += gc * G[(f * 6 + c) * C::IN + j];
           giy += gc * G[(f * 6 + 3 + c) * C::IN + j];
         }

@@ -109,6 +109,9 @@ class FusedLossPlan:
             raise TypeError("colour images must be stored as float32 or bfloat16")
         self.image_dtype = image_dtype
         self.automask = bool(flags & _lib.FLAG_AUTOMASK)
+        # channels of the tie-break noise: the identity losses are averaged over frames first with
+        # --avg_reprojection (trainer.py:629-630), so the reference draws [B,1,H,W] there
+        self.noise_channels = 1 if (flags & _lib.FLAG_AVG_REPROJECTION) else self.num_src
         d.image_dtype = _lib.DTYPE_BF16 if image_dtype == torch.bfloat16 else _lib.DTYPE_F32
         d.arith = int(arith)
         # Python-double scalars rounded to fp32 at the op, as PyTorch does (layers.py:90-93)
@@ -183,8 +186,8 @@ class _FusedLoss(torch.autograd.Function):
             keep += [t, d]
             if plan.automask:
                 z = _dev(noise[s], "noise[%d]" % s)
-                if tuple(z.shape) != (B, F, H, W):
-                    raise ValueError("noise[%d] has shape %s, expected %s" % (s, tuple(z.shape), (B, F, H, W)))
+                if tuple(z.shape) != (B, plan.noise_channels, H, W):
+                    raise ValueError("noise[%d] has shape %s, expected %s" % (s, tuple(z.shape), (B, plan.noise_channels, H, W)))
                 buf.noise[s] = z.data_ptr()
                 keep.append(z)
         for f in range(F):

@@ -30,8 +30,6 @@ from . import functional as VF
 
 def _unsupported(opt):
     bad = []
-    if getattr(opt, "avg_reprojection", False):
-        bad.append("--avg_reprojection")
     if getattr(opt, "predictive_mask", False):
         bad.append("--predictive_mask")
     if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn":
@@ -59,6 +57,8 @@ class ViewSynthesisLossMixin:
             flags |= _lib.FLAG_AUTOMASK
         if getattr(opt, "no_ssim", False):
             flags |= _lib.FLAG_NO_SSIM
+        if getattr(opt, "avg_reprojection", False):
+            flags |= _lib.FLAG_AVG_REPROJECTION
         v1 = bool(getattr(opt, "v1_multiscale", False))
         key = (opt.batch_size, opt.height, opt.width, tuple(opt.scales), len(opt.frame_ids) - 1,
                opt.min_depth, opt.max_depth, opt.disparity_smoothness, self.vsl_arith, flags, self.vsl_image_dtype, v1)
@@ -144,7 +144,8 @@ class ViewSynthesisLossMixin:
         # one draw per scale, same shape/order/device as trainer.py:656-657
         noise = None
         if plan.automask:
-            noise = [torch.randn((opt.batch_size, F, opt.height, opt.width), device=dev) for _ in opt.scales]
+            noise = [torch.randn((opt.batch_size, plan.noise_channels, opt.height, opt.width), device=dev)
+                     for _ in opt.scales]
         vec, masks = VF.fused_loss(plan, targets, sources, disps, inputs[("inv_K", 0)], Ps, noise)
         losses = {}
         for si, scale in enumerate(opt.scales):
@@ -165,7 +166,7 @@ class ViewSynthesisLossMixin:
             disp = outputs[("disp", scale)]
             noise = None
             if plan.automask:
-                noise = [torch.randn((opt.batch_size, F, plan.height, plan.width), device=disp.device)]
+                noise = [torch.randn((opt.batch_size, plan.noise_channels, plan.height, plan.width), device=disp.device)]
             vec, masks = VF.fused_loss(plan, [inputs[("color", 0, scale)]],
                                        [inputs[("color", f, scale)] for f in opt.frame_ids[1:]], [disp],
                                        inputs[("inv_K", scale)], self._vsl_projections(inputs, outputs, scale), noise)
