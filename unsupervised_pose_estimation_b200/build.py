@@ -45,7 +45,8 @@ def build(force=False, verbose=False):
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libvsl_b200.so (there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("VSL_NVCC_EXTRA", "").split()  # developer knob, e.g. -DVSL_CTAS_PER_SM=2
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
         ["-o", LIB_PATH] + [os.path.join(CSRC, f) for f in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

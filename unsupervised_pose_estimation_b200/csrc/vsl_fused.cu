@@ -58,6 +58,29 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sum 32 per-lane values across the warp at once: each butterfly step halves the number of values a lane
+// holds while adding its partner's copy of the half it keeps (31 shuffles instead of 32 x 5).  On return
+// lane l holds the warp total of v[l].  Fixed order, so the result is reproducible.
+template <int N>
+__device__ __forceinline__ void butterfly_step(float (&v)[32], int lane) {
+  constexpr int H = N / 2;
+  const bool up = (lane & H) != 0;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const float keep = up ? v[i + H] : v[i];
+    const float send = up ? v[i] : v[i + H];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+  }
+}
+__device__ __forceinline__ float warp_sum32(float (&v)[32], int lane) {
+  butterfly_step<32>(v, lane);
+  butterfly_step<16>(v, lane);
+  butterfly_step<8>(v, lane);
+  butterfly_step<4>(v, lane);
+  butterfly_step<2>(v, lane);
+  return v[0];
+}
+
 // block-wide sum in a fixed order; result valid in every thread
 template <int NT>
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
@@ -188,12 +211,16 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
     phase_backward<C>(p, g, t, sm, s, tid, ts);
     // deterministic block reduction of (loss, dP) -> one partial per CTA and scale
     const int w = tid >> 5, l = tid & 31;
-    float v = warp_sum(ts.loss);
-    if (l == 0) red[w * C::kPartial] = v;
 #pragma unroll
-    for (int k = 0; k < C::F * 12; ++k) {
-      v = warp_sum(ts.dP[k]);
-      if (l == 0) red[w * C::kPartial + 1 + k] = v;
+    for (int k0 = 0; k0 < C::kPartial; k0 += 32) {  // (loss, dP[...]) in batches of 32 values
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = k0 + i;
+        v[i] = k == 0 ? ts.loss : (k < C::kPartial ? ts.dP[k - 1 < C::F * 12 ? k - 1 : 0] : 0.f);
+      }
+      const float tot = warp_sum32(v, l);
+      if (k0 + l < C::kPartial) red[w * C::kPartial + k0 + l] = tot;
     }
     __syncthreads();
     if (tid < C::kPartial) {
