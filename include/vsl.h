@@ -66,7 +66,9 @@ enum {
   VSL_ARITH_TAP_NOFMA = 1 << 5,    /* probe: bilinear tap accumulation without FMA          */
   VSL_ARITH_MEAN_DIV = 1 << 6,     /* probe: channel mean as sum/3 instead of sum*(1/3)     */
   VSL_ARITH_DOT3_NOFMA = 1 << 7,   /* K=3 bmm (rays) adds un-fused products: cuBLAS, batch 1 */
-  VSL_ARITH_DOT3_REVERSE = 1 << 8  /* probe: k-descending accumulation in the K=3 bmm       */
+  VSL_ARITH_DOT3_REVERSE = 1 << 8, /* probe: k-descending accumulation in the K=3 bmm       */
+  VSL_ARITH_DOTKT_NOFMA = 1 << 9,  /* K@T (4x4x4 bmm, layers.py:254) adds un-fused products  */
+  VSL_ARITH_DOTKT_REVERSE = 1 << 10 /* probe: k-descending accumulation in K@T               */
 };
 
 /* Problem descriptor: what Trainer.__init__ fixes once (trainer.py:245-259, options.py). */
@@ -107,7 +109,11 @@ typedef struct VslLossBuffers {
   const void* source[VSL_MAX_SRC];      /* inputs[("color",f,0)]  [B,3,H,W] per source frame          */
   const float* disp[VSL_MAX_SCALES];    /* outputs[("disp",s)]    [B,1,H>>s,W>>s]                     */
   const float* inv_K;                   /* inputs[("inv_K",0)]    [B,4,4]                             */
-  const float* P[VSL_MAX_SRC];          /* (K @ T_f)[:, :3, :]    [B,3,4]  (layers.py:254)            */
+  const float* P[VSL_MAX_SRC];          /* (K @ T_f)[:, :3, :]    [B,3,4]  (layers.py:254); may be null
+                                           for a frame whose T is given                               */
+  const float* K;                       /* inputs[("K",0)]        [B,4,4]  (needed with T)            */
+  const float* T[VSL_MAX_SRC];          /* outputs[("cam_T_cam",0,f)] / inputs["stereo_T"] [B,4,4]: the
+                                           kernel then forms P_f = (K @ T_f)[:3,:] itself             */
   const float* noise[VSL_MAX_SCALES];   /* torch.randn draw of trainer.py:656 per scale [B,F,H,W]
                                            ([B,1,H,W] with VSL_FLAG_AVG_REPROJECTION); unused without automask */
   /* outputs */
@@ -137,10 +143,11 @@ int vsl_event_elapsed_ms(void* start, void* stop, float* ms);
 
 /* Chain rule from the loss dict to the leaves: `upstream` holds dL/d(losses[k]) on the DEVICE in
  * the order min_loss/0..S-1, loss/0..S-1, loss (2S+1 floats; trainer.py:672-685 defines how the
- * entries depend on each other).  Writes grad_disp[s] [B,1,H>>s,W>>s] and grad_P_out [F][B][12]. */
+ * entries depend on each other).  Writes grad_disp[s] [B,1,H>>s,W>>s] and, each optional (null to skip),
+ * grad_P_out [F][B][12] = dL/dP_f and grad_T_out [F][B][16] = K[:3,:]^T dL/dP_f (needs buf->K). */
 int vsl_loss_combine_grads(const VslDesc* desc, const float* upstream,
                            const VslLossBuffers* buf, float* const grad_disp[VSL_MAX_SCALES],
-                           float* grad_P_out, void* stream);
+                           float* grad_P_out, float* grad_T_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Side outputs of Trainer.generate_images_pred (trainer.py:491-541) for one scale:

@@ -27,6 +27,7 @@ static void run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
         t.b = b; t.x0 = tx * C::TW; t.y0 = ty * C::TH;
         t.cta = (b * tiles_y + ty) * tiles_x + tx;
         size_t img_off = (size_t)b * 3 * p.H * p.W;
+        for (int tid = 0; tid < C::NT; ++tid) phase_pose<C>(p, p.g, t, sm.data(), tid);
         for (int tid = 0; tid < C::NT; ++tid) phase_load_region<C>(p, t, (const float*)p.tgt + img_off, sm.data() + C::oT, tid);
         for (int tid = 0; tid < C::NT; ++tid) phase_target_stats<C>(p, t, sm.data(), tid);
         for (int tid = 0; tid < C::NT; ++tid) phase_load_sources<C>(p, t, sm.data(), tid);

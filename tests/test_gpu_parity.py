@@ -213,6 +213,32 @@ def test_bf16_image_storage(frames):
         run_ours(opt, mixed, outputs, leaves)
 
 
+def test_pose_given_as_T_equals_pose_given_as_P():
+    """K@T formed inside the kernel (calibrated to cuBLAS's order) == torch.matmul(K, T)[:, :3, :] fed as P;
+    the returned dL/dT equals autograd's K[:3,:]^T dL/dP."""
+    opt, inputs, outputs, leaves = build_case("stereo_c3_b2")
+    S, F = len(opt.scales), len(opt.frame_ids) - 1
+    plan = LossPath(make_opt(**vars(opt)), device=DEV)._vsl_plan()
+    K = inputs[("K", 0)]
+    Ts = []
+    for f in opt.frame_ids[1:]:
+        T = inputs["stereo_T"] if f == "s" else L.transformation_from_parameters(
+            leaves[("axisangle", 0, f)][:, 0].detach(), leaves[("translation", 0, f)][:, 0].detach(), f < 0)
+        Ts.append(T.clone().requires_grad_(f != "s"))
+    args = ([inputs[("color", 0, s)] for s in opt.scales], [inputs[("color", f, 0)] for f in opt.frame_ids[1:]],
+            [leaves[("disp", s)] for s in opt.scales], inputs[("inv_K", 0)])
+    torch.manual_seed(3)
+    noise = [torch.randn(opt.batch_size, F, opt.height, opt.width, device=DEV) for _ in opt.scales]
+    vec_t, masks_t = VF.fused_loss(plan, *args, None, noise, K=K, Ts=Ts)
+    vec_p, masks_p = VF.fused_loss(plan, *args, [torch.matmul(K, T)[:, :3, :] for T in Ts], noise)
+    assert torch.equal(vec_t, vec_p)
+    for a, b in zip(masks_t, masks_p):
+        assert torch.equal(a, b)
+    wrt = [leaves[("disp", s)] for s in opt.scales] + Ts[:2]
+    for a, b in zip(torch.autograd.grad(vec_t[2 * S], wrt), torch.autograd.grad(vec_p[2 * S], wrt)):
+        assert ((a - b).norm() / b.norm()).item() <= 1e-6
+
+
 def test_rng_stream_is_consumed_like_the_reference():
     opt, inputs, outputs, leaves = build_case("mono_iid_64x96")
     run_oracle(opt, inputs, outputs, leaves, seed=7)

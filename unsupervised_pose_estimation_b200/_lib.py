@@ -30,6 +30,8 @@ ARITH_TAP_NOFMA = 1 << 5
 ARITH_MEAN_DIV = 1 << 6
 ARITH_DOT3_NOFMA = 1 << 7
 ARITH_DOT3_REVERSE = 1 << 8
+ARITH_DOTKT_NOFMA = 1 << 9
+ARITH_DOTKT_REVERSE = 1 << 10
 
 # every symbol include/vsl.h declares (tests check the shared object exports all of them)
 EXPORTED_SYMBOLS = [
@@ -59,6 +61,7 @@ class VslLossBuffers(Structure):
     _fields_ = [
         ("target", c_void_p * VSL_MAX_SCALES), ("source", c_void_p * VSL_MAX_SRC),
         ("disp", c_void_p * VSL_MAX_SCALES), ("inv_K", c_void_p), ("P", c_void_p * VSL_MAX_SRC),
+        ("K", c_void_p), ("T", c_void_p * VSL_MAX_SRC),
         ("noise", c_void_p * VSL_MAX_SCALES),
         ("losses", c_void_p), ("mask", c_void_p * VSL_MAX_SCALES),
         ("grad_disp_photo", c_void_p * VSL_MAX_SCALES), ("grad_disp_smooth", c_void_p * VSL_MAX_SCALES),
@@ -105,7 +108,7 @@ def load():
     lib.vsl_event_destroy.argtypes = [vp]
     lib.vsl_event_elapsed_ms.argtypes = [vp, vp, POINTER(c_float)]
     lib.vsl_loss_combine_grads.argtypes = [POINTER(VslDesc), vp, POINTER(VslLossBuffers),
-                                           POINTER(c_void_p * VSL_MAX_SCALES), vp, vp]
+                                           POINTER(c_void_p * VSL_MAX_SCALES), vp, vp, vp]
     lib.vsl_warp_forward.argtypes = [POINTER(VslDesc), c_int, vp, vp, POINTER(c_void_p * VSL_MAX_SRC),
                                      POINTER(c_void_p * VSL_MAX_SRC), vp, POINTER(c_void_p * VSL_MAX_SRC),
                                      POINTER(c_void_p * VSL_MAX_SRC), vp]

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
   const int tid = threadIdx.x;
   const size_t img_off = (size_t)t.b * 3 * p.H * p.W;
 
+  phase_pose<C>(p, g, t, sm, tid);
   phase_load_region<C>(p, t, (const typename C::Img*)p.tgt + img_off, sm + C::oT, tid);
   __syncthreads();
   phase_target_stats<C>(p, t, sm, tid);
@@ -334,7 +335,9 @@ struct CombineParams {
   const float* gsmooth[kMaxScales];
   float* out[kMaxScales];
   const float* gradP;  // [S][F][B][12]
-  float* gradP_out;    // [F][B][12]
+  float* gradP_out;    // [F][B][12] or null
+  float* gradT_out;    // [F][B][16] or null: K[:3,:]^T @ dP
+  const float* K;      // [B,4,4]
   const float* norm;   // [S][B][2]
   int B, S, F, chunks0;
   int n[kMaxScales], scale_id[kMaxScales];
@@ -355,7 +358,8 @@ __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
     for (int i = chunk * kChunk + threadIdx.x; i < min(p.n[s], (chunk + 1) * kChunk); i += kSmallNT)
       o[i] = a * gp[i] + bb * (gs[i] * inv - corr);
   }
-  if (chunk == 0 && s == 0 && p.gradP_out) {
+  if (chunk == 0 && s == 0 && (p.gradP_out || p.gradT_out)) {
+    __shared__ float gP[kMaxSrc * 12];
     for (int k = threadIdx.x; k < p.F * 12; k += kSmallNT) {
       int f = k / 12, e = k % 12;
       float acc = 0.f;
@@ -363,7 +367,17 @@ __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
         float a = p.up[si] + p.up[p.S + si] + tot;
         acc += a * p.gradP[((size_t)(si * p.F + f) * p.B + b) * 12 + e];
       }
-      p.gradP_out[((size_t)f * p.B + b) * 12 + e] = acc;
+      gP[k] = acc;
+      if (p.gradP_out) p.gradP_out[((size_t)f * p.B + b) * 12 + e] = acc;
+    }
+    __syncthreads();
+    if (p.gradT_out) {  // P = K[:3,:] @ T  ->  dL/dT = K[:3,:]^T @ dL/dP
+      for (int k = threadIdx.x; k < p.F * 16; k += kSmallNT) {
+        int f = k / 16, e = k % 16, r = e >> 2, n = e & 3;
+        const float* Kb = p.K + b * 16;
+        p.gradT_out[((size_t)f * p.B + b) * 16 + e] =
+            Kb[r] * gP[f * 12 + n] + Kb[4 + r] * gP[f * 12 + 4 + n] + Kb[8 + r] * gP[f * 12 + 8 + n];
+      }
     }
   }
 }
@@ -554,8 +568,10 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     if (!buf->target[s] || !buf->disp[s] || (automask && !buf->noise[s]) || !buf->grad_disp_photo[s] ||
         !buf->grad_disp_smooth[s])
       return VSL_ERR_NULL_POINTER;
-  for (int f = 0; f < F; ++f)
-    if (!buf->source[f] || !buf->P[f]) return VSL_ERR_NULL_POINTER;
+  for (int f = 0; f < F; ++f) {
+    if (!buf->source[f] || (!buf->P[f] && !buf->T[f])) return VSL_ERR_NULL_POINTER;
+    if (buf->T[f] && !buf->K) return VSL_ERR_NULL_POINTER;
+  }
   if (d->scale_ids[0] != 0) return VSL_ERR_UNSUPPORTED;  // level 0 is the photometric target
 
   cudaStream_t st = (cudaStream_t)stream;
@@ -571,7 +587,8 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   pp.g = make_geo(d);
   pp.wpix = 1.0f / ((float)d->batch * d->height * d->width);
   pp.partials = ws + pl.off_partials;
-  for (int f = 0; f < F; ++f) { pp.src[f] = buf->source[f]; pp.P[f] = buf->P[f]; }
+  pp.K = buf->K;
+  for (int f = 0; f < F; ++f) { pp.src[f] = buf->source[f]; pp.P[f] = buf->P[f]; pp.T[f] = buf->T[f]; }
   for (int s = 0; s < S; ++s) {
     int e = d->scale_ids[s];
     int hs = d->height >> e, wsz = d->width >> e;
@@ -634,14 +651,15 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
 }
 
 int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLossBuffers* buf,
-                           float* const grad_disp[VSL_MAX_SCALES], float* grad_P_out, void* stream) {
+                           float* const grad_disp[VSL_MAX_SCALES], float* grad_P_out, float* grad_T_out, void* stream) {
   if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
   if (!upstream || !buf || !grad_disp) return VSL_ERR_NULL_POINTER;
   CombineParams cp = {};
   cp.up = upstream; cp.B = d->batch; cp.S = d->num_scales; cp.F = d->num_src;
   cp.chunks0 = (d->height * d->width + kChunk - 1) / kChunk;
   cp.smooth_weight = d->smooth_weight;
-  cp.gradP = buf->grad_P; cp.gradP_out = grad_P_out;
+  cp.gradP = buf->grad_P; cp.gradP_out = grad_P_out; cp.gradT_out = grad_T_out; cp.K = buf->K;
+  if (grad_T_out && !buf->K) return VSL_ERR_NULL_POINTER;
   cp.norm = buf->smooth_norm;
   if (!cp.norm) return VSL_ERR_NULL_POINTER;
   for (int s = 0; s < d->num_scales; ++s) {
@@ -651,7 +669,7 @@ int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLos
     cp.scale_id[s] = e + d->smooth_level_bias;
     cp.gphoto[s] = buf->grad_disp_photo[s]; cp.gsmooth[s] = buf->grad_disp_smooth[s]; cp.out[s] = grad_disp[s];
   }
-  if (grad_P_out && !buf->grad_P) return VSL_ERR_NULL_POINTER;
+  if ((grad_P_out || grad_T_out) && !buf->grad_P) return VSL_ERR_NULL_POINTER;
   dim3 grid(cp.chunks0, d->batch, d->num_scales);
   k_combine<<<grid, kSmallNT, 0, (cudaStream_t)stream>>>(cp);
   VSL_CUDA_OK(cudaGetLastError());

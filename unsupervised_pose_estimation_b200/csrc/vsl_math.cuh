@@ -86,7 +86,8 @@ VSL_HD F2 sub2(F2 a, F2 b) { return add2(a, f2(-b.x, -b.y)); }  // a + (-b) roun
 // arithmetic-order selectors; mirror VSL_ARITH_* in include/vsl.h
 enum : int {
   kTrueDiv = 1 << 0, kDotNoFma = 1 << 1, kDotReverse = 1 << 2, kUpsRight = 1 << 3,
-  kUpsNoFma = 1 << 4, kTapNoFma = 1 << 5, kMeanDiv = 1 << 6, kDot3NoFma = 1 << 7, kDot3Reverse = 1 << 8
+  kUpsNoFma = 1 << 4, kTapNoFma = 1 << 5, kMeanDiv = 1 << 6, kDot3NoFma = 1 << 7, kDot3Reverse = 1 << 8,
+  kDotKTNoFma = 1 << 9, kDotKTReverse = 1 << 10
 };
 
 // ---- bmm dot products ----------------------------------------------------------------------------
@@ -104,6 +105,12 @@ VSL_HD float dot4(float a0, float b0, float a1, float b1, float a2, float b2, fl
     return add_rn(add_rn(add_rn(mul_rn(a0, b0), mul_rn(a1, b1)), mul_rn(a2, b2)), mul_rn(a3, b3));
   if (arith & kDotReverse) return fma_rn(a0, b0, fma_rn(a1, b1, fma_rn(a2, b2, mul_rn(a3, b3))));
   return fma_rn(a3, b3, fma_rn(a2, b2, fma_rn(a1, b1, mul_rn(a0, b0))));
+}
+
+// P = (K @ T)[:3,:] (layers.py:254): a [B,4,4] x [B,4,4] bmm, calibrated separately (its own cuBLAS kernel)
+VSL_HD float dot4kt(float a0, float b0, float a1, float b1, float a2, float b2, float a3, float b3, int arith) {
+  return dot4(a0, b0, a1, b1, a2, b2, a3, b3,
+              ((arith & kDotKTNoFma) ? kDotNoFma : 0) | ((arith & kDotKTReverse) ? kDotReverse : 0));
 }
 
 // ---- F.interpolate(disp, [H,W], "bilinear", align_corners=False)  (trainer.py:500-501) --------

@@ -22,7 +22,9 @@ struct PhotoParams {
   const void* src[kMaxSrc];       // [B,3,H,W]
   const float* disp[kMaxScales];  // [B,1,hs,ws]
   const float* invK;              // [B,4,4]
-  const float* P[kMaxSrc];        // [B,3,4]
+  const float* P[kMaxSrc];        // [B,3,4] = (K@T_f)[:, :3, :], or null when T[f] is given
+  const float* K;                 // [B,4,4]  inputs[("K", 0)]
+  const float* T[kMaxSrc];        // [B,4,4]  cam_T_cam / stereo_T: P is then formed in the kernel (layers.py:254)
   const float* noise[kMaxScales]; // [B,F,H,W]
   float* mask[kMaxScales];        // [B,H,W] or null
   float* gD[kMaxScales];          // identity levels: [B,H,W] d(min_loss/s)/d disp_s, written directly
@@ -59,7 +61,8 @@ struct TileCfg {
   static constexpr int oRed = oG + F * 6 * IN;  // block-reduction scratch [NT/32][1 + F*12]
   static constexpr int oGD = oRed + (NT / 32) * (1 + F * 12);  // d/d(up-sampled disp) of the tile [IN]
   static constexpr int oH = oGD + IN;           // row-reduced adjoint [TH][TW/2 + 2]
-  static constexpr int kFloats = oH + TH * (TW / 2 + 2);
+  static constexpr int oP = oH + TH * (TW / 2 + 2);  // this image's projection matrices [F][12]
+  static constexpr int kFloats = oP + F * 12;
   static constexpr int kBytes = kFloats * 4;
   static constexpr int kPartial = 1 + F * 12;
   static_assert(oCoef % 4 == 0, "CoefRec needs 16-byte alignment");
@@ -84,6 +87,23 @@ struct TileCtx {
   int b, x0, y0;  // image index, tile origin (pixels)
   int cta;        // linear CTA id
 };
+
+// ---- phase: projection matrices of this image, P_f = (K @ T_f)[:3,:]  (layers.py:254) -------------
+template <class C>
+VSL_HD void phase_pose(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int tid) {
+  for (int k = tid; k < C::F * 12; k += C::NT) {
+    const int f = k / 12, e = k - f * 12, i = e >> 2, n = e & 3;
+    float v;
+    if (p.T[f]) {
+      const float* Kb = p.K + t.b * 16 + i * 4;
+      const float* Tb = p.T[f] + t.b * 16 + n;
+      v = dot4kt(Kb[0], Tb[0], Kb[1], Tb[4], Kb[2], Tb[8], Kb[3], Tb[12], g.arith);
+    } else {
+      v = p.P[f][t.b * 12 + e];
+    }
+    sm[C::oP + k] = v;
+  }
+}
 
 // ---- phase: load an image tile + 2 halo into a region buffer, reflect-mapped --------------------
 template <class C>
@@ -321,7 +341,7 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
       int j = (ry - 2) * C::TW + (rx - 2);
 #pragma unroll
       for (int f = 0; f < C::F; ++f) {
-        Proj pr = project_pixel(cam, p.P[f] + t.b * 12, g);
+        Proj pr = project_pixel(cam, sm + C::oP + f * 12, g);
         Taps tp = bilinear_taps(pr, p.W, p.H);
         const typename C::Img* img = (const typename C::Img*)p.src[f] + (size_t)t.b * 3 * HW + pr.y0 * p.W + pr.x0;
         int dx = tp.x1ok ? 1 : 0, dy = tp.y1ok ? p.W : 0;
@@ -647,7 +667,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
           gix += gc * G[(f * 6 + c) * C::IN + j];
           giy += gc * G[(f * 6 + 3 + c) * C::IN + j];
         }
-        const float* P = p.P[f] + t.b * 12;
+        const float* P = sm + C::oP + f * 12;
         float c0 = P[0] * cam.X + P[1] * cam.Y + P[2] * cam.Z + P[3];
         float c1 = P[4] * cam.X + P[5] * cam.Y + P[6] * cam.Z + P[7];
         float c2 = P[8] * cam.X + P[9] * cam.Y + P[10] * cam.Z + P[11];

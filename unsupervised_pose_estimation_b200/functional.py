@@ -52,24 +52,29 @@ def calibrate_arith(batch, height, width, device):
     gen = torch.Generator(device="cpu").manual_seed(1234)
     M = torch.randn(batch, 4, 4, generator=gen).to(device)
     bits = 0
-    for k, variants in ((3, (0, _lib.ARITH_DOT3_NOFMA, _lib.ARITH_DOT3_REVERSE)),
-                        (4, (0, _lib.ARITH_DOT_NOFMA, _lib.ARITH_DOT_REVERSE))):
+    # (k, columns, probe variants -> plan bits): rays [B,3,3]x[B,3,HW]; projection [B,3,4]x[B,4,HW];
+    # P = (K@T)[:, :3, :], a [B,4,4]x[B,4,4] product (probed through its first three rows)
+    probes = ((3, n, {0: 0, _lib.ARITH_DOT3_NOFMA: _lib.ARITH_DOT3_NOFMA, _lib.ARITH_DOT3_REVERSE: _lib.ARITH_DOT3_REVERSE}),
+              (4, n, {0: 0, _lib.ARITH_DOT_NOFMA: _lib.ARITH_DOT_NOFMA, _lib.ARITH_DOT_REVERSE: _lib.ARITH_DOT_REVERSE}),
+              (4, 4, {0: 0, _lib.ARITH_DOT_NOFMA: _lib.ARITH_DOTKT_NOFMA, _lib.ARITH_DOT_REVERSE: _lib.ARITH_DOTKT_REVERSE}))
+    for k, n, variants in probes:
         X = torch.randn(batch, k, n, generator=gen).to(device)
         A = M[:, :3, :k]                       # sliced like inv_K[:, :3, :3] / (K@T)[:, :3, :]
+        full_kt = (n == 4)
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
-            ref = torch.matmul(A, X)
+            ref = torch.matmul(M, X)[:, :3, :].contiguous() if full_kt else torch.matmul(A, X)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32
         Ac = A.contiguous()
         out = torch.empty_like(ref)
         chosen = None
-        for v in variants:
+        for v, plan_bits in variants.items():
             check(lib.vsl_probe_bmm(batch, k, n, v, Ac.data_ptr(), X.data_ptr(), out.data_ptr(), _stream()),
                   "vsl_probe_bmm")
             if torch.equal(out, ref):
-                chosen = v
+                chosen = plan_bits
                 break
         if chosen is None:
             raise _lib.VslError("could not reproduce torch.bmm's rounding for [%d,3,%d]x[%d,%d,%d] on this device; "
@@ -168,9 +173,9 @@ class _FusedLoss(torch.autograd.Function):
     """losses vector [2S+1] = (min_loss/s ..., loss/s ..., loss), masks...  <- disps, P matrices."""
 
     @staticmethod
-    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, *leaves):
+    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, *leaves):
         S, F = len(plan.scales), plan.num_src
-        disps, Ps = leaves[:S], leaves[S:]
+        disps, Ps = leaves[:S], leaves[S:]   # Ps: projection matrices [B,3,4], or poses T [B,4,4] if use_T
         dev = disps[0].device
         B, H, W = plan.batch, plan.height, plan.width
         buf = VslLossBuffers()
@@ -192,11 +197,21 @@ class _FusedLoss(torch.autograd.Function):
                 keep.append(z)
         for f in range(F):
             src = _dev(sources[f], "source[%d]" % f, plan.image_dtype)
-            P = _dev(Ps[f], "P[%d]" % f)
-            if tuple(src.shape) != (B, 3, H, W) or tuple(P.shape) != (B, 3, 4):
-                raise ValueError("source/P[%d] have shapes %s / %s" % (f, tuple(src.shape), tuple(P.shape)))
-            buf.source[f], buf.P[f] = src.data_ptr(), P.data_ptr()
+            P = _dev(Ps[f], "T[%d]" % f if use_T else "P[%d]" % f)
+            if tuple(src.shape) != (B, 3, H, W) or tuple(P.shape) != ((B, 4, 4) if use_T else (B, 3, 4)):
+                raise ValueError("source / pose[%d] have shapes %s / %s" % (f, tuple(src.shape), tuple(P.shape)))
+            buf.source[f] = src.data_ptr()
+            if use_T:
+                buf.T[f] = P.data_ptr()
+            else:
+                buf.P[f] = P.data_ptr()
             keep += [src, P]
+        if use_T:
+            Kc = _dev(K, "K")
+            if tuple(Kc.shape) != (B, 4, 4):
+                raise ValueError("K has shape %s" % (tuple(Kc.shape),))
+            buf.K = Kc.data_ptr()
+            keep.append(Kc)
         iK = _dev(inv_K, "inv_K")
         if tuple(iK.shape) != (B, 4, 4):
             raise ValueError("inv_K has shape %s" % (tuple(iK.shape),))
@@ -224,7 +239,7 @@ class _FusedLoss(torch.autograd.Function):
         check(plan.lib.vsl_loss_forward_backward_timed(ctypes.byref(plan.desc), ctypes.byref(buf), ws.data_ptr(),
                                                        plan.ws_bytes, _stream(), ev[0], ev[1]),
               "vsl_loss_forward_backward")
-        ctx.plan, ctx.buf, ctx.flat, ctx.keep = plan, buf, flat, keep
+        ctx.plan, ctx.buf, ctx.flat, ctx.keep, ctx.use_T = plan, buf, flat, keep, use_T
         ctx.mark_non_differentiable(*masks)
         out = losses[:2 * S + 1]
         ctx.smooth_terms = losses[2 * S + 1:]
@@ -237,28 +252,34 @@ class _FusedLoss(torch.autograd.Function):
         dev = gvec.device
         up = _dev(gvec, "upstream gradient")
         n_levels = [int(np.prod(sh)) for sh in plan.level_shapes]
-        flat = torch.empty(sum(n_levels) + F * B * 12, dtype=torch.float32, device=dev)
-        parts = torch.split(flat, n_levels + [F * B * 12])
+        pe = 16 if ctx.use_T else 12   # gradient w.r.t. T [B,4,4] or P [B,3,4]
+        flat = torch.empty(sum(n_levels) + F * B * pe, dtype=torch.float32, device=dev)
+        parts = torch.split(flat, n_levels + [F * B * pe])
         out_ptrs = (ctypes.c_void_p * VSL_MAX_SCALES)()
         for s in range(S):
             out_ptrs[s] = parts[s].data_ptr()
         gP = parts[S]
         check(plan.lib.vsl_loss_combine_grads(ctypes.byref(plan.desc), up.data_ptr(), ctypes.byref(ctx.buf),
-                                              ctypes.byref(out_ptrs), gP.data_ptr(), _stream()),
+                                              ctypes.byref(out_ptrs), None if ctx.use_T else gP.data_ptr(),
+                                              gP.data_ptr() if ctx.use_T else None, _stream()),
               "vsl_loss_combine_grads")
         gd = [parts[s].view(plan.level_shapes[s]) for s in range(S)]
-        gPs = [gP.view(F, B, 3, 4)[f] for f in range(F)]
-        return (None, None, None, None, None, None) + tuple(gd) + tuple(gPs)
+        gPs = [gP.view(F, B, 4, 4)[f] if ctx.use_T else gP.view(F, B, 3, 4)[f] for f in range(F)]
+        return (None, None, None, None, None, None, None, None) + tuple(gd) + tuple(gPs)
 
 
-def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True):
+def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, K=None, Ts=None):
     """Run the fused path.  Returns (loss_vector[2S+1], [mask_s ...]).
 
     loss_vector order: min_loss/s for every scale, loss/s for every scale, loss
-    (reference trainer.py:672-685).  Gradients flow to ``disps`` and ``Ps``.
+    (reference trainer.py:672-685).  The camera of each source frame is given either as ``Ps``
+    (projection matrices (K@T)[:, :3, :]) or, preferred, as ``K`` + ``Ts`` (the 4x4 poses): the kernel then
+    forms K@T itself and the backward returns dL/dT directly, with no torch matmul in between.
+    Gradients flow to ``disps`` and to ``Ps`` / ``Ts``.
     """
-    res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise or []), bool(want_mask),
-                           *(list(disps) + list(Ps)))
+    use_T = Ts is not None
+    res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise or []), bool(want_mask), K, use_T,
+                           *(list(disps) + list(Ts if use_T else Ps)))
     return res[0], list(res[1:])
 
 

@@ -92,6 +92,10 @@ class ViewSynthesisLossMixin:
             return [(pl, 0, s) for pl, s in zip(plan, self.opt.scales)]
         return [(plan, si, 0) for si, _ in enumerate(self.opt.scales)]
 
+    def _vsl_poses(self, inputs, outputs):
+        """T_f per source frame: stereo_T or cam_T_cam (reference trainer.py:510-513)."""
+        return [inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)] for f in self.opt.frame_ids[1:]]
+
     def _vsl_projections(self, inputs, outputs, source_scale=0):
         """P_f = (K @ T_f)[:, :3, :] per source frame (reference layers.py:254; T as trainer.py:510-513)."""
         K = inputs[("K", source_scale)]
@@ -139,14 +143,14 @@ class ViewSynthesisLossMixin:
         targets = [inputs[("color", 0, s)] for s in opt.scales]
         sources = [inputs[("color", f, 0)] for f in opt.frame_ids[1:]]
         disps = [outputs[("disp", s)] for s in opt.scales]
-        Ps = self._vsl_projections(inputs, outputs)
         dev = disps[0].device
         # one draw per scale, same shape/order/device as trainer.py:656-657
         noise = None
         if plan.automask:
             noise = [torch.randn((opt.batch_size, plan.noise_channels, opt.height, opt.width), device=dev)
                      for _ in opt.scales]
-        vec, masks = VF.fused_loss(plan, targets, sources, disps, inputs[("inv_K", 0)], Ps, noise)
+        vec, masks = VF.fused_loss(plan, targets, sources, disps, inputs[("inv_K", 0)], None, noise,
+                                   K=inputs[("K", 0)], Ts=self._vsl_poses(inputs, outputs))
         losses = {}
         for si, scale in enumerate(opt.scales):
             losses["min_loss/{}".format(scale)] = vec[si]
@@ -169,7 +173,8 @@ class ViewSynthesisLossMixin:
                 noise = [torch.randn((opt.batch_size, plan.noise_channels, plan.height, plan.width), device=disp.device)]
             vec, masks = VF.fused_loss(plan, [inputs[("color", 0, scale)]],
                                        [inputs[("color", f, scale)] for f in opt.frame_ids[1:]], [disp],
-                                       inputs[("inv_K", scale)], self._vsl_projections(inputs, outputs, scale), noise)
+                                       inputs[("inv_K", scale)], None, noise, K=inputs[("K", scale)],
+                                       Ts=self._vsl_poses(inputs, outputs))
             losses["min_loss/{}".format(scale)] = vec[0]
             losses["loss/{}".format(scale)] = vec[1]
             if plan.automask:
