@@ -60,6 +60,27 @@ def peak_hbm_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE it
+    allocates pinned host buffers, so first-touch places them on the GPU's NUMA node and the per-step H2D
+    copies of 2/4/8 ranks do not all cross one socket's memory controllers.  Best effort: returns the NUMA
+    node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return int(open(base + "/numa_node").read())
+    except Exception:
+        return None
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -238,6 +259,7 @@ def main():
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -359,7 +381,8 @@ def main():
             "config": workload_config(args, cfg),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": stager.bytes_per_batch,
                     "d2h_bytes_per_step": int(vec.numel() * 4), "ms_per_step": e2e_ms / args.steps,
-                    "note": "H2D of step i+1 (copy stream, pinned) overlaps the kernels of step i; loss dict read back every step"},
+                    "note": "H2D of step i+1 (copy stream, pinned) overlaps the kernels of step i; loss dict read back every step",
+                    "numa_node_rank0": numa_node},
             "gpu_launches": 5 * args.steps,
             "kernels_per_step": ["k_smooth_mean", "k_smooth_terms", "k_photometric", "k_epilogue", "k_combine"],
             "host_wall_ms_per_step": 1e3 * t_wall / args.steps,
