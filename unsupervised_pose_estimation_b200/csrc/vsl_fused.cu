@@ -305,24 +305,39 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // all (scale, image) sums are loaded in parallel (L2, bypassing L1), then added per scale in image order
+  __shared__ float fin[3][kMaxScales * 64];
+  const int nsb = p.S * p.B;
+  for (int i = threadIdx.x; i < nsb; i += kSmallNT) {
+    if (i < kMaxScales * 64) {
+      fin[0][i] = __ldcg(p.lossb + i);
+      fin[1][i] = __ldcg(p.smoothb + 2 * i);
+      fin[2][i] = __ldcg(p.smoothb + 2 * i + 1);
+    }
+  }
+  __syncthreads();
+  __shared__ double level_loss[kMaxScales];
+  if (threadIdx.x < p.S) {
+    const int si = threadIdx.x;
+    double ml = 0.0, sx = 0.0, sy = 0.0;
+    for (int bi = 0; bi < p.B; ++bi) {
+      const int i = si * p.B + bi;
+      if (i < kMaxScales * 64) { ml += (double)fin[0][i]; sx += (double)fin[1][i]; sy += (double)fin[2][i]; }
+      else { ml += (double)__ldcg(p.lossb + i); sx += (double)__ldcg(p.smoothb + 2 * i); sy += (double)__ldcg(p.smoothb + 2 * i + 1); }
+    }
+    int hh = p.hs[si], ww = p.ws[si];
+    double min_loss = ml / ((double)p.B * p.H * p.W);
+    double smooth = sx / ((double)p.B * hh * (ww - 1)) + sy / ((double)p.B * (hh - 1) * ww);
+    double loss = min_loss + (double)p.smooth_weight * smooth / (double)(1 << p.scale_id[si]);
+    p.losses[si] = (float)min_loss;
+    p.losses[p.S + si] = (float)loss;
+    p.losses[2 * p.S + 1 + si] = (float)smooth;
+    level_loss[si] = loss;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     double total = 0.0;
-    for (int si = 0; si < p.S; ++si) {
-      double ml = 0.0, sx = 0.0, sy = 0.0;
-      for (int bi = 0; bi < p.B; ++bi) {
-        ml += (double)((volatile float*)p.lossb)[si * p.B + bi];
-        sx += (double)((volatile float*)p.smoothb)[(si * p.B + bi) * 2];
-        sy += (double)((volatile float*)p.smoothb)[(si * p.B + bi) * 2 + 1];
-      }
-      int hh = p.hs[si], ww = p.ws[si];
-      double min_loss = ml / ((double)p.B * p.H * p.W);
-      double smooth = sx / ((double)p.B * hh * (ww - 1)) + sy / ((double)p.B * (hh - 1) * ww);
-      double loss = min_loss + (double)p.smooth_weight * smooth / (double)(1 << p.scale_id[si]);
-      p.losses[si] = (float)min_loss;
-      p.losses[p.S + si] = (float)loss;
-      p.losses[2 * p.S + 1 + si] = (float)smooth;
-      total += loss;
-    }
+    for (int si = 0; si < p.S; ++si) total += level_loss[si];
     p.losses[2 * p.S] = (float)(total / p.S);
     *p.counter = 0u;
   }
