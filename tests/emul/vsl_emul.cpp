@@ -14,11 +14,21 @@
 using namespace vsl;
 
 template <class C>
-static void run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
-  std::vector<float> sm_store(C::kFloats + 4);
-  float* sm_base = sm_store.data();
+static bool run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
+  // the "shared memory" sits between two guard zones filled with a sentinel; a phase that writes outside
+  // its CTA's allocation trips the check after the tile (compute-sanitizer is not available on the GPU pool)
+  constexpr int kGuard = 256;
+  std::vector<float> sm_store(C::kFloats + 2 * kGuard + 4);
+  float* sm_base = sm_store.data() + kGuard;
   while (reinterpret_cast<uintptr_t>(sm_base) & 15u) ++sm_base;  // CoefRec is 16-byte aligned
+  const float kSentinel = -12345.678f;
+  for (float& v : sm_store) v = kSentinel;
   struct { float* p; float* data() const { return p; } } sm{sm_base};
+  auto guards_intact = [&]() {
+    for (float* q = sm_store.data(); q < sm_base; ++q) if (*q != kSentinel) return false;
+    for (float* q = sm_base + C::kFloats; q < sm_store.data() + sm_store.size(); ++q) if (*q != kSentinel) return false;
+    return true;
+  };
   std::vector<ThreadState<C>> ts(C::NT);
   for (int b = 0; b < p.B; ++b)
     for (int ty = 0; ty < tiles_y; ++ty)
@@ -51,7 +61,9 @@ static void run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
             for (int k = 0; k < C::F * 12; ++k) out[1 + k] += ts[tid].dP[k];
           }
         }
+        if (!guards_intact()) return false;
       }
+  return true;
 }
 
 extern "C" int vsl_emul_photometric(int B, int H, int W, int S, int F, const int* scale_ids, const float* tgt,
@@ -86,10 +98,12 @@ extern "C" int vsl_emul_photometric(int B, int H, int W, int S, int F, const int
   std::vector<float> partials((size_t)tiles_x * tiles_y * B * S * kpartial, 0.f);
   p.partials = partials.data();
   bool ok = false;
-#define TRY(TW, TH, FF) if (tw == TW && th == TH && F == FF) { run_tiles<TileCfg<TW, TH, FF, 256>>(p, tiles_x, tiles_y); ok = true; }
+  bool guards = true;
+#define TRY(TW, TH, FF) if (tw == TW && th == TH && F == FF) { guards = run_tiles<TileCfg<TW, TH, FF, 256>>(p, tiles_x, tiles_y); ok = true; }
   TRY(32, 16, 1) TRY(32, 16, 2) TRY(32, 16, 3) TRY(16, 8, 2) TRY(16, 8, 3)
 #undef TRY
   if (!ok) return -4;
+  if (!guards) return -7;  // a phase wrote outside the CTA's shared-memory allocation
   int tpi = tiles_x * tiles_y;
   for (int s = 0; s < S; ++s) {
     loss_sums[s] = 0.0;

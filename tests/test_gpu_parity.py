@@ -137,6 +137,41 @@ def test_fused_path_matches_oracle(name):
         assert err <= 5e-5, (k, err)
 
 
+def test_randomised_shapes_and_options():
+    """Seeded sweep over shapes the fixed cases do not hit (odd tile remainders, every frame/scale count,
+    option mixes): auto-mask bit-exact, losses 1e-6, gradients 5e-5 rel-L2 against the oracle on the GPU."""
+    import random
+    rng = random.Random(2024)
+    frame_sets = [[0, 1], [0, -1, 1], [0, -1, 1, "s"], [0, "s"], [0, -1]]
+    scale_sets = [[0], [0, 1], [0, 1, 2], [0, 1, 2, 3], [0, 3], [0, 2]]
+    for trial in range(14):
+        scales = rng.choice(scale_sets)
+        m = 1 << max(scales)
+        H, W = m * rng.randint(max(1, 16 // m), 96 // m), m * rng.randint(max(1, 16 // m), 160 // m)
+        B = rng.randint(1, 3)
+        frames = rng.choice(frame_sets)
+        o = {"scales": scales, "no_ssim": rng.random() < 0.2, "disable_automasking": rng.random() < 0.2,
+             "avg_reprojection": rng.random() < 0.25, "v1_multiscale": rng.random() < 0.2}
+        if o["v1_multiscale"] and (H >> max(scales) < 2 or W >> max(scales) < 2):
+            o["v1_multiscale"] = False
+        opt = O.make_opt(height=H, width=W, batch_size=B, frame_ids=list(frames), **o)
+        inputs, outputs, leaves = synthetic.make_batch(B, H, W, frames, rng.choice([synthetic.K_KITTI, synthetic.K_SCARED]),
+                                                       scales=tuple(range(4)) if H % 8 == 0 and W % 8 == 0 else tuple(scales),
+                                                       seed=100 + trial, family=rng.choice(["iid", "smooth"]), device=DEV)
+        tag = (trial, B, H, W, frames, o)
+        ref_out, ref_losses, ref_g = run_oracle(opt, inputs, outputs, leaves, seed=trial)
+        out, losses, g = run_ours(opt, inputs, outputs, leaves, seed=trial, side="none")
+        for k in ref_losses:
+            assert abs(losses[k].item() - ref_losses[k].item()) <= 1e-6 * abs(ref_losses[k].item()), (tag, k)
+        for s in scales:
+            k = "identity_selection/%d" % s
+            if not o["disable_automasking"]:
+                assert torch.equal(out[k], ref_out[k]), (tag, k)
+        assert set(g) == set(ref_g), tag
+        for k in ref_g:
+            assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, (tag, k)
+
+
 @pytest.mark.parametrize("name", ["mono_smooth_c1_b3", "mono_iid_c1_b2", "stereo_c3_b2"])
 def test_gradients_three_way_against_fp64(name):
     """Our fp32 gradients are as close to the fp64 oracle as the fp32 oracle's own (same discrete
