@@ -185,15 +185,18 @@ int vsl_project_backward(int batch, int height, int width, float eps, const floa
 /* SSIM.forward (layers.py:318-332): x, y [B,C,H,W] -> [B,C,H,W] */
 int vsl_ssim_forward(int batch, int channels, int height, int width, const float* x, const float* y,
                      float* out, void* stream);
-/* its backward; grad_x / grad_y may be null */
+/* its backward; grad_x / grad_y may be null; workspace: vsl_ssim_workspace_bytes (4 floats per element) */
+size_t vsl_ssim_workspace_bytes(int batch, int channels, int height, int width);
 int vsl_ssim_backward(int batch, int channels, int height, int width, const float* x, const float* y,
-                      const float* grad_out, float* grad_x, float* grad_y, void* stream);
+                      const float* grad_out, float* grad_x, float* grad_y,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* Trainer.compute_reprojection_loss (trainer.py:543-555): pred, target [B,3,H,W] -> [B,1,H,W] */
 int vsl_reprojection_loss_forward(int batch, int height, int width, int no_ssim, int arith,
                                   const float* pred, const float* target, float* out, void* stream);
+/* workspace: vsl_ssim_workspace_bytes(batch, 3, height, width); not needed with no_ssim */
 int vsl_reprojection_loss_backward(int batch, int height, int width, int no_ssim, const float* pred,
                                    const float* target, const float* grad_out, float* grad_pred,
-                                   float* grad_target, void* stream);
+                                   float* grad_target, void* workspace, size_t workspace_bytes, void* stream);
 /* get_smooth_loss (layers.py:286-299): disp [B,1,h,w], img [B,3,h,w] -> scalar; ws: vsl_smooth_workspace_bytes */
 size_t vsl_smooth_workspace_bytes(int batch, int height, int width);
 int vsl_smooth_loss_forward(int batch, int height, int width, const float* disp, const float* img,

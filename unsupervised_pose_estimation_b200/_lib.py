@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "vsl_warp_forward", "vsl_probe_bmm",
     "vsl_backproject_forward", "vsl_backproject_backward",
     "vsl_project_forward", "vsl_project_workspace_bytes", "vsl_project_backward",
-    "vsl_ssim_forward", "vsl_ssim_backward",
+    "vsl_ssim_forward", "vsl_ssim_workspace_bytes", "vsl_ssim_backward",
     "vsl_reprojection_loss_forward", "vsl_reprojection_loss_backward",
     "vsl_smooth_workspace_bytes", "vsl_smooth_loss_forward", "vsl_smooth_loss_backward",
 ]
@@ -120,9 +120,11 @@ def load():
     lib.vsl_project_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.vsl_project_backward.argtypes = [c_int, c_int, c_int, c_float, vp, vp, vp, vp, vp, vp, c_size_t, vp]
     lib.vsl_ssim_forward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp]
-    lib.vsl_ssim_backward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    lib.vsl_ssim_workspace_bytes.restype = c_size_t
+    lib.vsl_ssim_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.vsl_ssim_backward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, c_size_t, vp]
     lib.vsl_reprojection_loss_forward.argtypes = [c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp]
-    lib.vsl_reprojection_loss_backward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    lib.vsl_reprojection_loss_backward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, c_size_t, vp]
     lib.vsl_smooth_workspace_bytes.restype = c_size_t
     lib.vsl_smooth_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.vsl_smooth_loss_forward.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]

@@ -165,13 +165,49 @@ __global__ void __launch_bounds__(kNT) k_ssim_fwd(int planes, int H, int W, cons
   out[gid] = ssim_at(x + pl * HW, y + pl * HW, w).val;
 }
 
-// d ssim(window p) / d x_q contributions gathered at q.  `swap` computes the gradient for y instead
-// (SSIM is symmetric in its arguments).  Returns sum_p cnt * go[p] * dssim_p/dx_q.
-__device__ __forceinline__ float ssim_grad_gather(const float* __restrict__ x, const float* __restrict__ y,
-                                                  const float* __restrict__ go, float go_scale, int qy, int qx, int H,
-                                                  int W) {
-  float xq = x[qy * W + qx], yq = y[qy * W + qx];
-  float acc = 0.f;
+// Backward of SSIM in two passes.  Pass 1, per window p: the four adjoint coefficients
+//   Ax = k dr/dmu_x, Ay = k dr/dmu_y, Bq = k dr/dE[x^2] (= dr/dE[y^2]), Cq = k dr/dE[xy],  k = -g_p/18 * live
+// (SSIM is symmetric in its arguments, so x and y share Bq and Cq).  Pass 2, per pixel q: gather the <= 9
+// windows that contain q, reflected border rows/columns counting twice:
+//   dL/dx_q = sum_p cnt (Ax_p + 2 x_q Bq_p + y_q Cq_p),   dL/dy_q = sum_p cnt (Ay_p + 2 y_q Bq_p + x_q Cq_p).
+// coef: [4][planes*HW] workspace.  `gstride`: 1 = one upstream value per plane element (SSIM layer),
+// 0-like broadcast over the 3 channels is expressed by passing gdiv = 3 (reprojection loss, go is [B,1,H,W]).
+__global__ void __launch_bounds__(kNT) k_ssim_coef(int planes, int H, int W, int gdiv, float gscale,
+                                                   const float* __restrict__ x, const float* __restrict__ y,
+                                                   const float* __restrict__ go, float* __restrict__ coef) {
+  int HW = H * W;
+  size_t n = (size_t)planes * HW;
+  size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
+  if (gid >= n) return;
+  size_t pl = gid / HW;
+  int i = (int)(gid - pl * HW);
+  float g = go[(pl / gdiv) * HW + i] * gscale;
+  float ax = 0.f, ay = 0.f, bq = 0.f, cq = 0.f;
+  if (g != 0.f) {
+    const float* xp = x + pl * HW;
+    const float* yp = y + pl * HW;
+    Win w = window_offsets(i / W, i % W, H, W);
+    float sy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sy = add_rn(sy, yp[w.o[k]]);
+    float mu_y = div9(sy);
+    SsimOut so = ssim_at(xp, yp, w);
+    if (so.live) {
+      float dmu, dexx, dexy;
+      ssim_r_grads(so, mu_y, dmu, dexx, dexy);
+      // d r / d mu_y: the same expression with the roles of x and y exchanged
+      float inv_d = fast_rcp(so.d1 * so.d2);
+      float dmuy = inv_d * (2.0f * so.mu_x * (so.n2 - so.n1) - so.r * 2.0f * mu_y * (so.d2 - so.d1));
+      float k = g * (-0.5f / 9.0f);
+      ax = k * dmu; ay = k * dmuy; bq = k * dexx; cq = k * dexy;
+    }
+  }
+  coef[gid] = ax; coef[n + gid] = ay; coef[2 * n + gid] = bq; coef[3 * n + gid] = cq;
+}
+
+__device__ __forceinline__ void ssim_gather(const float* __restrict__ coef, size_t n, size_t plane_off, int qy, int qx,
+                                            int H, int W, float& sa_x, float& sa_y, float& sb, float& sc) {
+  sa_x = sa_y = sb = sc = 0.f;
   for (int dy = -1; dy <= 1; ++dy) {
     int py = qy + dy;
     if (py < 0 || py >= H) continue;
@@ -179,38 +215,27 @@ __device__ __forceinline__ float ssim_grad_gather(const float* __restrict__ x, c
     for (int dx = -1; dx <= 1; ++dx) {
       int px = qx + dx;
       if (px < 0 || px >= W) continue;
-      float cx = ((dx == -1 && qx == 1) || (dx == 1 && qx == W - 2)) ? 2.f : 1.f;
-      float g = go[py * W + px];
-      if (g == 0.f) continue;
-      Win w = window_offsets(py, px, H, W);
-      // window sums of y for mu_y (ssim_at recomputes them; needed for the gradient too)
-      float sy = 0.f;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) sy = add_rn(sy, y[w.o[k]]);
-      float mu_y = div9(sy);
-      SsimOut so = ssim_at(x, y, w);
-      if (!so.live) continue;
-      float dmu, dexx, dexy;
-      ssim_r_grads(so, mu_y, dmu, dexx, dexy);
-      acc += cy * cx * g * go_scale * (-0.5f / 9.0f) * (dmu + 2.f * xq * dexx + yq * dexy);
+      float cnt = cy * (((dx == -1 && qx == 1) || (dx == 1 && qx == W - 2)) ? 2.f : 1.f);
+      size_t o = plane_off + (size_t)py * W + px;
+      sa_x += cnt * coef[o]; sa_y += cnt * coef[n + o]; sb += cnt * coef[2 * n + o]; sc += cnt * coef[3 * n + o];
     }
   }
-  return acc;
 }
 
 __global__ void __launch_bounds__(kNT) k_ssim_bwd(int planes, int H, int W, const float* __restrict__ x,
-                                                  const float* __restrict__ y, const float* __restrict__ go,
+                                                  const float* __restrict__ y, const float* __restrict__ coef,
                                                   float* __restrict__ gx, float* __restrict__ gy) {
   int HW = H * W;
+  size_t n = (size_t)planes * HW;
   size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
-  if (gid >= (size_t)planes * HW) return;
+  if (gid >= n) return;
   size_t pl = gid / HW;
   int i = (int)(gid - pl * HW);
-  const float* xp = x + pl * HW;
-  const float* yp = y + pl * HW;
-  const float* gp = go + pl * HW;
-  if (gx) gx[gid] = ssim_grad_gather(xp, yp, gp, 1.f, i / W, i % W, H, W);
-  if (gy) gy[gid] = ssim_grad_gather(yp, xp, gp, 1.f, i / W, i % W, H, W);
+  float sax, say, sb, sc;
+  ssim_gather(coef, n, pl * HW, i / W, i % W, H, W, sax, say, sb, sc);
+  float xq = x[gid], yq = y[gid];
+  if (gx) gx[gid] = sax + 2.f * xq * sb + yq * sc;
+  if (gy) gy[gid] = say + 2.f * yq * sb + xq * sc;
 }
 
 __global__ void __launch_bounds__(kNT) k_reproj_fwd(int B, int H, int W, int no_ssim, int arith,
@@ -235,24 +260,22 @@ __global__ void __launch_bounds__(kNT) k_reproj_fwd(int B, int H, int W, int no_
 
 __global__ void __launch_bounds__(kNT) k_reproj_bwd(int B, int H, int W, int no_ssim, const float* __restrict__ pred,
                                                     const float* __restrict__ tgt, const float* __restrict__ go,
-                                                    float* __restrict__ gpred, float* __restrict__ gtgt) {
+                                                    const float* __restrict__ coef, float* __restrict__ gpred,
+                                                    float* __restrict__ gtgt) {
   int HW = H * W;
+  size_t n = (size_t)B * 3 * HW;
   size_t gid = (size_t)blockIdx.x * kNT + threadIdx.x;
-  if (gid >= (size_t)B * HW) return;
-  int b = (int)(gid / HW), i = (int)(gid - (size_t)b * HW);
-  const float* gp = go + (size_t)b * HW;
-  float wl1 = no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f);
-  for (int c = 0; c < 3; ++c) {
-    const float* x = pred + ((size_t)b * 3 + c) * HW;
-    const float* y = tgt + ((size_t)b * 3 + c) * HW;
-    float d = x[i] - y[i];
-    float s = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-    float l1g = gp[i] * wl1 * s;
-    if (gpred) gpred[((size_t)b * 3 + c) * HW + i] =
-        l1g + (no_ssim ? 0.f : ssim_grad_gather(x, y, gp, 0.85f / 3.0f, i / W, i % W, H, W));
-    if (gtgt) gtgt[((size_t)b * 3 + c) * HW + i] =
-        -l1g + (no_ssim ? 0.f : ssim_grad_gather(y, x, gp, 0.85f / 3.0f, i / W, i % W, H, W));
-  }
+  if (gid >= n) return;
+  size_t pl = gid / HW;  // b * 3 + c
+  int i = (int)(gid - pl * HW);
+  float xq = pred[gid], yq = tgt[gid];
+  float d = xq - yq;
+  float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  float l1g = go[(pl / 3) * HW + i] * (no_ssim ? (1.0f / 3.0f) : (0.15f / 3.0f)) * sgn;
+  float sax = 0.f, say = 0.f, sb = 0.f, sc = 0.f;
+  if (!no_ssim) ssim_gather(coef, n, pl * HW, i / W, i % W, H, W, sax, say, sb, sc);
+  if (gpred) gpred[gid] = l1g + sax + 2.f * xq * sb + yq * sc;
+  if (gtgt) gtgt[gid] = -l1g + say + 2.f * yq * sb + xq * sc;
 }
 
 // ---- get_smooth_loss (layers.py:286-299) --------------------------------------------------------------
@@ -383,11 +406,19 @@ int vsl_ssim_forward(int B, int C, int H, int W, const float* x, const float* y,
   VSL_L_OK(cudaGetLastError());
   return VSL_OK;
 }
+size_t vsl_ssim_workspace_bytes(int B, int C, int H, int W) {
+  if (B < 1 || C < 1 || H < 2 || W < 2) return 0;
+  return (size_t)4 * B * C * H * W * sizeof(float);
+}
 int vsl_ssim_backward(int B, int C, int H, int W, const float* x, const float* y, const float* go, float* gx, float* gy,
-                      void* stream) {
+                      void* ws, size_t ws_bytes, void* stream) {
   if (B < 1 || C < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
-  if (!x || !y || !go) return VSL_ERR_NULL_POINTER;
-  k_ssim_bwd<<<blocks_for((size_t)B * C * H * W), kNT, 0, (cudaStream_t)stream>>>(B * C, H, W, x, y, go, gx, gy);
+  if (!x || !y || !go || !ws) return VSL_ERR_NULL_POINTER;
+  if (ws_bytes < vsl_ssim_workspace_bytes(B, C, H, W)) return VSL_ERR_WORKSPACE;
+  unsigned nb = blocks_for((size_t)B * C * H * W);
+  k_ssim_coef<<<nb, kNT, 0, (cudaStream_t)stream>>>(B * C, H, W, 1, 1.0f, x, y, go, (float*)ws);
+  VSL_L_OK(cudaGetLastError());
+  k_ssim_bwd<<<nb, kNT, 0, (cudaStream_t)stream>>>(B * C, H, W, x, y, (const float*)ws, gx, gy);
   VSL_L_OK(cudaGetLastError());
   return VSL_OK;
 }
@@ -400,10 +431,17 @@ int vsl_reprojection_loss_forward(int B, int H, int W, int no_ssim, int arith, c
   return VSL_OK;
 }
 int vsl_reprojection_loss_backward(int B, int H, int W, int no_ssim, const float* pred, const float* target,
-                                   const float* go, float* gpred, float* gtarget, void* stream) {
+                                   const float* go, float* gpred, float* gtarget, void* ws, size_t ws_bytes,
+                                   void* stream) {
   if (B < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
-  if (!pred || !target || !go) return VSL_ERR_NULL_POINTER;
-  k_reproj_bwd<<<blocks_for((size_t)B * H * W), kNT, 0, (cudaStream_t)stream>>>(B, H, W, no_ssim, pred, target, go, gpred, gtarget);
+  if (!pred || !target || !go || (!no_ssim && !ws)) return VSL_ERR_NULL_POINTER;
+  if (!no_ssim && ws_bytes < vsl_ssim_workspace_bytes(B, 3, H, W)) return VSL_ERR_WORKSPACE;
+  unsigned nb = blocks_for((size_t)B * 3 * H * W);
+  if (!no_ssim) {  // 0.85 * mean_c ssim: the upstream value of pixel p reaches each channel's window scaled by 0.85/3
+    k_ssim_coef<<<nb, kNT, 0, (cudaStream_t)stream>>>(B * 3, H, W, 3, 0.85f / 3.0f, pred, target, go, (float*)ws);
+    VSL_L_OK(cudaGetLastError());
+  }
+  k_reproj_bwd<<<nb, kNT, 0, (cudaStream_t)stream>>>(B, H, W, no_ssim, pred, target, go, (const float*)ws, gpred, gtarget);
   VSL_L_OK(cudaGetLastError());
   return VSL_OK;
 }

@@ -398,8 +398,11 @@ class _Ssim(torch.autograd.Function):
         g = _dev(g, "grad")
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
-        check(_lib.load().vsl_ssim_backward(B, C, H, W, x.data_ptr(), y.data_ptr(), g.data_ptr(), ptr(gx), ptr(gy),
-                                            _stream()), "vsl_ssim_backward")
+        lib = _lib.load()
+        nbytes = lib.vsl_ssim_workspace_bytes(B, C, H, W)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=g.device)
+        check(lib.vsl_ssim_backward(B, C, H, W, x.data_ptr(), y.data_ptr(), g.data_ptr(), ptr(gx), ptr(gy),
+                                    ws.data_ptr(), nbytes, _stream()), "vsl_ssim_backward")
         return gx, gy
 
 
@@ -429,8 +432,11 @@ class _ReprojLoss(torch.autograd.Function):
         g = _dev(g, "grad")
         gp = torch.empty_like(pred) if ctx.needs_input_grad[0] else None
         gt = torch.empty_like(target) if ctx.needs_input_grad[1] else None
-        check(_lib.load().vsl_reprojection_loss_backward(B, H, W, ctx.no_ssim, pred.data_ptr(), target.data_ptr(),
-                                                         g.data_ptr(), ptr(gp), ptr(gt), _stream()),
+        lib = _lib.load()
+        nbytes = 0 if ctx.no_ssim else lib.vsl_ssim_workspace_bytes(B, 3, H, W)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=g.device) if nbytes else None
+        check(lib.vsl_reprojection_loss_backward(B, H, W, ctx.no_ssim, pred.data_ptr(), target.data_ptr(),
+                                                 g.data_ptr(), ptr(gp), ptr(gt), ptr(ws), nbytes, _stream()),
               "vsl_reprojection_loss_backward")
         return gp, gt, None, None
 
