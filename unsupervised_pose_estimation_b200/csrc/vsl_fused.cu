@@ -471,7 +471,8 @@ struct Plan {  // sizes derived from the descriptor; identical in workspace_byte
 
 static Plan make_plan(const VslDesc* d) {
   Plan pl;
-  pl.tw = 32; pl.th = 16;
+  pl.tw = 32;
+  pl.th = d->num_src >= 3 ? 8 : 16;  // three source frames: a 32x8 tile keeps two CTAs per SM (127 KB -> 71 KB)
   pl.tiles_x = (d->width + pl.tw - 1) / pl.tw;
   pl.tiles_y = (d->height + pl.th - 1) / pl.th;
   pl.num_cta = pl.tiles_x * pl.tiles_y * d->batch;
@@ -648,15 +649,15 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   int rc;
   if (avg) {
     if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, float, true>>(pp, pl, d->batch, st);
-    else rc = launch_photometric<TileCfg<32, 16, 3, 256, float, true>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, 8, 3, 256, float, true>>(pp, pl, d->batch, st);
   } else if (d->image_dtype == VSL_DTYPE_BF16) {
     if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256, bf16_t>>(pp, pl, d->batch, st);
     else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, bf16_t>>(pp, pl, d->batch, st);
-    else rc = launch_photometric<TileCfg<32, 16, 3, 256, bf16_t>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, 8, 3, 256, bf16_t>>(pp, pl, d->batch, st);
   } else {
     if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256>>(pp, pl, d->batch, st);
     else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256>>(pp, pl, d->batch, st);
-    else rc = launch_photometric<TileCfg<32, 16, 3, 256>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, 8, 3, 256>>(pp, pl, d->batch, st);
   }
   if (rc != VSL_OK) return rc;
   if (event_after) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after, st));
