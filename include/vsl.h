@@ -114,6 +114,9 @@ typedef struct VslLossBuffers {
   const float* K;                       /* inputs[("K",0)]        [B,4,4]  (needed with T)            */
   const float* T[VSL_MAX_SRC];          /* outputs[("cam_T_cam",0,f)] / inputs["stereo_T"] [B,4,4]: the
                                            kernel then forms P_f = (K @ T_f)[:3,:] itself             */
+  const float* T_scale[VSL_MAX_SCALES][VSL_MAX_SRC]; /* optional per-(scale, frame) override of T: posecnn
+                                           rescales the translation by each level's mean inverse depth
+                                           (trainer.py:516-525); null entries fall back to T[f]        */
   const float* noise[VSL_MAX_SCALES];   /* torch.randn draw of trainer.py:656 per scale [B,F,H,W]
                                            ([B,1,H,W] with VSL_FLAG_AVG_REPROJECTION); unused without automask */
   /* outputs */
@@ -144,7 +147,8 @@ int vsl_event_elapsed_ms(void* start, void* stop, float* ms);
 /* Chain rule from the loss dict to the leaves: `upstream` holds dL/d(losses[k]) on the DEVICE in
  * the order min_loss/0..S-1, loss/0..S-1, loss (2S+1 floats; trainer.py:672-685 defines how the
  * entries depend on each other).  Writes grad_disp[s] [B,1,H>>s,W>>s] and, each optional (null to skip),
- * grad_P_out [F][B][12] = dL/dP_f and grad_T_out [F][B][16] = K[:3,:]^T dL/dP_f (needs buf->K). */
+ * grad_P_out [F][B][12] = dL/dP_f and grad_T_out [F][B][16] = K[:3,:]^T dL/dP_f (needs buf->K).  When
+ * buf->T_scale is used the poses differ per scale: grad_T_out is then [S][F][B][16] and grad_P_out must be null. */
 int vsl_loss_combine_grads(const VslDesc* desc, const float* upstream,
                            const VslLossBuffers* buf, float* const grad_disp[VSL_MAX_SCALES],
                            float* grad_P_out, float* grad_T_out, void* stream);

@@ -37,7 +37,6 @@ static bool run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
         t.b = b; t.x0 = tx * C::TW; t.y0 = ty * C::TH;
         t.cta = (b * tiles_y + ty) * tiles_x + tx;
         size_t img_off = (size_t)b * 3 * p.H * p.W;
-        for (int tid = 0; tid < C::NT; ++tid) phase_pose<C>(p, p.g, t, sm.data(), tid);
         for (int tid = 0; tid < C::NT; ++tid) phase_load_region<C>(p, t, (const float*)p.tgt + img_off, sm.data() + C::oT, tid);
         for (int tid = 0; tid < C::NT; ++tid) phase_target_stats<C>(p, t, sm.data(), tid);
         for (int tid = 0; tid < C::NT; ++tid) phase_load_sources<C>(p, t, sm.data(), tid);
@@ -47,6 +46,7 @@ static bool run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
             ts[tid].loss = 0.f;
             for (int k = 0; k < C::F * 12; ++k) ts[tid].dP[k] = 0.f;
           }
+          for (int tid = 0; tid < C::NT; ++tid) phase_pose<C>(p, p.g, t, sm.data(), s, tid);
           for (int tid = 0; tid < C::NT; ++tid) phase_warp<C>(p, p.g, t, sm.data(), s, tid);
           for (int tid = 0; tid < C::NT; ++tid) phase_windows<C>(p, p.g, t, sm.data(), s, tid, ts[tid]);
           for (int tid = 0; tid < C::NT; ++tid) phase_backward<C>(p, p.g, t, sm.data(), s, tid, ts[tid]);

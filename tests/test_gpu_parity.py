@@ -91,6 +91,10 @@ CASES = {
     "avg_no_automask": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "smooth", 19,
                         {"avg_reprojection": True, "disable_automasking": True}),
     "avg_one_frame": (2, 64, 96, [0, 1], synthetic.K_KITTI, "iid", 20, {"avg_reprojection": True}),
+    "posecnn": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "smooth", 22, {"pose_model_type": "posecnn"}),
+    "posecnn_c1_b2": (2, 192, 640, [0, -1, 1], synthetic.K_KITTI, "iid", 23, {"pose_model_type": "posecnn"}),
+    "posecnn_v1_multiscale": (2, 64, 96, [0, 1], synthetic.K_KITTI, "smooth", 24,
+                              {"pose_model_type": "posecnn", "v1_multiscale": True}),
     "v1_multiscale": (2, 64, 96, [0, -1, 1], synthetic.K_KITTI, "iid", 15, {"v1_multiscale": True}),
     "v1_multiscale_c1_b2": (2, 192, 640, [0, -1, 1, "s"], synthetic.K_KITTI, "smooth", 16, {"v1_multiscale": True}),
 }

@@ -186,7 +186,6 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
   const int tid = threadIdx.x;
   const size_t img_off = (size_t)t.b * 3 * p.H * p.W;
 
-  phase_pose<C>(p, g, t, sm, tid);
   phase_load_region<C>(p, t, (const typename C::Img*)p.tgt + img_off, sm + C::oT, tid);
   __syncthreads();
   phase_target_stats<C>(p, t, sm, tid);
@@ -202,6 +201,7 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
     ts.loss = 0.f;
 #pragma unroll
     for (int k = 0; k < C::F * 12; ++k) ts.dP[k] = 0.f;
+    phase_pose<C>(p, g, t, sm, s, tid);  // P of the previous scale is no longer read (sync after its adjoint)
     __syncthreads();
     phase_warp<C>(p, g, t, sm, s, tid);
     __syncthreads();
@@ -351,7 +351,8 @@ struct CombineParams {
   float* out[kMaxScales];
   const float* gradP;  // [S][F][B][12]
   float* gradP_out;    // [F][B][12] or null
-  float* gradT_out;    // [F][B][16] or null: K[:3,:]^T @ dP
+  float* gradT_out;    // [F][B][16] ([S][F][B][16] with pose_per_scale) or null: K[:3,:]^T @ dP
+  int pose_per_scale;
   const float* K;      // [B,4,4]
   const float* norm;   // [S][B][2]
   int B, S, F, chunks0;
@@ -373,24 +374,26 @@ __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
     for (int i = chunk * kChunk + threadIdx.x; i < min(p.n[s], (chunk + 1) * kChunk); i += kSmallNT)
       o[i] = a * gp[i] + bb * (gs[i] * inv - corr);
   }
-  if (chunk == 0 && s == 0 && (p.gradP_out || p.gradT_out)) {
+  if (chunk == 0 && (s == 0 || p.pose_per_scale) && (p.gradP_out || p.gradT_out)) {
+    // shared pose: sum the scales' dL/dP with their upstream weights; posecnn: one pose per scale, no sum
     __shared__ float gP[kMaxSrc * 12];
     for (int k = threadIdx.x; k < p.F * 12; k += kSmallNT) {
       int f = k / 12, e = k % 12;
       float acc = 0.f;
-      for (int si = 0; si < p.S; ++si) {
+      for (int si = (p.pose_per_scale ? s : 0); si < (p.pose_per_scale ? s + 1 : p.S); ++si) {
         float a = p.up[si] + p.up[p.S + si] + tot;
         acc += a * p.gradP[((size_t)(si * p.F + f) * p.B + b) * 12 + e];
       }
       gP[k] = acc;
-      if (p.gradP_out) p.gradP_out[((size_t)f * p.B + b) * 12 + e] = acc;
+      if (p.gradP_out && !p.pose_per_scale) p.gradP_out[((size_t)f * p.B + b) * 12 + e] = acc;
     }
     __syncthreads();
     if (p.gradT_out) {  // P = K[:3,:] @ T  ->  dL/dT = K[:3,:]^T @ dL/dP
+      const size_t base = p.pose_per_scale ? (size_t)s * p.F * p.B * 16 : 0;
       for (int k = threadIdx.x; k < p.F * 16; k += kSmallNT) {
         int f = k / 16, e = k % 16, r = e >> 2, n = e & 3;
         const float* Kb = p.K + b * 16;
-        p.gradT_out[((size_t)f * p.B + b) * 16 + e] =
+        p.gradT_out[base + ((size_t)f * p.B + b) * 16 + e] =
             Kb[r] * gP[f * 12 + n] + Kb[4 + r] * gP[f * 12 + 4 + n] + Kb[8 + r] * gP[f * 12 + 8 + n];
       }
     }
@@ -585,8 +588,12 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
         !buf->grad_disp_smooth[s])
       return VSL_ERR_NULL_POINTER;
   for (int f = 0; f < F; ++f) {
-    if (!buf->source[f] || (!buf->P[f] && !buf->T[f])) return VSL_ERR_NULL_POINTER;
-    if (buf->T[f] && !buf->K) return VSL_ERR_NULL_POINTER;
+    if (!buf->source[f]) return VSL_ERR_NULL_POINTER;
+    for (int s = 0; s < S; ++s) {
+      const float* T = buf->T_scale[s][f] ? buf->T_scale[s][f] : buf->T[f];
+      if (!buf->P[f] && !T) return VSL_ERR_NULL_POINTER;
+      if (T && !buf->K) return VSL_ERR_NULL_POINTER;
+    }
   }
   if (d->scale_ids[0] != 0) return VSL_ERR_UNSUPPORTED;  // level 0 is the photometric target
 
@@ -604,7 +611,10 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   pp.wpix = 1.0f / ((float)d->batch * d->height * d->width);
   pp.partials = ws + pl.off_partials;
   pp.K = buf->K;
-  for (int f = 0; f < F; ++f) { pp.src[f] = buf->source[f]; pp.P[f] = buf->P[f]; pp.T[f] = buf->T[f]; }
+  for (int f = 0; f < F; ++f) {
+    pp.src[f] = buf->source[f]; pp.P[f] = buf->P[f];
+    for (int s = 0; s < S; ++s) pp.T[s][f] = buf->T_scale[s][f] ? buf->T_scale[s][f] : buf->T[f];
+  }
   for (int s = 0; s < S; ++s) {
     int e = d->scale_ids[s];
     int hs = d->height >> e, wsz = d->width >> e;
@@ -675,6 +685,10 @@ int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLos
   cp.chunks0 = (d->height * d->width + kChunk - 1) / kChunk;
   cp.smooth_weight = d->smooth_weight;
   cp.gradP = buf->grad_P; cp.gradP_out = grad_P_out; cp.gradT_out = grad_T_out; cp.K = buf->K;
+  cp.pose_per_scale = 0;
+  for (int s = 0; s < d->num_scales; ++s)
+    for (int f = 0; f < d->num_src; ++f) cp.pose_per_scale |= buf->T_scale[s][f] != nullptr;
+  if (cp.pose_per_scale && grad_P_out) return VSL_ERR_UNSUPPORTED;  // per-scale poses report dL/dT only
   if (grad_T_out && !buf->K) return VSL_ERR_NULL_POINTER;
   cp.norm = buf->smooth_norm;
   if (!cp.norm) return VSL_ERR_NULL_POINTER;

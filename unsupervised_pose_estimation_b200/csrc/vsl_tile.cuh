@@ -24,7 +24,9 @@ struct PhotoParams {
   const float* invK;              // [B,4,4]
   const float* P[kMaxSrc];        // [B,3,4] = (K@T_f)[:, :3, :], or null when T[f] is given
   const float* K;                 // [B,4,4]  inputs[("K", 0)]
-  const float* T[kMaxSrc];        // [B,4,4]  cam_T_cam / stereo_T: P is then formed in the kernel (layers.py:254)
+  const float* T[kMaxScales][kMaxSrc];  // [B,4,4] cam_T_cam / stereo_T per (scale, frame): P is then formed in the
+                                  // kernel (layers.py:254).  The same pointer for every scale except with posecnn,
+                                  // whose translation is rescaled by each level's mean inverse depth (trainer.py:516-525)
   const float* noise[kMaxScales]; // [B,F,H,W]
   float* mask[kMaxScales];        // [B,H,W] or null
   float* gD[kMaxScales];          // identity levels: [B,H,W] d(min_loss/s)/d disp_s, written directly
@@ -90,13 +92,13 @@ struct TileCtx {
 
 // ---- phase: projection matrices of this image, P_f = (K @ T_f)[:3,:]  (layers.py:254) -------------
 template <class C>
-VSL_HD void phase_pose(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int tid) {
+VSL_HD void phase_pose(const PhotoParams& p, const GeoConst& g, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
   for (int k = tid; k < C::F * 12; k += C::NT) {
     const int f = k / 12, e = k - f * 12, i = e >> 2, n = e & 3;
     float v;
-    if (p.T[f]) {
+    if (p.T[s][f]) {
       const float* Kb = p.K + t.b * 16 + i * 4;
-      const float* Tb = p.T[f] + t.b * 16 + n;
+      const float* Tb = p.T[s][f] + t.b * 16 + n;
       v = dot4kt(Kb[0], Tb[0], Kb[1], Tb[4], Kb[2], Tb[8], Kb[3], Tb[12], g.arith);
     } else {
       v = p.P[f][t.b * 12 + e];

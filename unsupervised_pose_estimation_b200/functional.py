@@ -176,6 +176,7 @@ class _FusedLoss(torch.autograd.Function):
     def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, *leaves):
         S, F = len(plan.scales), plan.num_src
         disps, Ps = leaves[:S], leaves[S:]   # Ps: projection matrices [B,3,4], or poses T [B,4,4] if use_T
+        per_scale = use_T == "per_scale"     # poses given per (scale, frame): S*F tensors, scale-major
         dev = disps[0].device
         B, H, W = plan.batch, plan.height, plan.width
         buf = VslLossBuffers()
@@ -197,15 +198,21 @@ class _FusedLoss(torch.autograd.Function):
                 keep.append(z)
         for f in range(F):
             src = _dev(sources[f], "source[%d]" % f, plan.image_dtype)
-            P = _dev(Ps[f], "T[%d]" % f if use_T else "P[%d]" % f)
-            if tuple(src.shape) != (B, 3, H, W) or tuple(P.shape) != ((B, 4, 4) if use_T else (B, 3, 4)):
-                raise ValueError("source / pose[%d] have shapes %s / %s" % (f, tuple(src.shape), tuple(P.shape)))
+            if tuple(src.shape) != (B, 3, H, W):
+                raise ValueError("source[%d] has shape %s" % (f, tuple(src.shape)))
             buf.source[f] = src.data_ptr()
-            if use_T:
-                buf.T[f] = P.data_ptr()
-            else:
-                buf.P[f] = P.data_ptr()
-            keep += [src, P]
+            keep.append(src)
+            for s in range(S if per_scale else 1):
+                P = _dev(Ps[s * F + f], "T[%d]" % f if use_T else "P[%d]" % f)
+                if tuple(P.shape) != ((B, 4, 4) if use_T else (B, 3, 4)):
+                    raise ValueError("pose[%d] has shape %s" % (f, tuple(P.shape)))
+                if per_scale:
+                    buf.T_scale[s][f] = P.data_ptr()
+                elif use_T:
+                    buf.T[f] = P.data_ptr()
+                else:
+                    buf.P[f] = P.data_ptr()
+                keep.append(P)
         if use_T:
             Kc = _dev(K, "K")
             if tuple(Kc.shape) != (B, 4, 4):
@@ -253,8 +260,9 @@ class _FusedLoss(torch.autograd.Function):
         up = _dev(gvec, "upstream gradient")
         n_levels = [int(np.prod(sh)) for sh in plan.level_shapes]
         pe = 16 if ctx.use_T else 12   # gradient w.r.t. T [B,4,4] or P [B,3,4]
-        flat = torch.empty(sum(n_levels) + F * B * pe, dtype=torch.float32, device=dev)
-        parts = torch.split(flat, n_levels + [F * B * pe])
+        n_pose = (S if ctx.use_T == "per_scale" else 1) * F
+        flat = torch.empty(sum(n_levels) + n_pose * B * pe, dtype=torch.float32, device=dev)
+        parts = torch.split(flat, n_levels + [n_pose * B * pe])
         out_ptrs = (ctypes.c_void_p * VSL_MAX_SCALES)()
         for s in range(S):
             out_ptrs[s] = parts[s].data_ptr()
@@ -264,7 +272,7 @@ class _FusedLoss(torch.autograd.Function):
                                               gP.data_ptr() if ctx.use_T else None, _stream()),
               "vsl_loss_combine_grads")
         gd = [parts[s].view(plan.level_shapes[s]) for s in range(S)]
-        gPs = [gP.view(F, B, 4, 4)[f] if ctx.use_T else gP.view(F, B, 3, 4)[f] for f in range(F)]
+        gPs = [gP.view(n_pose, B, 4, 4)[i] if ctx.use_T else gP.view(F, B, 3, 4)[i] for i in range(n_pose)]
         return (None, None, None, None, None, None, None, None) + tuple(gd) + tuple(gPs)
 
 
@@ -278,8 +286,13 @@ def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, 
     Gradients flow to ``disps`` and to ``Ps`` / ``Ts``.
     """
     use_T = Ts is not None
+    poses = list(Ts if use_T else Ps)
+    if use_T and poses and isinstance(poses[0], (list, tuple)):
+        # one pose per (scale, frame) — posecnn (trainer.py:516-525): Ts[s][f]
+        use_T = "per_scale"
+        poses = [T for per_frame in poses for T in per_frame]
     res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise or []), bool(want_mask), K, use_T,
-                           *(list(disps) + list(Ts if use_T else Ps)))
+                           *(list(disps) + poses))
     return res[0], list(res[1:])
 
 

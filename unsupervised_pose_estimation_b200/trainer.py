@@ -32,8 +32,8 @@ def _unsupported(opt):
     bad = []
     if getattr(opt, "predictive_mask", False):
         bad.append("--predictive_mask")
-    if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn":
-        bad.append("--pose_model_type posecnn")
+    if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn" and "s" in opt.frame_ids:
+        bad.append("--pose_model_type posecnn with a stereo frame (the reference itself fails there)")
     if getattr(opt, "pre_trained_generator", False):
         bad.append("--pre_trained_generator")
     return bad
@@ -92,18 +92,30 @@ class ViewSynthesisLossMixin:
             return [(pl, 0, s) for pl, s in zip(plan, self.opt.scales)]
         return [(plan, si, 0) for si, _ in enumerate(self.opt.scales)]
 
-    def _vsl_poses(self, inputs, outputs):
-        """T_f per source frame: stereo_T or cam_T_cam (reference trainer.py:510-513)."""
-        return [inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)] for f in self.opt.frame_ids[1:]]
+    def _vsl_poses(self, inputs, outputs, scales=None):
+        """T_f per source frame: stereo_T or cam_T_cam (reference trainer.py:510-513).  With posecnn the
+        pose depends on the scale (trainer.py:516-525: translation times the level's mean inverse depth) and
+        a list per scale is returned; that branch is plain torch on [B,1,H,W] tensors, as in the reference."""
+        opt = self.opt
+        if getattr(opt, "pose_model_type", "separate_resnet") != "posecnn":
+            return [inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)] for f in opt.frame_ids[1:]]
+        from .layers import disp_to_depth, transformation_from_parameters
+        per_scale = []
+        for scale in (opt.scales if scales is None else scales):
+            disp = outputs[("disp", scale)]
+            if not getattr(opt, "v1_multiscale", False):
+                disp = torch.nn.functional.interpolate(disp, [opt.height, opt.width], mode="bilinear", align_corners=False)
+            _, depth = disp_to_depth(disp, opt.min_depth, opt.max_depth)
+            mean_inv_depth = (1 / depth).mean(3, True).mean(2, True)
+            per_scale.append([transformation_from_parameters(
+                outputs[("axisangle", 0, f)][:, 0], outputs[("translation", 0, f)][:, 0] * mean_inv_depth[:, 0], f < 0)
+                for f in opt.frame_ids[1:]])
+        return per_scale
 
     def _vsl_projections(self, inputs, outputs, source_scale=0):
         """P_f = (K @ T_f)[:, :3, :] per source frame (reference layers.py:254; T as trainer.py:510-513)."""
         K = inputs[("K", source_scale)]
-        Ps = []
-        for frame_id in self.opt.frame_ids[1:]:
-            T = inputs["stereo_T"] if frame_id == "s" else outputs[("cam_T_cam", 0, frame_id)]
-            Ps.append(torch.matmul(K, T)[:, :3, :])
-        return Ps
+        return [torch.matmul(K, T)[:, :3, :] for T in self._vsl_poses(inputs, outputs)]
 
     # -- reference surface ----------------------------------------------------------------------
     def generate_images_pred(self, inputs, outputs):
@@ -117,8 +129,13 @@ class ViewSynthesisLossMixin:
     def materialize_side_outputs(self, inputs, outputs):
         """Write ("depth",0,s), ("sample",f,s), ("color",f,s), ("color_identity",f,s) into ``outputs``."""
         with torch.no_grad():
+            posecnn = getattr(self.opt, "pose_model_type", "") == "posecnn"
             for (plan, si, src_scale), scale in zip(self._vsl_level_plans(inputs[("color", 0, 0)].dtype), self.opt.scales):
-                Ps = self._vsl_projections(inputs, outputs, src_scale)
+                if posecnn:
+                    Ps = [torch.matmul(inputs[("K", src_scale)], T)[:, :3, :]
+                          for T in self._vsl_poses(inputs, outputs, [scale])[0]]
+                else:
+                    Ps = self._vsl_projections(inputs, outputs, src_scale)
                 sources = [inputs[("color", f, src_scale)] for f in self.opt.frame_ids[1:]]
                 depth, samples, colors = VF.warp_side_outputs(
                     plan, si, outputs[("disp", scale)], inputs[("inv_K", src_scale)], Ps, sources)
@@ -174,7 +191,7 @@ class ViewSynthesisLossMixin:
             vec, masks = VF.fused_loss(plan, [inputs[("color", 0, scale)]],
                                        [inputs[("color", f, scale)] for f in opt.frame_ids[1:]], [disp],
                                        inputs[("inv_K", scale)], None, noise, K=inputs[("K", scale)],
-                                       Ts=self._vsl_poses(inputs, outputs))
+                                       Ts=self._vsl_poses(inputs, outputs, [scale]))
             losses["min_loss/{}".format(scale)] = vec[0]
             losses["loss/{}".format(scale)] = vec[1]
             if plan.automask:
