@@ -119,6 +119,8 @@ typedef struct VslLossBuffers {
                                            (trainer.py:516-525); null entries fall back to T[f]        */
   const float* noise[VSL_MAX_SCALES];   /* torch.randn draw of trainer.py:656 per scale [B,F,H,W]
                                            ([B,1,H,W] with VSL_FLAG_AVG_REPROJECTION); unused without automask */
+  const float* predictive_mask[VSL_MAX_SCALES]; /* optional, --predictive_mask with --disable_automasking
+                                           (trainer.py:635-642): the mask at the warp resolution [B,F,H,W]  */
   /* outputs */
   float* losses;                        /* [3*S+1]: min_loss/s (S), loss/s (S), loss, smooth/s (S)    */
   float* mask[VSL_MAX_SCALES];          /* outputs["identity_selection/s"] [B,H,W]; may be null       */
@@ -127,6 +129,7 @@ typedef struct VslLossBuffers {
                                               the chain through the per-image mean with smooth_norm        */
   float* smooth_norm;                   /* [S][B][2] per-image normalisation terms for the backward          */
   float* grad_P;                        /* d(min_loss/s)/d P_f  [S][F][B][12]                         */
+  float* grad_predictive_mask[VSL_MAX_SCALES]; /* d(min_loss/s)/d predictive_mask[s] [B,F,H,W] (with it)    */
 } VslLossBuffers;
 
 size_t vsl_loss_workspace_bytes(const VslDesc* desc);

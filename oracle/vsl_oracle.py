@@ -241,6 +241,13 @@ def compute_losses(opt, inputs, outputs, noise=None):
                  for f in opt.frame_ids[1:]], 1)
             if opt.avg_reprojection:
                 ident = ident.mean(1, keepdim=True)
+        elif opt.predictive_mask:  # trainer.py:635-647 (device-agnostic instead of the hard-coded .cuda())
+            mask = outputs["predictive_mask"][("disp", scale)]
+            if not opt.v1_multiscale:
+                mask = F.interpolate(mask, [opt.height, opt.width], mode="bilinear", align_corners=False)
+            reproj *= mask
+            weighting = 0.2 * torch.nn.BCELoss()(mask, torch.ones(mask.shape, device=mask.device))
+            loss += weighting.mean()
         if opt.avg_reprojection:
             reproj = reproj.mean(1, keepdim=True)
 

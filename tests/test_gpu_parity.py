@@ -278,6 +278,36 @@ def test_pose_given_as_T_equals_pose_given_as_P():
         assert ((a - b).norm() / b.norm()).item() <= 1e-6
 
 
+@pytest.mark.parametrize("extra", [{}, {"avg_reprojection": True}, {"v1_multiscale": True}, {"frames": [0, -1, 1, "s"]}])
+def test_predictive_mask(extra):
+    """--predictive_mask with --disable_automasking (trainer.py:635-647): losses, and gradients to the
+    disparities, the poses AND the mask network's outputs."""
+    extra = dict(extra)
+    frames = extra.pop("frames", [0, -1, 1])
+    B, H, W = 2, 64, 96
+    F = len(frames) - 1
+    opt = O.make_opt(height=H, width=W, batch_size=B, frame_ids=list(frames), predictive_mask=True,
+                     disable_automasking=True, **extra)
+    inputs, outputs, leaves = synthetic.make_batch(B, H, W, frames, seed=31, family="smooth", device=DEV)
+    gen = torch.Generator().manual_seed(5)
+    for s in opt.scales:
+        leaves[("pmask", s)] = torch.sigmoid(2 * torch.randn(B, F, H >> s, W >> s, generator=gen)).to(DEV).requires_grad_(True)
+    outputs = dict(outputs)
+    outputs["predictive_mask"] = {("disp", s): leaves[("pmask", s)] for s in opt.scales}
+    ref_out, ref_losses, ref_g = run_oracle(opt, inputs, outputs, leaves)
+    out, losses, g = run_ours(opt, inputs, outputs, leaves, side="none")
+    for k in ref_losses:
+        assert abs(losses[k].item() - ref_losses[k].item()) <= 1e-6 * abs(ref_losses[k].item()), k
+    assert set(g) == set(ref_g)
+    for k in ref_g:
+        assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
+    # with automasking on the reference ignores the predictive mask (elif branch): so do we
+    opt2 = O.make_opt(height=H, width=W, batch_size=B, frame_ids=list(frames), predictive_mask=True, **extra)
+    _, l_ref, _ = run_oracle(opt2, inputs, outputs, leaves)
+    _, l_ours, _ = run_ours(opt2, inputs, outputs, leaves, side="none")
+    assert abs(l_ours["loss"].item() - l_ref["loss"].item()) <= 1e-6 * l_ref["loss"].item()
+
+
 def test_rng_stream_is_consumed_like_the_reference():
     opt, inputs, outputs, leaves = build_case("mono_iid_64x96")
     run_oracle(opt, inputs, outputs, leaves, seed=7)
@@ -453,7 +483,7 @@ def test_errors_are_loud():
     cpu_inputs[("color", 0, 0)] = inputs[("color", 0, 0)].cpu()
     with pytest.raises(_lib.VslError):
         path.compute_losses(cpu_inputs, out)
-    for flag in ("predictive_mask", "pre_trained_generator"):
+    for flag in ("pre_trained_generator",):
         with pytest.raises(NotImplementedError):
             LossPath(make_opt(**{flag: True}), device=DEV).generate_images_pred(inputs, out)
     lib = _lib.load()

@@ -48,7 +48,7 @@ def test_layers_reexports_reference_names():
     assert L.ConvBlock(3, 4)(x).shape == (1, 4, 8, 8) and L.upsample(x).shape == (1, 3, 16, 16)
 
 
-@pytest.mark.parametrize("flag", ["predictive_mask", "pre_trained_generator"])
+@pytest.mark.parametrize("flag", ["pre_trained_generator"])
 def test_unsupported_flags_fail_loudly(flag):
     class P(ViewSynthesisLossMixin):
         pass

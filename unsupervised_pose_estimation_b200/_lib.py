@@ -62,10 +62,10 @@ class VslLossBuffers(Structure):
         ("target", c_void_p * VSL_MAX_SCALES), ("source", c_void_p * VSL_MAX_SRC),
         ("disp", c_void_p * VSL_MAX_SCALES), ("inv_K", c_void_p), ("P", c_void_p * VSL_MAX_SRC),
         ("K", c_void_p), ("T", c_void_p * VSL_MAX_SRC), ("T_scale", (c_void_p * VSL_MAX_SRC) * VSL_MAX_SCALES),
-        ("noise", c_void_p * VSL_MAX_SCALES),
+        ("noise", c_void_p * VSL_MAX_SCALES), ("predictive_mask", c_void_p * VSL_MAX_SCALES),
         ("losses", c_void_p), ("mask", c_void_p * VSL_MAX_SCALES),
         ("grad_disp_photo", c_void_p * VSL_MAX_SCALES), ("grad_disp_smooth", c_void_p * VSL_MAX_SCALES),
-        ("smooth_norm", c_void_p), ("grad_P", c_void_p),
+        ("smooth_norm", c_void_p), ("grad_P", c_void_p), ("grad_predictive_mask", c_void_p * VSL_MAX_SCALES),
     ]
 
 

@@ -625,6 +625,9 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     pp.disp[s] = sp.disp[s] = buf->disp[s];
     pp.noise[s] = buf->noise[s];
     pp.mask[s] = automask ? buf->mask[s] : nullptr;
+    pp.pmask[s] = automask ? nullptr : buf->predictive_mask[s];  // the reference only uses it without automasking
+    pp.gpmask[s] = pp.pmask[s] ? buf->grad_predictive_mask[s] : nullptr;
+    if (pp.pmask[s] && !pp.gpmask[s]) return VSL_ERR_NULL_POINTER;
     pp.gD[s] = (e == 0) ? buf->grad_disp_photo[s] : nullptr;
     pp.gpart[s] = (e == 0) ? nullptr : ws + pl.off_gpart[s];
     sp.gpart[s] = pp.gpart[s];

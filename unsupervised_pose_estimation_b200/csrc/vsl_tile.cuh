@@ -29,6 +29,8 @@ struct PhotoParams {
                                   // whose translation is rescaled by each level's mean inverse depth (trainer.py:516-525)
   const float* noise[kMaxScales]; // [B,F,H,W]
   float* mask[kMaxScales];        // [B,H,W] or null
+  const float* pmask[kMaxScales]; // [B,F,H,W] --predictive_mask, already at the warp resolution; or null
+  float* gpmask[kMaxScales];      // [B,F,H,W] d(min_loss/s)/d pmask
   float* gD[kMaxScales];          // identity levels: [B,H,W] d(min_loss/s)/d disp_s, written directly
   float* gpart[kMaxScales];       // other levels: per-CTA partial up-sample adjoints [numCTA][ncy][ncx]
   float* partials;                // [numCTA][S][1 + F*12]
@@ -75,7 +77,8 @@ struct TileCfg {
 // three 128-bit shared loads.
 struct alignas(16) CoefRec {
   float c[9];
-  float pad0, pad1;
+  float m;     // predictive-mask value of the frame at this window (1 without --predictive_mask)
+  float pad1;
   int idx;  // winning source frame, or -1 (identity won / window outside the image)
 };
 
@@ -389,12 +392,25 @@ VSL_HD void window_coefs(const SsimOut so[3], const float* __restrict__ TS, int 
   }
 }
 
-VSL_HD void store_rec(CoefRec* __restrict__ rec, const float coef[9], int idx) {
+VSL_HD void store_rec(CoefRec* __restrict__ rec, const float coef[9], int idx, float m = 1.0f) {
   CoefRec r;
 #pragma unroll
   for (int k = 0; k < 9; ++k) r.c[k] = coef[k];
-  r.pad0 = 0.f; r.pad1 = 0.f; r.idx = idx;
+  r.m = m; r.pad1 = 0.f; r.idx = idx;
   *rec = r;
+}
+
+// --predictive_mask (trainer.py:635-642, only reached with --disable_automasking): every frame's
+// reprojection loss is multiplied by a learnt per-pixel mask before the minimum.  The kernel receives the
+// mask at the warp resolution, multiplies (one rounding, like `reprojection_losses *= mask`), scales the
+// frame's adjoint by it and returns d/d mask = loss of the winning frame.
+template <class C>
+VSL_HD float pmask_at(const PhotoParams& p, const TileCtx& t, int s, int f, int gy, int gx) {
+  return p.pmask[s] ? p.pmask[s][((size_t)t.b * C::F + f) * p.H * p.W + gy * p.W + gx] : 1.0f;
+}
+template <class C>
+VSL_HD void store_gpmask(const PhotoParams& p, const TileCtx& t, int s, int f, int gy, int gx, float v) {
+  if (p.gpmask[s]) p.gpmask[s][((size_t)t.b * C::F + f) * p.H * p.W + gy * p.W + gx] = v;
 }
 
 // torch.mean over the frame dimension (sequential sum times float(1/F)), trainer.py:629-630, 649-650
@@ -437,19 +453,21 @@ VSL_HD void phase_windows_avg(const PhotoParams& p, const GeoConst& g, const Til
       for (int f = 0; f < C::F; ++f) idl[f] = Id[f * C::WN + i];
       best = add_rn(mean_frames<C::F>(idl), mul_rn(p.noise[s][(size_t)t.b * HW + gy * p.W + gx], 1e-5f));
     }
-    float l[C::F];
+    float l[C::F], lraw[C::F];
 #pragma unroll
     for (int f = 0; f < C::F; ++f) {
       SsimOut so[3];
       if (f < 2 * XL::NP)  // one half of a pair buffer (pixel stride 2) or the un-paired odd last frame
-        l[f] = reproj_window<C, 2>(X + XL::pair_base(f >> 1, 0) + (f & 1), 2 * C::RN, T, TS, wy, wx, i, g.arith, so,
-                                   p.no_ssim != 0);
+        lraw[f] = reproj_window<C, 2>(X + XL::pair_base(f >> 1, 0) + (f & 1), 2 * C::RN, T, TS, wy, wx, i, g.arith, so,
+                                      p.no_ssim != 0);
       else
-        l[f] = reproj_window<C, 1>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
+        lraw[f] = reproj_window<C, 1>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
+      const float m = pmask_at<C>(p, t, s, f, gy, gx);
+      l[f] = p.pmask[s] ? mul_rn(lraw[f], m) : lraw[f];
 #pragma unroll
       for (int k = 0; k < 9; ++k) coef[k] = 0.f;
-      if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc, coef);
-      store_rec(Rec + f * C::WN + i, coef, f);
+      if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc * m, coef);
+      store_rec(Rec + f * C::WN + i, coef, f, m);
     }
     const float avg = mean_frames<C::F>(l);
     const bool warped = avg < best;  // identity first: ties keep the identity channel
@@ -461,6 +479,9 @@ VSL_HD void phase_windows_avg(const PhotoParams& p, const GeoConst& g, const Til
     if (interior) {
       ts.loss += warped ? avg : best;
       if (p.mask[s]) p.mask[s][(size_t)t.b * HW + gy * p.W + gx] = warped ? 1.f : 0.f;
+#pragma unroll
+      for (int f = 0; f < C::F; ++f)
+        store_gpmask<C>(p, t, s, f, gy, gx, warped ? p.wpix * (1.0f / (float)C::F) * lraw[f] : 0.f);
     }
   }
 }
@@ -498,40 +519,51 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
         if (cand < best) { best = cand; bidx = f; }
       }
     }
+    float lraw[C::F], wm = 1.0f;  // un-masked losses (for d/d pmask), mask value of the current winner
 #pragma unroll
     for (int pr = 0; pr < XL::NP; ++pr) {
       PairSums sums;
       F2 l = reproj_window_pair<C>(X + XL::pair_base(pr, 0), T, TS, wy, wx, i, g.arith, g.one, sums, p.no_ssim != 0);
+      lraw[2 * pr] = l.x; lraw[2 * pr + 1] = l.y;
+      const float m0 = pmask_at<C>(p, t, s, 2 * pr, gy, gx), m1 = pmask_at<C>(p, t, s, 2 * pr + 1, gy, gx);
+      if (p.pmask[s]) l = f2(mul_rn(l.x, m0), mul_rn(l.y, m1));
       int win = -1;
       if (l.x < best) { best = l.x; win = 0; }
       if (l.y < best) { best = l.y; win = 1; }
-      if (win >= 0) bidx = C::F + 2 * pr + win;
+      if (win >= 0) { bidx = C::F + 2 * pr + win; wm = win == 0 ? m0 : m1; }
       if (win >= 0 && !p.no_ssim) {  // rebuild the winner's SSIM state from its window sums (same ops, same bits)
         SsimOut so[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           so[c] = win == 0 ? ssim_from_sums(sums.sx[c].x, sums.sxx[c].x, sums.sxy[c].x, TS[c * C::WN + i], TS[(3 + c) * C::WN + i])
                            : ssim_from_sums(sums.sx[c].y, sums.sxx[c].y, sums.sxy[c].y, TS[c * C::WN + i], TS[(3 + c) * C::WN + i]);
-        window_coefs(so, TS, C::WN, i, kc, coef);
+        window_coefs(so, TS, C::WN, i, kc * wm, coef);
       }
     }
     if (XL::R) {
       SsimOut so[3];
       float l = reproj_window<C>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
+      lraw[C::F - 1] = l;
+      const float m = pmask_at<C>(p, t, s, C::F - 1, gy, gx);
+      if (p.pmask[s]) l = mul_rn(l, m);
       if (l < best) {
         best = l;
         bidx = 2 * C::F - 1;
+        wm = m;
 #pragma unroll
         for (int k = 0; k < 9; ++k) coef[k] = 0.f;  // a pair frame may have set them before losing to this one
-        if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc, coef);
+        if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc * wm, coef);
       }
     }
     bool warped = bidx >= C::F;
-    store_rec(Rec + i, coef, warped ? bidx - C::F : -1);
+    store_rec(Rec + i, coef, warped ? bidx - C::F : -1, wm);
     bool interior = wy >= 1 && wy <= C::TH && wx >= 1 && wx <= C::TW;
     if (interior) {
       ts.loss += best;
       if (p.mask[s]) p.mask[s][(size_t)t.b * HW + gy * p.W + gx] = warped ? 1.f : 0.f;
+#pragma unroll
+      for (int f = 0; f < C::F; ++f)
+        store_gpmask<C>(p, t, s, f, gy, gx, (warped && bidx - C::F == f) ? p.wpix * lraw[f] : 0.f);
     }
   }
 }
@@ -560,7 +592,7 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
     int wy = i / C::WW, wx = i - wy * C::WW;
     int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
     const bool inside = live && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-    float best = INFINITY, l = INFINITY;
+    float best = INFINITY, l = INFINITY, lraw = 0.f, m = 1.0f;
     SsimOut so[3];
     if (inside) {
       if (p.automask) {
@@ -569,31 +601,36 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
         float c1 = add_rn(Id[C::WN + i], mul_rn(nz[HW], 1e-5f));
         best = c1 < c0 ? c1 : c0;
       }
-      l = reproj_window<C, 2>(X + XL::pair_base(0, 0) + f, 2 * C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
+      l = lraw = reproj_window<C, 2>(X + XL::pair_base(0, 0) + f, 2 * C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
+      if (p.pmask[s]) {
+        m = pmask_at<C>(p, t, s, f, gy, gx);
+        l = mul_rn(lraw, m);
+      }
     }
     const float other = __shfl_xor_sync(0xffffffffu, l, 1);
     if (!live) continue;
     // arg-min over (identity..., frame 0, frame 1) with ties to the lower index
     const float l0 = f == 0 ? l : other, l1 = f == 0 ? other : l;
     int win = -1;
-    float m = best;
+    float mn = best;
     if (inside) {
-      if (l0 < m) { m = l0; win = 0; }
-      if (l1 < m) { m = l1; win = 1; }
+      if (l0 < mn) { mn = l0; win = 0; }
+      if (l1 < mn) { mn = l1; win = 1; }
     }
     float coef[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) coef[k] = 0.f;
     if (win == f) {
-      if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc, coef);
-      store_rec(Rec + i, coef, f);
+      if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc * m, coef);
+      store_rec(Rec + i, coef, f, m);
     } else if (win < 0 && f == 0) {
       store_rec(Rec + i, coef, -1);
     }
-    if (f == 0 && inside) {
-      bool interior = wy >= 1 && wy <= C::TH && wx >= 1 && wx <= C::TW;
-      if (interior) {
-        ts.loss += m;
+    const bool interior = inside && wy >= 1 && wy <= C::TH && wx >= 1 && wx <= C::TW;
+    if (interior) {
+      store_gpmask<C>(p, t, s, f, gy, gx, win == f ? p.wpix * lraw : 0.f);
+      if (f == 0) {
+        ts.loss += mn;
         if (p.mask[s]) p.mask[s][(size_t)t.b * HW + gy * p.W + gx] = win >= 0 ? 1.f : 0.f;
       }
     }
@@ -656,7 +693,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
                               gx, g.arith);
       cam = backproject_pixel(D, invK, gx, gy, g);
       const int center = (iy + 2) * C::RW + (ix + 2);
-      const int own = Rec[(iy + 1) * C::WW + (ix + 1)].idx;  // AVG: record 0 is live iff the warped mean won
+      const int wc = (iy + 1) * C::WW + (ix + 1);  // this pixel's own window
 #pragma unroll
       for (int f = 0; f < C::F; ++f) {
         if (!(used & (1u << f))) continue;
@@ -665,7 +702,12 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
         for (int c = 0; c < 3; ++c) {
           float xq = X[XL::at(f, c, center)], yq = T[c * C::RN + center];
           float gc = acc[f][c] + 2.f * xq * acc[f][3 + c] + yq * acc[f][6 + c];
-          if (C::AVG ? own >= 0 : own == f) gc += (xq > yq) ? kl1 : ((xq < yq) ? -kl1 : 0.f);
+          // L1 term of the pixel's own window, if frame f is live there; scaled by its predictive-mask value
+          const CoefRec& own = Rec[(C::AVG ? f : 0) * C::WN + wc];
+          if (C::AVG ? own.idx >= 0 : own.idx == f) {
+            const float k1 = kl1 * own.m;
+            gc += (xq > yq) ? k1 : ((xq < yq) ? -k1 : 0.f);
+          }
           gix += gc * G[(f * 6 + c) * C::IN + j];
           giy += gc * G[(f * 6 + 3 + c) * C::IN + j];
         }

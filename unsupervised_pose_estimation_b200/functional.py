@@ -173,8 +173,10 @@ class _FusedLoss(torch.autograd.Function):
     """losses vector [2S+1] = (min_loss/s ..., loss/s ..., loss), masks...  <- disps, P matrices."""
 
     @staticmethod
-    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, *leaves):
+    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, n_pmask, *leaves):
         S, F = len(plan.scales), plan.num_src
+        pmasks = leaves[len(leaves) - n_pmask:] if n_pmask else ()   # --predictive_mask, one [B,F,H,W] per scale
+        leaves = leaves[:len(leaves) - n_pmask] if n_pmask else leaves
         disps, Ps = leaves[:S], leaves[S:]   # Ps: projection matrices [B,3,4], or poses T [B,4,4] if use_T
         per_scale = use_T == "per_scale"     # poses given per (scale, frame): S*F tensors, scale-major
         dev = disps[0].device
@@ -225,6 +227,20 @@ class _FusedLoss(torch.autograd.Function):
         buf.inv_K = iK.data_ptr()
         keep.append(iK)
 
+        if n_pmask:
+            if plan.automask or n_pmask != S:
+                raise ValueError("predictive masks need --disable_automasking and one mask per scale")
+            gpm = []
+            for s in range(S):
+                m = _dev(pmasks[s], "predictive_mask[%d]" % s)
+                if tuple(m.shape) != (B, F, H, W):
+                    raise ValueError("predictive_mask[%d] has shape %s, expected %s" % (s, tuple(m.shape), (B, F, H, W)))
+                gm = torch.empty_like(m)
+                buf.predictive_mask[s], buf.grad_predictive_mask[s] = m.data_ptr(), gm.data_ptr()
+                keep.append(m)
+                gpm.append(gm)
+            ctx.gpm = gpm
+        ctx.n_pmask = n_pmask
         # one flat allocation for everything the backward keeps
         n_levels = [B * (H >> s) * (W >> s) for s in plan.scales]
         sizes = [3 * S + 1, S * F * B * 12, S * B * 2] + n_levels + n_levels
@@ -273,10 +289,17 @@ class _FusedLoss(torch.autograd.Function):
               "vsl_loss_combine_grads")
         gd = [parts[s].view(plan.level_shapes[s]) for s in range(S)]
         gPs = [gP.view(n_pose, B, 4, 4)[i] if ctx.use_T else gP.view(F, B, 3, 4)[i] for i in range(n_pose)]
-        return (None, None, None, None, None, None, None, None) + tuple(gd) + tuple(gPs)
+        gpm = ()
+        if ctx.n_pmask:
+            # d L / d mask_s = a_s * d(min_loss/s)/d mask_s with a_s the upstream weight of min_loss/s
+            # (the same a_s vsl_loss_combine_grads uses; tiny torch arithmetic on the [2S+1] vector)
+            a = up[:S] + up[S:2 * S] + up[2 * S] / S
+            gpm = tuple(ctx.gpm[s] * a[s] for s in range(S))
+        return (None, None, None, None, None, None, None, None, None) + tuple(gd) + tuple(gPs) + gpm
 
 
-def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, K=None, Ts=None):
+def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, K=None, Ts=None,
+               predictive_masks=None):
     """Run the fused path.  Returns (loss_vector[2S+1], [mask_s ...]).
 
     loss_vector order: min_loss/s for every scale, loss/s for every scale, loss
@@ -291,8 +314,9 @@ def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, 
         # one pose per (scale, frame) — posecnn (trainer.py:516-525): Ts[s][f]
         use_T = "per_scale"
         poses = [T for per_frame in poses for T in per_frame]
+    pm = list(predictive_masks or [])
     res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise or []), bool(want_mask), K, use_T,
-                           *(list(disps) + poses))
+                           len(pm), *(list(disps) + poses + pm))
     return res[0], list(res[1:])
 
 

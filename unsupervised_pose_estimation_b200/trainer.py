@@ -30,8 +30,6 @@ from . import functional as VF
 
 def _unsupported(opt):
     bad = []
-    if getattr(opt, "predictive_mask", False):
-        bad.append("--predictive_mask")
     if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn" and "s" in opt.frame_ids:
         bad.append("--pose_model_type posecnn with a stereo frame (the reference itself fails there)")
     if getattr(opt, "pre_trained_generator", False):
@@ -91,6 +89,23 @@ class ViewSynthesisLossMixin:
         if isinstance(plan, list):
             return [(pl, 0, s) for pl, s in zip(plan, self.opt.scales)]
         return [(plan, si, 0) for si, _ in enumerate(self.opt.scales)]
+
+    def _vsl_predictive_masks(self, outputs, scales=None):
+        """--predictive_mask (trainer.py:635-647; only used by the reference together with
+        --disable_automasking): the mask network's outputs at the warp resolution, and the reference's
+        0.2 * BCE(mask, 1) weighting term per scale (plain torch, as in the reference)."""
+        opt = self.opt
+        if not (getattr(opt, "predictive_mask", False) and getattr(opt, "disable_automasking", False)):
+            return None, None
+        masks, weighting = [], []
+        for scale in (opt.scales if scales is None else scales):
+            mask = outputs["predictive_mask"][("disp", scale)]
+            if not getattr(opt, "v1_multiscale", False):
+                mask = torch.nn.functional.interpolate(mask, [opt.height, opt.width], mode="bilinear",
+                                                       align_corners=False)
+            masks.append(mask)
+            weighting.append((0.2 * torch.nn.functional.binary_cross_entropy(mask, torch.ones_like(mask))).mean())
+        return masks, weighting
 
     def _vsl_poses(self, inputs, outputs, scales=None):
         """T_f per source frame: stereo_T or cam_T_cam (reference trainer.py:510-513).  With posecnn the
@@ -166,15 +181,16 @@ class ViewSynthesisLossMixin:
         if plan.automask:
             noise = [torch.randn((opt.batch_size, plan.noise_channels, opt.height, opt.width), device=dev)
                      for _ in opt.scales]
+        pmasks, weighting = self._vsl_predictive_masks(outputs)
         vec, masks = VF.fused_loss(plan, targets, sources, disps, inputs[("inv_K", 0)], None, noise,
-                                   K=inputs[("K", 0)], Ts=self._vsl_poses(inputs, outputs))
+                                   K=inputs[("K", 0)], Ts=self._vsl_poses(inputs, outputs), predictive_masks=pmasks)
         losses = {}
         for si, scale in enumerate(opt.scales):
             losses["min_loss/{}".format(scale)] = vec[si]
-            losses["loss/{}".format(scale)] = vec[S + si]
+            losses["loss/{}".format(scale)] = vec[S + si] if weighting is None else vec[S + si] + weighting[si]
             if plan.automask:  # the reference writes the mask only with automasking on (trainer.py:668-670)
                 outputs["identity_selection/{}".format(scale)] = masks[si]
-        losses["loss"] = vec[2 * S]
+        losses["loss"] = vec[2 * S] if weighting is None else vec[2 * S] + sum(weighting) / S
         return losses
 
 
@@ -188,15 +204,17 @@ class ViewSynthesisLossMixin:
             noise = None
             if plan.automask:
                 noise = [torch.randn((opt.batch_size, plan.noise_channels, plan.height, plan.width), device=disp.device)]
+            pmasks, weighting = self._vsl_predictive_masks(outputs, [scale])
             vec, masks = VF.fused_loss(plan, [inputs[("color", 0, scale)]],
                                        [inputs[("color", f, scale)] for f in opt.frame_ids[1:]], [disp],
                                        inputs[("inv_K", scale)], None, noise, K=inputs[("K", scale)],
-                                       Ts=self._vsl_poses(inputs, outputs, [scale]))
+                                       Ts=self._vsl_poses(inputs, outputs, [scale]), predictive_masks=pmasks)
+            level_loss = vec[1] if weighting is None else vec[1] + weighting[0]
             losses["min_loss/{}".format(scale)] = vec[0]
-            losses["loss/{}".format(scale)] = vec[1]
+            losses["loss/{}".format(scale)] = level_loss
             if plan.automask:
                 outputs["identity_selection/{}".format(scale)] = masks[0]
-            total = total + vec[1]
+            total = total + level_loss
         losses["loss"] = total / self.num_scales if hasattr(self, "num_scales") else total / len(opt.scales)
         return losses
 
