@@ -74,7 +74,7 @@ extern "C" int vsl_emul_photometric(int B, int H, int W, int S, int F, const int
   PhotoParams p;
   std::memset(&p, 0, sizeof(p));
   p.tgt = tgt; p.invK = invK; p.B = B; p.H = H; p.W = W; p.S = S; p.F = F;
-  p.g.one = 1.0f; p.automask = 1; p.no_ssim = 0; p.g.min_disp = min_disp; p.g.disp_range = disp_range; p.g.eps = eps; p.g.W = W; p.g.H = H;
+  p.g.one = 1.0f; p.automask = 1; p.no_ssim = 0; p.pose_per_scale = 0; p.g.min_disp = min_disp; p.g.disp_range = disp_range; p.g.eps = eps; p.g.W = W; p.g.H = H;
   p.g.wm1 = (float)(W - 1); p.g.hm1 = (float)(H - 1);
   p.g.inv_wm1 = 1.0f / p.g.wm1; p.g.inv_hm1 = 1.0f / p.g.hm1; p.g.arith = arith;
   p.wpix = 1.0f / ((float)B * H * W);

@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
     ts.loss = 0.f;
 #pragma unroll
     for (int k = 0; k < C::F * 12; ++k) ts.dP[k] = 0.f;
-    phase_pose<C>(p, g, t, sm, s, tid);  // P of the previous scale is no longer read (sync after its adjoint)
+    // P of the previous scale is no longer read (sync after its adjoint); with one pose for all scales it is formed once
+    if (s == 0 || p.pose_per_scale) phase_pose<C>(p, g, t, sm, s, tid);
     __syncthreads();
     phase_warp<C>(p, g, t, sm, s, tid);
     __syncthreads();
@@ -604,6 +605,12 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   PhotoParams pp = {};
   pp.tgt = buf->target[0];
   pp.automask = automask ? 1 : 0;
+  pp.pose_per_scale = 0;
+  for (int s = 0; s < S; ++s)
+    for (int f = 0; f < F; ++f) pp.pose_per_scale |= buf->T_scale[s][f] != nullptr;
+  bool pmask = false;
+  for (int s = 0; s < S; ++s) pmask |= !automask && buf->predictive_mask[s] != nullptr;
+  if (pmask && d->image_dtype != VSL_DTYPE_F32) return VSL_ERR_UNSUPPORTED;  // predictive mask + bf16 storage: not instantiated
   pp.no_ssim = (d->flags & VSL_FLAG_NO_SSIM) ? 1 : 0;
   pp.invK = buf->inv_K;
   pp.B = sp.B = d->batch; pp.H = sp.H = d->height; pp.W = sp.W = d->width; pp.S = sp.S = S; pp.F = sp.F = F;
@@ -660,7 +667,13 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   VSL_CUDA_OK(cudaGetLastError());
   if (event_before) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_before, st));
   int rc;
-  if (avg) {
+  if (pmask) {  // --predictive_mask kernels: run-time rounding selectors only (one instantiation each)
+    if (avg && F == 2) rc = launch_photometric_impl<TileCfg<32, 16, 2, 256, float, true, true>, false>(pp, pl, d->batch, st);
+    else if (avg) rc = launch_photometric_impl<TileCfg<32, 8, 3, 256, float, true, true>, false>(pp, pl, d->batch, st);
+    else if (F == 1) rc = launch_photometric_impl<TileCfg<32, 16, 1, 256, float, false, true>, false>(pp, pl, d->batch, st);
+    else if (F == 2) rc = launch_photometric_impl<TileCfg<32, 16, 2, 256, float, false, true>, false>(pp, pl, d->batch, st);
+    else rc = launch_photometric_impl<TileCfg<32, 8, 3, 256, float, false, true>, false>(pp, pl, d->batch, st);
+  } else if (avg) {
     if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, float, true>>(pp, pl, d->batch, st);
     else rc = launch_photometric<TileCfg<32, 8, 3, 256, float, true>>(pp, pl, d->batch, st);
   } else if (d->image_dtype == VSL_DTYPE_BF16) {

@@ -42,11 +42,13 @@ struct PhotoParams {
   float wpix;                     // 1 / (B*H*W): weight of one pixel in min_loss/s
   int automask;                   // 0: --disable_automasking (no identity candidates, no noise, no mask)
   int no_ssim;                    // 1: --no_ssim (reprojection loss = mean_c L1)
+  int pose_per_scale;             // 1: T differs per scale (posecnn), P is re-formed at every scale
 };
 
-template <int TW_, int TH_, int F_, int NT_, class Img_ = float, bool AVG_ = false>
+template <int TW_, int TH_, int F_, int NT_, class Img_ = float, bool AVG_ = false, bool PMASK_ = false>
 struct TileCfg {
   typedef Img_ Img;  // storage type of the colour images
+  static constexpr bool PMASK = PMASK_;  // --predictive_mask compiled in (costs ~2 % when merely present)
   static constexpr int TW = TW_, TH = TH_, F = F_, NT = NT_;
   // --avg_reprojection (trainer.py:629-630, 649-650): the frames' losses are averaged before the minimum,
   // so when the warped average wins EVERY frame receives gradient: one coefficient record per frame
@@ -405,12 +407,15 @@ VSL_HD void store_rec(CoefRec* __restrict__ rec, const float coef[9], int idx, f
 // mask at the warp resolution, multiplies (one rounding, like `reprojection_losses *= mask`), scales the
 // frame's adjoint by it and returns d/d mask = loss of the winning frame.
 template <class C>
+VSL_HD bool has_pmask(const PhotoParams& p, int s) { return C::PMASK && p.pmask[s] != nullptr; }
+template <class C>
 VSL_HD float pmask_at(const PhotoParams& p, const TileCtx& t, int s, int f, int gy, int gx) {
+  if (!C::PMASK) return 1.0f;
   return p.pmask[s] ? p.pmask[s][((size_t)t.b * C::F + f) * p.H * p.W + gy * p.W + gx] : 1.0f;
 }
 template <class C>
 VSL_HD void store_gpmask(const PhotoParams& p, const TileCtx& t, int s, int f, int gy, int gx, float v) {
-  if (p.gpmask[s]) p.gpmask[s][((size_t)t.b * C::F + f) * p.H * p.W + gy * p.W + gx] = v;
+  if (C::PMASK && p.gpmask[s]) p.gpmask[s][((size_t)t.b * C::F + f) * p.H * p.W + gy * p.W + gx] = v;
 }
 
 // torch.mean over the frame dimension (sequential sum times float(1/F)), trainer.py:629-630, 649-650
@@ -463,7 +468,7 @@ VSL_HD void phase_windows_avg(const PhotoParams& p, const GeoConst& g, const Til
       else
         lraw[f] = reproj_window<C, 1>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
       const float m = pmask_at<C>(p, t, s, f, gy, gx);
-      l[f] = p.pmask[s] ? mul_rn(lraw[f], m) : lraw[f];
+      l[f] = has_pmask<C>(p, s) ? mul_rn(lraw[f], m) : lraw[f];
 #pragma unroll
       for (int k = 0; k < 9; ++k) coef[k] = 0.f;
       if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc * m, coef);
@@ -526,7 +531,7 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
       F2 l = reproj_window_pair<C>(X + XL::pair_base(pr, 0), T, TS, wy, wx, i, g.arith, g.one, sums, p.no_ssim != 0);
       lraw[2 * pr] = l.x; lraw[2 * pr + 1] = l.y;
       const float m0 = pmask_at<C>(p, t, s, 2 * pr, gy, gx), m1 = pmask_at<C>(p, t, s, 2 * pr + 1, gy, gx);
-      if (p.pmask[s]) l = f2(mul_rn(l.x, m0), mul_rn(l.y, m1));
+      if (has_pmask<C>(p, s)) l = f2(mul_rn(l.x, m0), mul_rn(l.y, m1));
       int win = -1;
       if (l.x < best) { best = l.x; win = 0; }
       if (l.y < best) { best = l.y; win = 1; }
@@ -545,7 +550,7 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
       float l = reproj_window<C>(X + XL::single_base(0), C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
       lraw[C::F - 1] = l;
       const float m = pmask_at<C>(p, t, s, C::F - 1, gy, gx);
-      if (p.pmask[s]) l = mul_rn(l, m);
+      if (has_pmask<C>(p, s)) l = mul_rn(l, m);
       if (l < best) {
         best = l;
         bidx = 2 * C::F - 1;
@@ -602,7 +607,7 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
         best = c1 < c0 ? c1 : c0;
       }
       l = lraw = reproj_window<C, 2>(X + XL::pair_base(0, 0) + f, 2 * C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
-      if (p.pmask[s]) {
+      if (has_pmask<C>(p, s)) {
         m = pmask_at<C>(p, t, s, f, gy, gx);
         l = mul_rn(lraw, m);
       }
@@ -698,16 +703,15 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
       for (int f = 0; f < C::F; ++f) {
         if (!(used & (1u << f))) continue;
         float gix = 0.f, giy = 0.f;
+        // L1 term of the pixel's own window, if frame f is live there; scaled by its predictive-mask value
+        const int own_idx = Rec[(C::AVG ? f : 0) * C::WN + wc].idx;
+        const float k1 = (C::AVG ? own_idx >= 0 : own_idx == f)
+                             ? (C::PMASK ? kl1 * Rec[(C::AVG ? f : 0) * C::WN + wc].m : kl1) : 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float xq = X[XL::at(f, c, center)], yq = T[c * C::RN + center];
           float gc = acc[f][c] + 2.f * xq * acc[f][3 + c] + yq * acc[f][6 + c];
-          // L1 term of the pixel's own window, if frame f is live there; scaled by its predictive-mask value
-          const CoefRec& own = Rec[(C::AVG ? f : 0) * C::WN + wc];
-          if (C::AVG ? own.idx >= 0 : own.idx == f) {
-            const float k1 = kl1 * own.m;
-            gc += (xq > yq) ? k1 : ((xq < yq) ? -k1 : 0.f);
-          }
+          gc += (xq > yq) ? k1 : ((xq < yq) ? -k1 : 0.f);
           gix += gc * G[(f * 6 + c) * C::IN + j];
           giy += gc * G[(f * 6 + 3 + c) * C::IN + j];
         }
