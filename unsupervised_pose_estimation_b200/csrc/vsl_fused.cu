@@ -49,6 +49,7 @@ struct SmallParams {  // smoothness + epilogue
   int hs[kMaxScales], ws[kMaxScales], scale_id[kMaxScales], identity_scale[kMaxScales];
   float scale_h[kMaxScales], scale_w[kMaxScales];
   int chunks0, tiles_per_image, kpartial;
+  unsigned epilogue_blocks;       // number of k_epilogue blocks that have work (the others exit at once)
   float smooth_weight;
 };
 
@@ -246,7 +247,9 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
   int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   int h = p.hs[s], w = p.ws[s], n = h * w;
   int nchunk = (n + kChunk - 1) / kChunk;
-  if (chunk < nchunk && !p.identity_scale[s]) {
+  // identity levels only have the per-image reductions of chunk 0; idle blocks must not touch the counter
+  if (chunk >= (p.identity_scale[s] ? 1 : nchunk)) return;
+  if (!p.identity_scale[s]) {
     // d(min_loss/s)/d disp_s: add the (<= 4) tile partials of every coarse pixel, tiles in a fixed order
     float* gp = p.gphoto[s] + (size_t)b * n;
     const int r = p.W / w;
@@ -300,8 +303,7 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    is_last = atomicAdd(p.counter, 1u) == total - 1;
+    is_last = atomicAdd(p.counter, 1u) == p.epilogue_blocks - 1;
   }
   __syncthreads();
   if (!is_last) return;
@@ -687,7 +689,17 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   }
   if (rc != VSL_OK) return rc;
   if (event_after) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after, st));
-  k_epilogue<<<sgrid, kSmallNT, 0, st>>>(sp);
+  {
+    int gx = 1;
+    sp.epilogue_blocks = 0;
+    for (int s = 0; s < S; ++s) {
+      int nchunk = (sp.hs[s] * sp.ws[s] + kChunk - 1) / kChunk;
+      int active = sp.identity_scale[s] ? 1 : nchunk;
+      if (active > gx) gx = active;
+      sp.epilogue_blocks += (unsigned)active * d->batch;
+    }
+    k_epilogue<<<dim3(gx, d->batch, S), kSmallNT, 0, st>>>(sp);
+  }
   VSL_CUDA_OK(cudaGetLastError());
   return VSL_OK;
 }
