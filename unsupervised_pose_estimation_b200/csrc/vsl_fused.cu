@@ -126,9 +126,22 @@ __device__ __forceinline__ float edge_weight(const Img* img, int n, int ia, int 
 }
 __device__ __forceinline__ float sgnf(float t) { return t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f); }
 
+// signed, weighted difference across one edge: sgn(dhat_a - dhat_b) * exp(-mean_c|img_a - img_b|), and |.| term
+template <class Img>
+__device__ __forceinline__ void edge_term(const float* __restrict__ d, const Img* __restrict__ img, int n, int ia, int ib,
+                                          float inv, float& signed_w, float& abs_term) {
+  float e = edge_weight(img, n, ia, ib), t = (d[ia] - d[ib]) * inv;
+  signed_w = sgnf(t) * e;
+  abs_term = fabsf(t) * e;
+}
+
+// Each pixel owns its right and its down edge: their terms are computed once, kept in shared memory for
+// the chunk, and the left / up neighbours' terms are read back from there (re-computed only when the
+// neighbour lies in another chunk), instead of evaluating all four incident edges per pixel.
 template <class Img>
 __global__ void __launch_bounds__(kSmallNT) k_smooth_terms(const SmallParams p) {
   __shared__ float scratch[kSmallNT / 32];
+  __shared__ float ex[kChunk], ey[kChunk];  // signed weights of the right / down edge of every pixel of the chunk
   int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   int h = p.hs[s], w = p.ws[s], n = h * w;
   if (chunk * kChunk >= n) return;
@@ -136,31 +149,32 @@ __global__ void __launch_bounds__(kSmallNT) k_smooth_terms(const SmallParams p) 
   const float* d = p.disp[s] + (size_t)b * n;
   const Img* img = (const Img*)p.img[s] + (size_t)b * 3 * n;
   float* g_out = p.gsmooth[s] + (size_t)b * n;
-  float cx = 1.0f / ((float)p.B * h * (w - 1)), cy = 1.0f / ((float)p.B * (h - 1) * w);
+  const float cx = 1.0f / ((float)p.B * h * (w - 1)), cy = 1.0f / ((float)p.B * (h - 1) * w);
+  const int i0 = chunk * kChunk, i1 = min(n, i0 + kChunk);
   float sx = 0.f, sy = 0.f, sgd = 0.f;
-  for (int i = chunk * kChunk + threadIdx.x; i < min(n, (chunk + 1) * kChunk); i += kSmallNT) {
+  for (int i = i0 + threadIdx.x; i < i1; i += kSmallNT) {
     int v = i / w, u = i - v * w;
-    float di = d[i], g = 0.f;
-    if (u + 1 < w) {
-      float e = edge_weight(img, n, i, i + 1), t = (di - d[i + 1]) * inv;
-      sx += fabsf(t) * e;
-      g += sgnf(t) * e * cx;
-    }
+    float wx = 0.f, wy = 0.f, a;
+    if (u + 1 < w) { edge_term(d, img, n, i, i + 1, inv, wx, a); sx += a; }
+    if (v + 1 < h) { edge_term(d, img, n, i, i + w, inv, wy, a); sy += a; }
+    ex[i - i0] = wx;
+    ey[i - i0] = wy;
+  }
+  __syncthreads();
+  for (int i = i0 + threadIdx.x; i < i1; i += kSmallNT) {
+    int v = i / w, u = i - v * w;
+    float g = ex[i - i0] * cx + ey[i - i0] * cy, wl = 0.f, wu = 0.f, a;
     if (u > 0) {
-      float e = edge_weight(img, n, i - 1, i), t = (d[i - 1] - di) * inv;
-      g -= sgnf(t) * e * cx;
-    }
-    if (v + 1 < h) {
-      float e = edge_weight(img, n, i, i + w), t = (di - d[i + w]) * inv;
-      sy += fabsf(t) * e;
-      g += sgnf(t) * e * cy;
+      if (i - 1 >= i0) wl = ex[i - 1 - i0];
+      else edge_term(d, img, n, i - 1, i, inv, wl, a);
     }
     if (v > 0) {
-      float e = edge_weight(img, n, i - w, i), t = (d[i - w] - di) * inv;
-      g -= sgnf(t) * e * cy;
+      if (i - w >= i0) wu = ey[i - w - i0];
+      else edge_term(d, img, n, i - w, i, inv, wu, a);
     }
-    g_out[i] = g;  // d smooth / d(norm disp); the chain through the mean is finished in k_epilogue
-    sgd += g * di;
+    g -= wl * cx + wu * cy;
+    g_out[i] = g;  // d smooth / d(norm disp); the chain through the per-image mean is applied by k_combine
+    sgd += g * d[i];
   }
   sx = block_sum<kSmallNT>(sx, scratch);
   sy = block_sum<kSmallNT>(sy, scratch);
