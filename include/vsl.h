@@ -68,7 +68,9 @@ enum {
   VSL_ARITH_DOT3_NOFMA = 1 << 7,   /* K=3 bmm (rays) adds un-fused products: cuBLAS, batch 1 */
   VSL_ARITH_DOT3_REVERSE = 1 << 8, /* probe: k-descending accumulation in the K=3 bmm       */
   VSL_ARITH_DOTKT_NOFMA = 1 << 9,  /* K@T (4x4x4 bmm, layers.py:254) adds un-fused products  */
-  VSL_ARITH_DOTKT_REVERSE = 1 << 10 /* probe: k-descending accumulation in K@T               */
+  VSL_ARITH_DOTKT_REVERSE = 1 << 10, /* probe: k-descending accumulation in K@T              */
+  VSL_ARITH_NORM_SEQ = 1 << 11      /* torch.norm of the axis-angle as (x0^2+x1^2)+x2^2 instead of the
+                                       4-lane shuffle tree (x0^2+x2^2)+x1^2 (vsl_pose_forward)        */
 };
 
 /* Problem descriptor: what Trainer.__init__ fixes once (trainer.py:245-259, options.py). */
@@ -175,6 +177,14 @@ int vsl_probe_bmm(int batch, int k, int n, int arith, const float* A, const floa
 /* ------------------------------------------------------------------------------------
  * Stand-alone layers (the layers.py call surface).  fp32 only.
  * ------------------------------------------------------------------------------------ */
+/* transformation_from_parameters (layers.py:97-114, with rot_from_axisangle :133-172 and
+ * get_translation_matrix :117-130): axisangle [B,3], translation [B,3] -> T [B,4,4]; invert != 0 gives
+ * R^T T(-t) (used for frames before the target, trainer.py:437-438). */
+int vsl_pose_forward(int batch, int invert, int arith, const float* axisangle, const float* translation,
+                     float* T, void* stream);
+/* its backward: grad_T [B,4,4] -> grad_axisangle [B,3], grad_translation [B,3] */
+int vsl_pose_backward(int batch, int invert, const float* axisangle, const float* translation,
+                      const float* grad_T, float* grad_axisangle, float* grad_translation, void* stream);
 /* BackprojectDepth.forward (layers.py:234-239): depth [B,1,h,w], inv_K [B,4,4] -> cam [B,4,hw] */
 int vsl_backproject_forward(int batch, int height, int width, int arith, const float* depth,
                             const float* inv_K, float* cam_points, void* stream);

@@ -401,6 +401,31 @@ def test_graph_replay_equals_eager():
         assert torch.equal(after_eager, after_graph)
 
 
+@pytest.mark.parametrize("batch", [1, 2, 12, 257])
+def test_transformation_from_parameters_kernel(batch):
+    """layers.transformation_from_parameters on CUDA is one kernel: bit-identical to the torch op sequence
+    of the reference (layers.py:97-172), analytic backward equal to autograd's."""
+    gen = torch.Generator().manual_seed(batch)
+    for scale in (0.01, 0.5, 3.0):
+        aa = (scale * torch.randn(batch, 1, 3, generator=gen)).to(DEV).requires_grad_(True)
+        tr = (scale * torch.randn(batch, 1, 3, generator=gen)).to(DEV).requires_grad_(True)
+        w = torch.randn(batch, 4, 4, generator=gen).to(DEV)
+        for invert in (False, True):
+            got, ref = L.transformation_from_parameters(aa, tr, invert), O.transformation_from_parameters(aa, tr, invert)
+            assert got.shape == (batch, 4, 4) and torch.equal(got, ref), (scale, invert)
+            g = torch.autograd.grad((got * w).sum(), [aa, tr])
+            rg = torch.autograd.grad((ref * w).sum(), [aa, tr])
+            for a, b in zip(g, rg):
+                assert ((a - b).norm() / b.norm()).item() <= 2e-5, (scale, invert)
+    zero = torch.zeros(batch, 1, 3, device=DEV, requires_grad=True)
+    T = L.transformation_from_parameters(zero, zero, True)
+    assert torch.equal(T, torch.eye(4, device=DEV).expand(batch, 4, 4))
+    (gz,) = torch.autograd.grad(T.sum(), [zero])
+    assert torch.isfinite(gz).all()
+    cpu = L.transformation_from_parameters(torch.zeros(2, 1, 3), torch.ones(2, 1, 3))  # CPU callers keep working
+    assert cpu.shape == (2, 4, 4) and cpu[0, 0, 3].item() == 1.0
+
+
 # ------------------------------------------------------------------------------------------------
 # stand-alone layers (the layers.py surface)
 # ------------------------------------------------------------------------------------------------

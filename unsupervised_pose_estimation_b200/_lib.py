@@ -32,13 +32,14 @@ ARITH_DOT3_NOFMA = 1 << 7
 ARITH_DOT3_REVERSE = 1 << 8
 ARITH_DOTKT_NOFMA = 1 << 9
 ARITH_DOTKT_REVERSE = 1 << 10
+ARITH_NORM_SEQ = 1 << 11
 
 # every symbol include/vsl.h declares (tests check the shared object exports all of them)
 EXPORTED_SYMBOLS = [
     "vsl_abi_version", "vsl_status_string", "vsl_last_cuda_error",
     "vsl_loss_workspace_bytes", "vsl_loss_forward_backward", "vsl_loss_forward_backward_timed",
     "vsl_event_create", "vsl_event_destroy", "vsl_event_elapsed_ms", "vsl_loss_combine_grads",
-    "vsl_warp_forward", "vsl_probe_bmm",
+    "vsl_warp_forward", "vsl_probe_bmm", "vsl_pose_forward", "vsl_pose_backward",
     "vsl_backproject_forward", "vsl_backproject_backward",
     "vsl_project_forward", "vsl_project_workspace_bytes", "vsl_project_backward",
     "vsl_ssim_forward", "vsl_ssim_workspace_bytes", "vsl_ssim_backward",
@@ -112,6 +113,8 @@ def load():
     lib.vsl_warp_forward.argtypes = [POINTER(VslDesc), c_int, vp, vp, POINTER(c_void_p * VSL_MAX_SRC),
                                      POINTER(c_void_p * VSL_MAX_SRC), vp, POINTER(c_void_p * VSL_MAX_SRC),
                                      POINTER(c_void_p * VSL_MAX_SRC), vp]
+    lib.vsl_pose_forward.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
+    lib.vsl_pose_backward.argtypes = [c_int, c_int, vp, vp, vp, vp, vp, vp]
     lib.vsl_probe_bmm.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp]
     lib.vsl_backproject_forward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp]
     lib.vsl_backproject_backward.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]

@@ -344,6 +344,71 @@ __global__ void __launch_bounds__(kNT) k_probe_bmm(int B, int K, int N, int arit
   }
 }
 
+// ---- transformation_from_parameters (layers.py:97-172) ---------------------------------------------------
+__global__ void __launch_bounds__(kNT) k_pose_fwd(int B, int invert, int arith, const float* __restrict__ aa,
+                                                  const float* __restrict__ tr, float* __restrict__ T) {
+  int b = blockIdx.x * kNT + threadIdx.x;
+  if (b >= B) return;
+  float v[3] = {aa[3 * b], aa[3 * b + 1], aa[3 * b + 2]}, t[3] = {tr[3 * b], tr[3 * b + 1], tr[3 * b + 2]}, M[16];
+  pose_matrix(v, t, invert != 0, arith, M);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) T[16 * b + k] = M[k];
+}
+// Rodrigues backward: R = ca I + sa [a]x + (1 - ca) a a^T, a = v / (|v| + 1e-7)
+__global__ void __launch_bounds__(kNT) k_pose_bwd(int B, int invert, const float* __restrict__ aa,
+                                                  const float* __restrict__ tr, const float* __restrict__ gT,
+                                                  float* __restrict__ gaa, float* __restrict__ gtr) {
+  int b = blockIdx.x * kNT + threadIdx.x;
+  if (b >= B) return;
+  const float v[3] = {aa[3 * b], aa[3 * b + 1], aa[3 * b + 2]}, t[3] = {tr[3 * b], tr[3 * b + 1], tr[3 * b + 2]};
+  const float* g = gT + 16 * b;
+  const float th = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), den = th + 1e-7f;
+  const float a[3] = {v[0] / den, v[1] / den, v[2] / den};
+  const float ca = cosf(th), sa = sinf(th), C = 1.0f - ca;
+  float R[9] = {a[0] * a[0] * C + ca, a[0] * a[1] * C - a[2] * sa, a[2] * a[0] * C + a[1] * sa,
+                a[0] * a[1] * C + a[2] * sa, a[1] * a[1] * C + ca, a[1] * a[2] * C - a[0] * sa,
+                a[2] * a[0] * C - a[1] * sa, a[1] * a[2] * C + a[0] * sa, a[2] * a[2] * C + ca};
+  float gR[9], gt[3];
+  if (!invert) {  // M = [R | t]
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) gR[i * 3 + j] = g[i * 4 + j];
+      gt[i] = g[i * 4 + 3];
+    }
+  } else {        // M = [R^T | -R^T t]
+    const float gc[3] = {g[3], g[7], g[11]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      gt[k] = -(R[k * 3] * gc[0] + R[k * 3 + 1] * gc[1] + R[k * 3 + 2] * gc[2]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gR[k * 3 + i] = g[i * 4 + k] - t[k] * gc[i];
+    }
+  }
+  // R -> (ca, sa, a)
+  float gC = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) gC += gR[i * 3 + j] * a[i] * a[j];
+  const float gca = gR[0] + gR[4] + gR[8] - gC;
+  const float gsa = a[0] * (gR[7] - gR[5]) + a[1] * (gR[2] - gR[6]) + a[2] * (gR[3] - gR[1]);
+  float ga[3] = {sa * (gR[7] - gR[5]), sa * (gR[2] - gR[6]), sa * (gR[3] - gR[1])};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ga[i] += C * (gR[i * 3 + j] + gR[j * 3 + i]) * a[j];
+  float gth = gsa * ca - gca * sa;
+  // a = v / (th + eps)
+  gth -= (ga[0] * v[0] + ga[1] * v[1] + ga[2] * v[2]) / (den * den);
+  const float k = th > 0.f ? gth / th : 0.f;  // d|v|/dv = v/|v| (torch gives 0 at the origin)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    gaa[3 * b + i] = ga[i] / den + k * v[i];
+    gtr[3 * b + i] = gt[i];
+  }
+}
+
 static unsigned blocks_for(size_t n) { return (unsigned)((n + kNT - 1) / kNT); }
 
 }  // namespace vsl
@@ -351,6 +416,24 @@ static unsigned blocks_for(size_t n) { return (unsigned)((n + kNT - 1) / kNT); }
 using namespace vsl;
 
 extern "C" {
+
+int vsl_pose_forward(int B, int invert, int arith, const float* axisangle, const float* translation, float* T,
+                     void* stream) {
+  if (B < 1) return VSL_ERR_BAD_DESC;
+  if (!axisangle || !translation || !T) return VSL_ERR_NULL_POINTER;
+  k_pose_fwd<<<blocks_for((size_t)B), kNT, 0, (cudaStream_t)stream>>>(B, invert, arith, axisangle, translation, T);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+int vsl_pose_backward(int B, int invert, const float* axisangle, const float* translation, const float* grad_T,
+                      float* grad_axisangle, float* grad_translation, void* stream) {
+  if (B < 1) return VSL_ERR_BAD_DESC;
+  if (!axisangle || !translation || !grad_T || !grad_axisangle || !grad_translation) return VSL_ERR_NULL_POINTER;
+  k_pose_bwd<<<blocks_for((size_t)B), kNT, 0, (cudaStream_t)stream>>>(B, invert, axisangle, translation, grad_T,
+                                                                      grad_axisangle, grad_translation);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
 
 int vsl_probe_bmm(int B, int K, int N, int arith, const float* A, const float* X, float* out, void* stream) {
   if (B < 1 || N < 1 || (K != 3 && K != 4)) return VSL_ERR_BAD_DESC;

@@ -87,7 +87,7 @@ VSL_HD F2 sub2(F2 a, F2 b) { return add2(a, f2(-b.x, -b.y)); }  // a + (-b) roun
 enum : int {
   kTrueDiv = 1 << 0, kDotNoFma = 1 << 1, kDotReverse = 1 << 2, kUpsRight = 1 << 3,
   kUpsNoFma = 1 << 4, kTapNoFma = 1 << 5, kMeanDiv = 1 << 6, kDot3NoFma = 1 << 7, kDot3Reverse = 1 << 8,
-  kDotKTNoFma = 1 << 9, kDotKTReverse = 1 << 10
+  kDotKTNoFma = 1 << 9, kDotKTReverse = 1 << 10, kNormSeq = 1 << 11
 };
 
 // ---- bmm dot products ----------------------------------------------------------------------------
@@ -342,6 +342,40 @@ VSL_HD void ssim_r_grads(const SsimOut& o, float mu_y, float& dmu, float& dexx, 
   dexy = 2.0f * o.n1 * inv_d;
   dexx = -o.r * o.d1 * inv_d;  // -r/d2
   dmu = inv_d * (2.0f * mu_y * (o.n2 - o.n1) - o.r * 2.0f * o.mu_x * (o.d2 - o.d1));
+}
+
+// ---- pose network output -> 4x4 (layers.py:97-172), rounded like the reference's torch ops on CUDA ------
+// torch.norm over the 3 contiguous components reduces across 4 lanes with a shuffle tree:
+// (x0^2 + x2^2) + x1^2 (probed on the B200, tools/probe_pose.py; kNormSeq selects the sequential order).
+// M = T(t) R, or inverted R^T T(-t): every product with the 0/1 entries is exact, only the inverted
+// translation column is a real 3-term dot product (accumulated in the calibrated 4x4x4 bmm order).
+VSL_HD void pose_matrix(const float v[3], const float t[3], bool invert, int arith, float M[16]) {
+  const float q0 = mul_rn(v[0], v[0]), q1 = mul_rn(v[1], v[1]), q2 = mul_rn(v[2], v[2]);
+  const float ss = (arith & kNormSeq) ? add_rn(add_rn(q0, q1), q2) : add_rn(add_rn(q0, q2), q1);
+#if defined(__CUDA_ARCH__)
+  const float angle = __fsqrt_rn(ss);
+#else
+  const float angle = sqrtf(ss);
+#endif
+  const float den = add_rn(angle, 1e-7f);
+  const float x = div_rn(v[0], den), y = div_rn(v[1], den), z = div_rn(v[2], den);
+  const float ca = cosf(angle), sa = sinf(angle);
+  const float C = sub_rn(1.0f, ca);
+  const float xs = mul_rn(x, sa), ys = mul_rn(y, sa), zs = mul_rn(z, sa);
+  const float xC = mul_rn(x, C), yC = mul_rn(y, C), zC = mul_rn(z, C);
+  const float xyC = mul_rn(x, yC), yzC = mul_rn(y, zC), zxC = mul_rn(z, xC);
+  float R[9];
+  R[0] = add_rn(mul_rn(x, xC), ca); R[1] = sub_rn(xyC, zs);           R[2] = add_rn(zxC, ys);
+  R[3] = add_rn(xyC, zs);           R[4] = add_rn(mul_rn(y, yC), ca); R[5] = sub_rn(yzC, xs);
+  R[6] = sub_rn(zxC, ys);           R[7] = add_rn(yzC, xs);           R[8] = add_rn(mul_rn(z, zC), ca);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) M[i * 4 + j] = invert ? R[j * 3 + i] : R[i * 3 + j];
+    M[i * 4 + 3] = invert ? dot4kt(R[i], -t[0], R[3 + i], -t[1], R[6 + i], -t[2], 0.0f, 1.0f, arith) : t[i];
+    M[12 + i] = 0.0f;
+  }
+  M[15] = 1.0f;
 }
 
 // reflect-pad-1 index map (nn.ReflectionPad2d(1), layers.py:313): -1 -> 1, n -> n-2

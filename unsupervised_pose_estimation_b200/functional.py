@@ -84,6 +84,84 @@ def calibrate_arith(batch, height, width, device):
     return bits
 
 
+_POSE_ARITH_CACHE = {}
+
+
+def calibrate_pose_arith(batch, device):
+    """Rounding order of the reference's pose -> 4x4 ops for this batch size on this device: the
+    [B,4,4]x[B,4,4] bmm (shared with K@T) and torch.norm over the three axis-angle components (a 4-lane
+    shuffle tree on CUDA).  Checked once per (batch, device) against torch; raises if neither known order
+    reproduces it."""
+    device = torch.device(device)
+    key = (batch, device.index if device.index is not None else torch.cuda.current_device())
+    if key in _POSE_ARITH_CACHE:
+        return _POSE_ARITH_CACHE[key]
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(7)
+    # the only inexact product of the conversion is matmul(R.transpose(1, 2), T(-t)) of the inverted pose
+    # (layers.py:104-111): a TRANSPOSED left operand, for which cuBLAS may pick another kernel than for K@T
+    Rm, Tm = torch.randn(batch, 4, 4, generator=gen).to(device), torch.randn(batch, 4, 4, generator=gen).to(device)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = torch.matmul(Rm.transpose(1, 2), Tm)[:, :3, :].contiguous()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    A = Rm.transpose(1, 2)[:, :3, :].contiguous()
+    out = torch.empty_like(ref)
+    bits = None
+    for probe, plan_bits in ((0, 0), (_lib.ARITH_DOT_NOFMA, _lib.ARITH_DOTKT_NOFMA), (_lib.ARITH_DOT_REVERSE, _lib.ARITH_DOTKT_REVERSE)):
+        check(lib.vsl_probe_bmm(batch, 4, 4, probe, A.data_ptr(), Tm.data_ptr(), out.data_ptr(), _stream()), "vsl_probe_bmm")
+        if torch.equal(out, ref):
+            bits = plan_bits
+            break
+    if bits is None:
+        raise _lib.VslError("could not reproduce torch.matmul(R^T, T) rounding for batch %d on this device" % batch)
+    v = (0.3 * torch.randn(batch, 1, 3, generator=gen)).to(device)
+    ref = torch.norm(v, 2, 2, True).view(-1)
+    sq = (v * v).view(-1, 3)
+    tree, seq = torch.sqrt((sq[:, 0] + sq[:, 2]) + sq[:, 1]), torch.sqrt((sq[:, 0] + sq[:, 1]) + sq[:, 2])
+    if torch.equal(tree, ref):
+        pass
+    elif torch.equal(seq, ref):
+        bits |= _lib.ARITH_NORM_SEQ
+    else:
+        raise _lib.VslError("could not reproduce torch.norm's rounding for [%d,1,3] on this device" % batch)
+    _POSE_ARITH_CACHE[key] = bits
+    return bits
+
+
+class _PoseMatrix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert, arith):
+        aa, tr = _dev(axisangle, "axisangle"), _dev(translation, "translation")
+        B = aa.shape[0]
+        if aa.numel() != 3 * B or tr.numel() != 3 * B:
+            raise ValueError("axisangle / translation must be [B,1,3], got %s / %s" % (tuple(aa.shape), tuple(tr.shape)))
+        T = torch.empty(B, 4, 4, dtype=torch.float32, device=aa.device)
+        check(_lib.load().vsl_pose_forward(B, int(invert), arith, aa.data_ptr(), tr.data_ptr(), T.data_ptr(), _stream()),
+              "vsl_pose_forward")
+        ctx.save_for_backward(aa, tr)
+        ctx.invert = int(invert)
+        return T
+
+    @staticmethod
+    def backward(ctx, g):
+        aa, tr = ctx.saved_tensors
+        g = _dev(g, "grad")
+        gaa, gtr = torch.empty_like(aa), torch.empty_like(tr)
+        check(_lib.load().vsl_pose_backward(aa.shape[0], ctx.invert, aa.data_ptr(), tr.data_ptr(), g.data_ptr(),
+                                            gaa.data_ptr(), gtr.data_ptr(), _stream()), "vsl_pose_backward")
+        return gaa, gtr, None, None
+
+
+def pose_matrix(axisangle, translation, invert=False, arith="auto"):
+    """transformation_from_parameters (layers.py:97-114) in one kernel, bit-identical to the torch ops."""
+    if arith == "auto":
+        arith = calibrate_pose_arith(axisangle.shape[0], axisangle.device)
+    return _PoseMatrix.apply(axisangle, translation, bool(invert), arith)
+
+
 # --------------------------------------------------------------------------------------------------
 # fused loss
 # --------------------------------------------------------------------------------------------------

@@ -4,9 +4,9 @@ with the view-synthesis layers executing in hand-written sm_100a kernels (libvsl
 CUDA-backed (the hot path; reference layers.py lines in brackets):
     disp_to_depth [85-94] (thin torch arithmetic, identical op order), BackprojectDepth [210-239],
     Project3D [242-264], get_smooth_loss [286-299], SSIM [302-332].
-Host-side pose helpers that stay in PyTorch because they are B x 16 floats and autograd carries
-them: transformation_from_parameters [97-114], get_translation_matrix [117-130],
-rot_from_axisangle [133-172].
+Pose helpers: transformation_from_parameters [97-114] is one CUDA kernel
+for CUDA inputs (bit-identical to the torch ops, with an analytic backward) and the original torch ops
+otherwise; get_translation_matrix [117-130] and rot_from_axisangle [133-172] stay plain torch.
 Names re-exported only so ``from layers import *`` users keep working (networks/depth_decoder.py:14,
 evaluate_depth.py:10): SLlog, RMSE_log, depth_to_disp, ConvBlock, Conv3x3, batchNorm, upsample,
 deconv, compute_depth_errors.  They are network blocks / eval metrics, not part of the path.
@@ -128,7 +128,14 @@ def get_translation_matrix(translation_vector):
 
 
 def transformation_from_parameters(axisangle, translation, invert=False):
-    """Pose-net (axisangle, translation) -> 4x4 (reference layers.py:97-114)."""
+    """Pose-net (axisangle, translation) -> 4x4 (reference layers.py:97-114).
+
+    CUDA float32 tensors go through one kernel (vsl_pose_forward / _backward) that reproduces the torch op
+    sequence below bit for bit; anything else (the CPU callers evaluate_pose.py / test_simple.py, float64)
+    runs the original torch ops, which are this helper's definition."""
+    if axisangle.is_cuda and axisangle.dtype == torch.float32 and translation.dtype == torch.float32 \
+            and axisangle.dim() == 3 and axisangle.shape[1:] == (1, 3) and translation.shape == axisangle.shape:
+        return VF.pose_matrix(axisangle, translation, invert)
     R = rot_from_axisangle(axisangle)
     t = translation.clone()
     if invert:
