@@ -374,6 +374,27 @@ def main():
     e2e_ms = float(t.item())
     e2e_value = world * n0 * args.steps / (e2e_ms * 1e-3)
 
+    # ---- informational (N > 1): the one exchange of data-parallel training with this loss, outside the path:
+    # an all-reduce of the depth/pose-net gradients (28,641,888 fp32 parameters)
+    grad_allreduce = None
+    if dist is not None:
+        payload = torch.zeros(28641888, device=device)
+        for _ in range(3):
+            dist.all_reduce(payload)
+        barrier()
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(payload)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 10], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t.item())
+        nbytes = payload.numel() * 4
+        grad_allreduce = {"bytes": nbytes, "ms": ar_ms,
+                          "bus_gbs": 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+                          "note": "NCCL all-reduce of the net gradients; not part of the timed loss path"}
+
     if rank == 0:
         peak, peak_src = peak_hbm_gbs()
         kms = sum(kernel_ms) / max(1, len(kernel_ms))
@@ -402,6 +423,8 @@ def main():
                                  "see DESIGN.md section 4 and profiles/"},
             "clocks": clocks,
         }
+        if grad_allreduce is not None:
+            line["grad_allreduce"] = grad_allreduce
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             run = oracle_step_cpu(cfg, args.family, B, threads)
