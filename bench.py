@@ -48,7 +48,10 @@ def profiled_traffic_bytes():
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_k_photometric.md")))
     if not files:
         return None, None
-    m = re.search(r"traffic = dram read \+ write\*\* \| ([0-9.]+) \| MB", open(files[-1]).read())
+    text = open(files[-1]).read()
+    m = re.search(r"traffic = dram read \+ write\*\* \| ([0-9.]+) \| MB", text)
+    mi = re.search(r"smsp__inst_executed.sum \| ([0-9.]+) \| inst", text)
+    profiled_traffic_bytes.warp_instructions = float(mi.group(1)) if mi else None
     return (float(m.group(1)) * 1e6, os.path.basename(files[-1])) if m else (None, None)
 
 
@@ -423,6 +426,16 @@ def main():
                                  "see DESIGN.md section 4 and profiles/"},
             "clocks": clocks,
         }
+        winst = getattr(profiled_traffic_bytes, "warp_instructions", None)
+        if traffic is not None and winst:
+            # what actually bounds the kernel: warp-instruction issue (4 schedulers/SM, 1 instruction/clock each)
+            sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_issue = 148 * 4 * sm_hz * 1e6
+            line["roofline_issue"] = {"bound": "instruction issue", "kernel": "k_photometric",
+                                      "warp_instructions_per_launch": winst, "achieved": winst / (kms * 1e-3) / 1e9,
+                                      "peak": peak_issue / 1e9, "unit": "G warp-inst/s",
+                                      "frac": winst / (kms * 1e-3) / peak_issue,
+                                      "source": "smsp__inst_executed.sum of " + traffic_src + ", live kernel time"}
         if grad_allreduce is not None:
             line["grad_allreduce"] = grad_allreduce
         if not args.no_cpu_baseline and world == 1:
