@@ -47,6 +47,8 @@ static bool run_tiles(const PhotoParams& p, int tiles_x, int tiles_y) {
             for (int k = 0; k < C::F * 12; ++k) ts[tid].dP[k] = 0.f;
           }
           for (int tid = 0; tid < C::NT; ++tid) phase_pose<C>(p, p.g, t, sm.data(), s, tid);
+          for (int tid = 0; tid < C::NT; ++tid) phase_stage_noise<C>(p, t, sm.data(), s, tid);
+          for (int tid = 0; tid < C::NT; ++tid) phase_stage_disp<C>(p, t, sm.data(), s, tid);
           for (int tid = 0; tid < C::NT; ++tid) phase_warp<C>(p, p.g, t, sm.data(), s, tid);
           for (int tid = 0; tid < C::NT; ++tid) phase_windows<C>(p, p.g, t, sm.data(), s, tid, ts[tid]);
           for (int tid = 0; tid < C::NT; ++tid) phase_backward<C>(p, p.g, t, sm.data(), s, tid, ts[tid]);

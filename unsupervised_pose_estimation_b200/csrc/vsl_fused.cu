@@ -194,20 +194,38 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
   GeoConst g = p.g;
   if (kFastArith) g.arith = 0;
   TileCtx t;
-  t.b = blockIdx.z;
-  t.x0 = blockIdx.x * C::TW;
-  t.y0 = blockIdx.y * C::TH;
-  t.cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  {
+    // read once and kept: left to itself the compiler re-reads the special registers inside the phase loops
+    unsigned bx, by, bz;
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
+    asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by));
+    asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(bz));
+    t.b = (int)bz;
+    t.x0 = (int)bx * C::TW;
+    t.y0 = (int)by * C::TH;
+    t.cta = (int)((bz * gridDim.y + by) * gridDim.x + bx);
+  }
   const int tid = threadIdx.x;
   const size_t img_off = (size_t)t.b * 3 * p.H * p.W;
 
-  phase_load_region<C>(p, t, (const typename C::Img*)p.tgt + img_off, sm + C::oT, tid);
-  __syncthreads();
-  phase_target_stats<C>(p, t, sm, tid);
-  if (p.automask) {
-    phase_load_sources<C>(p, t, sm, tid);
+  // Global reads whose addresses do not depend on computed values are issued as asynchronous copies well
+  // before their phase: disp_s window (one scale ahead), tie-break noise (a phase ahead), image tiles.
+  phase_stage_disp<C>(p, t, sm, 0, tid);
+  if constexpr (sizeof(typename C::Img) == 4) {
+    phase_stage_images<C>(p, t, sm, tid, p.automask != 0);
+    stage_wait<0>();
     __syncthreads();
-    phase_identity<C>(p, g, t, sm, tid);
+    phase_target_stats<C>(p, t, sm, tid);
+    if (p.automask) phase_identity<C>(p, g, t, sm, tid);
+  } else {
+    phase_load_region<C>(p, t, (const typename C::Img*)p.tgt + img_off, sm + C::oT, tid);
+    __syncthreads();
+    phase_target_stats<C>(p, t, sm, tid);
+    if (p.automask) {
+      phase_load_sources<C>(p, t, sm, tid);
+      __syncthreads();
+      phase_identity<C>(p, g, t, sm, tid);
+    }
   }
 
   float* red = sm + C::oRed;
@@ -218,9 +236,13 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
     for (int k = 0; k < C::F * 12; ++k) ts.dP[k] = 0.f;
     // P of the previous scale is no longer read (sync after its adjoint); with one pose for all scales it is formed once
     if (s == 0 || p.pose_per_scale) phase_pose<C>(p, g, t, sm, s, tid);
+    phase_stage_noise<C>(p, t, sm, s, tid);  // lands during the warp phase
+    stage_wait<1>();                         // this scale's disp window (committed one scale earlier)
     __syncthreads();
     phase_warp<C>(p, g, t, sm, s, tid);
+    stage_wait<0>();
     __syncthreads();
+    if (s + 1 < p.S) phase_stage_disp<C>(p, t, sm, s + 1, tid);  // the adjoint reads the saved depth, not disp
     if constexpr (C::AVG) phase_windows_avg<C>(p, g, t, sm, s, tid, ts);
     else if constexpr (C::F == 2) phase_windows_paired<C>(p, g, t, sm, s, tid, ts);
     else phase_windows<C>(p, g, t, sm, s, tid, ts);

@@ -144,6 +144,41 @@ VSL_HD float upsample_disp(const float* __restrict__ disp, int hs, int ws, float
   return ups_combine(ty.l0, top, ty.l1, bot, arith);
 }
 
+// The same up-sample reading a staged window of disp_s (row stride `stride`, origin (cy0, cx0) in level
+// coordinates; the staging clamps to the level, so every tap index ups_tap() can produce is inside it).
+VSL_HD float upsample_disp_staged(const float* __restrict__ st, int stride, int cy0, int cx0, int hs, int ws,
+                                  float scale_h, float scale_w, bool identity, int v, int u, int arith) {
+  if (identity) return st[(v - cy0) * stride + (u - cx0)];
+  UpsTap ty = ups_tap(v, hs, scale_h), tx = ups_tap(u, ws, scale_w);
+  const float* r0 = st + (ty.i0 - cy0) * stride - cx0;
+  const float* r1 = st + (ty.i1 - cy0) * stride - cx0;
+  float top = ups_combine(tx.l0, r0[tx.i0], tx.l1, r0[tx.i1], arith);
+  float bot = ups_combine(tx.l0, r1[tx.i0], tx.l1, r1[tx.i1], arith);
+  return ups_combine(ty.l0, top, ty.l1, bot, arith);
+}
+
+// ---- asynchronous global -> shared copies (LDGSTS): issued early, awaited right before the data is read,
+// so the global-memory latency overlaps the arithmetic of the phases in between.  Host build: plain copy.
+VSL_HD void stage4(float* __restrict__ dst_shared, const float* __restrict__ src_global) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src_global) : "memory");
+#else
+  *dst_shared = *src_global;
+#endif
+}
+VSL_HD void stage_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+VSL_HD void stage_wait() {  // all but the N most recently committed groups of this thread have landed
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 // ---- geometry ---------------------------------------------------------------------------------
 struct GeoConst {  // per call
   float min_disp, disp_range, eps;
@@ -158,10 +193,11 @@ struct Cam {  // camera-space point of a target pixel: X~ = (z*ray, 1)
 };
 
 // disp_to_depth (layers.py:90-93) + BackprojectDepth (layers.py:235-236); invK: row-major 4x4
-VSL_HD Cam backproject_pixel(float D, const float* __restrict__ invK, int u, int v, const GeoConst& g) {
+VSL_HD float disp_to_z(float D, const GeoConst& g) { return rcp_rn(add_rn(mul_rn(g.disp_range, D), g.min_disp)); }
+// camera point from a known depth z (invK: the first three rows of inv_K, row-major with stride 4)
+VSL_HD Cam backproject_z(float z, const float* __restrict__ invK, int u, int v, const GeoConst& g) {
   Cam c;
-  float scaled = add_rn(mul_rn(g.disp_range, D), g.min_disp);
-  c.z = rcp_rn(scaled);
+  c.z = z;
   float fu = (float)u, fv = (float)v;
   c.rx = dot3(invK[0], fu, invK[1], fv, invK[2], 1.0f, g.arith);
   c.ry = dot3(invK[4], fu, invK[5], fv, invK[6], 1.0f, g.arith);
@@ -170,6 +206,9 @@ VSL_HD Cam backproject_pixel(float D, const float* __restrict__ invK, int u, int
   c.Y = mul_rn(c.z, c.ry);
   c.Z = mul_rn(c.z, c.rz);
   return c;
+}
+VSL_HD Cam backproject_pixel(float D, const float* __restrict__ invK, int u, int v, const GeoConst& g) {
+  return backproject_z(disp_to_z(D, g), invK, u, v, g);
 }
 
 struct Proj {       // Project3D + grid_sample coordinate chain for one source frame
@@ -259,6 +298,44 @@ VSL_HD float div9(float a) {
 #endif
 }
 
+// The unguarded 3-instruction quotient and the guard as a key: the fast result is the correctly rounded
+// a/9 iff div9_key(a) < kDiv9KeyLimit.  Callers that divide several sums take the maximum key and branch
+// once for all of them (div9_all) instead of once per quotient.
+constexpr unsigned kDiv9KeyLimit = 0x63000000u;
+VSL_HD float div9_fast(float a) {
+#if defined(__CUDA_ARCH__)
+  const float y = 1.0f / 9.0f;
+  float q = __fmul_rn(a, y);
+  float r = __fmaf_rn(-9.0f, q, a);
+  return __fmaf_rn(r, y, q);
+#else
+  return div_rn(a, 9.0f);
+#endif
+}
+VSL_HD unsigned div9_key(float a) {
+#if defined(__CUDA_ARCH__)
+  return (__float_as_uint(a) & 0x7fffffffu) - 0x0e000000u;
+#else
+  (void)a;
+  return 0u;
+#endif
+}
+VSL_HD unsigned umax2(unsigned a, unsigned b) { return a > b ? a : b; }
+// q[i] = s[i] / 9 for N sums with one guard branch
+template <int N>
+VSL_HD void div9_all(const float (&s)[N], float (&q)[N]) {
+  unsigned key = 0u;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    q[i] = div9_fast(s[i]);
+    key = umax2(key, div9_key(s[i]));
+  }
+  if (key >= kDiv9KeyLimit) {  // some sum is zero, denormal-ish or huge: IEEE division for all (same bits where the fast path is valid)
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = div_rn(s[i], 9.0f);
+  }
+}
+
 VSL_HD bool div9_fast_ok(float a) {
 #if defined(__CUDA_ARCH__)
   return ((__float_as_uint(a) & 0x7fffffffu) - 0x0e000000u) < 0x63000000u;
@@ -295,12 +372,17 @@ struct SsimOut {
   bool live;                 // clamp passes gradient
 };
 // window sums are the row-major sequential sums ATen's avg_pool2d forms
+// from the pooled means mu_x = sum x / 9, E[x^2], E[xy]
+VSL_HD SsimOut ssim_from_means(float mu_x, float exx, float exy, float mu_y, float sig_y);
 VSL_HD SsimOut ssim_from_sums(float sx, float sxx, float sxy, float mu_y, float sig_y) {
+  return ssim_from_means(div9(sx), div9(sxx), div9(sxy), mu_y, sig_y);
+}
+VSL_HD SsimOut ssim_from_means(float mu_x, float exx, float exy, float mu_y, float sig_y) {
   SsimOut o;
-  o.mu_x = div9(sx);
+  o.mu_x = mu_x;
   float mu_x2 = mul_rn(o.mu_x, o.mu_x);
-  float sig_x = sub_rn(div9(sxx), mu_x2);
-  float sig_xy = sub_rn(div9(sxy), mul_rn(o.mu_x, mu_y));
+  float sig_x = sub_rn(exx, mu_x2);
+  float sig_xy = sub_rn(exy, mul_rn(o.mu_x, mu_y));
   o.n1 = add_rn(mul_rn(mul_rn(2.0f, o.mu_x), mu_y), c1f());
   o.n2 = add_rn(mul_rn(2.0f, sig_xy), c2f());
   o.d1 = add_rn(add_rn(mu_x2, mul_rn(mu_y, mu_y)), c1f());
@@ -314,13 +396,38 @@ VSL_HD SsimOut ssim_from_sums(float sx, float sxx, float sxy, float mu_y, float 
 
 // The same SSIM value for two x-images against one y (the two halves are two source frames); op for op
 // the chain of ssim_from_sums, so each half is bit-identical to the scalar evaluation.
+// N pair quotients with one guard branch (both halves of every pair share it); same bits as div9_2
+template <int N>
+VSL_HD void div9_2_all(const F2 (&s)[N], F2 (&q)[N]) {
+#if defined(__CUDA_ARCH__)
+  const F2 y = splat(1.0f / 9.0f);
+  unsigned key = 0u;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    F2 t = mul2_packed(s[i], y);  // only ever an FMA operand below
+    F2 r = fma2(splat(-9.0f), t, s[i]);
+    q[i] = fma2(r, y, t);
+    key = umax2(key, umax2(div9_key(s[i].x), div9_key(s[i].y)));
+  }
+  if (key >= kDiv9KeyLimit) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = f2(__fdiv_rn(s[i].x, 9.0f), __fdiv_rn(s[i].y, 9.0f));
+  }
+#else
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = f2(div_rn(s[i].x, 9.0f), div_rn(s[i].y, 9.0f));
+#endif
+}
+VSL_HD F2 ssim_val2_means(F2 mu_x, F2 exx, F2 exy, float mu_y, float sig_y, F2 one);
 VSL_HD F2 ssim_val2(F2 sx, F2 sxx, F2 sxy, float mu_y, float sig_y, F2 one) {
+  return ssim_val2_means(div9_2(sx), div9_2(sxx), div9_2(sxy), mu_y, sig_y, one);
+}
+VSL_HD F2 ssim_val2_means(F2 mu_x, F2 exx, F2 exy, float mu_y, float sig_y, F2 one) {
   const F2 muy = splat(mu_y), c1 = splat(c1f()), c2 = splat(c2f());
   const F2 mone = f2(-one.x, -one.y);
-  F2 mu_x = div9_2(sx);
   F2 mu_x2 = mul2_packed(mu_x, mu_x);                       // consumed through FMAs by `one` only
-  F2 sig_x = fma2(mu_x2, mone, div9_2(sxx));                // E[x^2] - mu_x^2
-  F2 sig_xy = fma2(mul2_packed(mu_x, muy), mone, div9_2(sxy));
+  F2 sig_x = fma2(mu_x2, mone, exx);                        // E[x^2] - mu_x^2
+  F2 sig_xy = fma2(mul2_packed(mu_x, muy), mone, exy);
   F2 n1 = addp(c1, add2(mu_x, mu_x), muy, one);             // (2 mu_x) mu_y + C1  (2 mu_x is exact)
   F2 n2 = add2(add2(sig_xy, sig_xy), c2);                   // 2 sigma_xy + C2
   F2 d1 = add2(fma2(mu_x2, one, splat(mul_rn(mu_y, mu_y))), c1);

@@ -68,7 +68,14 @@ struct TileCfg {
   static constexpr int oGD = oRed + (NT / 32) * (1 + F * 12);  // d/d(up-sampled disp) of the tile [IN]
   static constexpr int oH = oGD + IN;           // row-reduced adjoint [TH][TW/2 + 2]
   static constexpr int oP = oH + TH * (TW / 2 + 2);  // this image's projection matrices [F][12]
-  static constexpr int kFloats = oP + F * 12;
+  static constexpr int oInvK = oP + F * 12;     // first three rows of inv_K [12]
+  // staged by asynchronous copies (stage4) while earlier phases compute:
+  static constexpr int NZC = AVG_ ? 1 : F_;     // tie-break noise channels (trainer.py:654-657)
+  static constexpr int oNz = oInvK + 12;        // noise of the current scale on the window grid [NZC][WN]
+  static constexpr int DW = TW + 4, DH = TH + 4;  // window of disp_s under the region (clamped to the level)
+  static constexpr int oDisp = oNz + NZC * WN;  // [DH][DW]
+  static constexpr int oZ = oDisp + DW * DH;    // depth of the interior pixels at the current scale [IN]
+  static constexpr int kFloats = oZ + IN;
   static constexpr int kBytes = kFloats * 4;
   static constexpr int kPartial = 1 + F * 12;
   static_assert(oCoef % 4 == 0, "CoefRec needs 16-byte alignment");
@@ -110,6 +117,49 @@ VSL_HD void phase_pose(const PhotoParams& p, const GeoConst& g, const TileCtx& t
     }
     sm[C::oP + k] = v;
   }
+  if (s == 0 && tid < 12) sm[C::oInvK + tid] = p.invK[t.b * 16 + tid];
+}
+
+// ---- staging (asynchronous): window of disp_s under the region, noise of the window grid --------------
+// Level coordinates of the staged disp window: origin (y0/r - 2, x0/r - 2), (TH/r + 4) x (TW/r + 4) entries
+// (row stride DW), r = 2^e the level's ratio; entries outside the level repeat the border (never selected
+// with a non-zero weight by ups_tap, but they keep every tap index in range).  H and W are multiples of r.
+template <class C>
+VSL_HD void disp_window(const PhotoParams& p, const TileCtx& t, int s, int& cy0, int& cx0, int& rows, int& cols) {
+  const int r = p.W / p.ws[s];
+  cy0 = t.y0 / r - 2; cx0 = t.x0 / r - 2;
+  rows = C::TH / r + 4; cols = C::TW / r + 4;
+}
+template <class C>
+VSL_HD void phase_stage_disp(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
+  int cy0, cx0, rows, cols;
+  disp_window<C>(p, t, s, cy0, cx0, rows, cols);
+  const int hs = p.hs[s], ws = p.ws[s];
+  const float* disp = p.disp[s] + (size_t)t.b * hs * ws;
+  for (int i = tid; i < rows * cols; i += C::NT) {
+    const int ry = i / cols, rx = i - ry * cols;
+    int yy = cy0 + ry, xx = cx0 + rx;
+    yy = yy < 0 ? 0 : (yy > hs - 1 ? hs - 1 : yy);
+    xx = xx < 0 ? 0 : (xx > ws - 1 ? ws - 1 : xx);
+    stage4(sm + C::oDisp + ry * C::DW + rx, disp + yy * ws + xx);
+  }
+  stage_commit();
+}
+template <class C>
+VSL_HD void phase_stage_noise(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
+  if (p.automask) {
+    const int HW = p.H * p.W;
+    const float* nz = p.noise[s] + (size_t)t.b * C::NZC * HW;
+    for (int i = tid; i < C::WN; i += C::NT) {
+      const int wy = i / C::WW, wx = i - wy * C::WW;
+      const int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
+      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+#pragma unroll
+        for (int f = 0; f < C::NZC; ++f) stage4(sm + C::oNz + f * C::WN + i, nz + (size_t)f * HW + gy * p.W + gx);
+      }
+    }
+  }
+  stage_commit();
 }
 
 // ---- phase: load an image tile + 2 halo into a region buffer, reflect-mapped --------------------
@@ -147,8 +197,8 @@ VSL_HD void phase_target_stats(const PhotoParams& p, const TileCtx& t, float* __
 #pragma unroll
           for (int dx = -1; dx <= 1; ++dx) {
             float v = y[dy * C::RW + dx];
-            sy = add_rn(sy, v);
-            syy = add_rn(syy, mul_rn(v, v));
+            if (dy == -1 && dx == -1) { sy = v; syy = mul_rn(v, v); }  // 0 + v: same bits downstream (see reproj_window)
+            else { sy = add_rn(sy, v); syy = add_rn(syy, mul_rn(v, v)); }
           }
         mu = div9(sy);
         sig = sub_rn(div9(syy), mul_rn(mu, mu));
@@ -191,6 +241,10 @@ VSL_HD float reproj_window(const float* __restrict__ X, int cs, const float* __r
     }
     return mean3(l1[0], l1[1], l1[2], arith);
   }
+  // Window sums in avg_pool2d's order (row-major, sequential).  The accumulator's initial 0 + v is skipped:
+  // it changes the result only when every term is -0, and a -0 instead of +0 sum leaves every later value of
+  // the SSIM chain unchanged (each is added to a non-zero constant before it is used).
+  float sums[9], mean[9];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float* x = X + c * cs + XS * center;
@@ -201,13 +255,22 @@ VSL_HD float reproj_window(const float* __restrict__ X, int cs, const float* __r
 #pragma unroll
       for (int dx = -1; dx <= 1; ++dx) {
         float xv = x[XS * (dy * C::RW + dx)], yv = y[dy * C::RW + dx];
-        sx = add_rn(sx, xv);
-        sxx = add_rn(sxx, mul_rn(xv, xv));
-        sxy = add_rn(sxy, mul_rn(xv, yv));
+        if (dy == -1 && dx == -1) {
+          sx = xv; sxx = mul_rn(xv, xv); sxy = mul_rn(xv, yv);
+        } else {
+          sx = add_rn(sx, xv);
+          sxx = add_rn(sxx, mul_rn(xv, xv));
+          sxy = add_rn(sxy, mul_rn(xv, yv));
+        }
       }
-    so[c] = ssim_from_sums(sx, sxx, sxy, TS[c * C::WN + widx], TS[(3 + c) * C::WN + widx]);
-    ss[c] = so[c].val;
+    sums[3 * c] = sx; sums[3 * c + 1] = sxx; sums[3 * c + 2] = sxy;
     l1[c] = fabsf(sub_rn(y[0], x[0]));
+  }
+  div9_all<9>(sums, mean);  // one guard branch for the nine quotients
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    so[c] = ssim_from_means(mean[3 * c], mean[3 * c + 1], mean[3 * c + 2], TS[c * C::WN + widx], TS[(3 + c) * C::WN + widx]);
+    ss[c] = so[c].val;
   }
   float ms = mean3(ss[0], ss[1], ss[2], arith);
   float ml = mean3(l1[0], l1[1], l1[2], arith);
@@ -244,14 +307,26 @@ VSL_HD F2 reproj_window_pair(const float* __restrict__ X2, const float* __restri
       for (int dx = -1; dx <= 1; ++dx) {
         F2 xv = x[dy * C::RW + dx];
         F2 yv = splat(y[dy * C::RW + dx]);
-        sx = add2(sx, xv);
-        sxx = addp(sxx, xv, xv, one);
-        sxy = addp(sxy, xv, yv, one);
+        if (dy == -1 && dx == -1) {  // 0 + v skipped, see reproj_window
+          sx = xv; sxx = mul2(xv, xv); sxy = mul2(xv, yv);
+        } else {
+          sx = add2(sx, xv);
+          sxx = addp(sxx, xv, xv, one);
+          sxy = addp(sxy, xv, yv, one);
+        }
       }
     sums.sx[c] = sx; sums.sxx[c] = sxx; sums.sxy[c] = sxy;
-    ss[c] = ssim_val2(sx, sxx, sxy, TS[c * C::WN + widx], TS[(3 + c) * C::WN + widx], one);
     F2 d = sub2(splat(y[0]), x[0]);
     l1[c] = f2(fabsf(d.x), fabsf(d.y));
+  }
+  {
+    F2 sv[9], mean[9];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { sv[3 * c] = sums.sx[c]; sv[3 * c + 1] = sums.sxx[c]; sv[3 * c + 2] = sums.sxy[c]; }
+    div9_2_all<9>(sv, mean);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      ss[c] = ssim_val2_means(mean[3 * c], mean[3 * c + 1], mean[3 * c + 2], TS[c * C::WN + widx], TS[(3 + c) * C::WN + widx], one);
   }
   F2 ms = mean3_2(ss[0], ss[1], ss[2], arith);
   F2 ml = mean3_2(l1[0], l1[1], l1[2], arith);
@@ -285,6 +360,43 @@ VSL_HD void phase_load_sources(const PhotoParams& p, const TileCtx& t, float* __
         X[XL::single_base(c) + i] = valid ? ldimg((const typename C::Img*)p.src[C::F - 1], img_off + c * HW + o) : 0.f;
     }
   }
+}
+
+// ---- staging (asynchronous, fp32 images): target and source tiles in one batch of copies ---------------
+// Same placement as phase_load_region + phase_load_sources; pixels outside the padded image are zero-filled
+// with ordinary stores (disjoint addresses).
+template <class C>
+VSL_HD void phase_stage_images(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int tid, bool sources) {
+  using XL = XLayout<C>;
+  float* T = sm + C::oT;
+  float* X = sm + C::oX;
+  const int HW = p.H * p.W;
+  const size_t img_off = (size_t)t.b * 3 * HW;
+  const float* tg = (const float*)p.tgt + img_off;
+  for (int i = tid; i < C::RN; i += C::NT) {
+    int ry = i / C::RW, rx = i - ry * C::RW;
+    int gy = t.y0 - 2 + ry, gx = t.x0 - 2 + rx;
+    bool valid = gy >= -1 && gy <= p.H && gx >= -1 && gx <= p.W;
+    int o = reflect1(gy, p.H) * p.W + reflect1(gx, p.W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (valid) stage4(T + c * C::RN + i, tg + c * HW + o);
+      else T[c * C::RN + i] = 0.f;
+    }
+    if (sources) {
+#pragma unroll
+      for (int f = 0; f < C::F; ++f) {
+        const float* sf = (const float*)p.src[f] + img_off;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float* dst = X + XL::at(f, c, i);
+          if (valid) stage4(dst, sf + c * HW + o);
+          else *dst = 0.f;
+        }
+      }
+    }
+  }
+  stage_commit();
 }
 
 // ---- phase: identity reprojection losses of all source frames (trainer.py:620-633) --------------
@@ -328,8 +440,9 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
   float* X = sm + C::oX;
   float* G = sm + C::oG;
   const int HW = p.H * p.W;
-  const float* invK = p.invK + t.b * 16;
-  const float* disp = p.disp[s] + (size_t)t.b * p.hs[s] * p.ws[s];
+  const float* invK = sm + C::oInvK;
+  int cy0, cx0, drows, dcols;
+  disp_window<C>(p, t, s, cy0, cx0, drows, dcols);
   for (int i = tid; i < C::RN; i += C::NT) {
     int ry = i / C::RW, rx = i - ry * C::RW;
     int gy = t.y0 - 2 + ry, gx = t.x0 - 2 + rx;
@@ -341,11 +454,12 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
       for (int c = 0; c < 3; ++c) val[f][c] = 0.f;
     if (valid) {
       int v = reflect1(gy, p.H), u = reflect1(gx, p.W);
-      float D = upsample_disp(disp, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s], p.identity_scale[s] != 0, v, u,
-                              g.arith);
+      float D = upsample_disp_staged(sm + C::oDisp, C::DW, cy0, cx0, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s],
+                                     p.identity_scale[s] != 0, v, u, g.arith);
       Cam cam = backproject_pixel(D, invK, u, v, g);
       bool interior = ry >= 2 && ry < C::TH + 2 && rx >= 2 && rx < C::TW + 2 && gy < p.H && gx < p.W;
       int j = (ry - 2) * C::TW + (rx - 2);
+      if (interior) sm[C::oZ + j] = cam.z;  // the adjoint re-forms the camera point from it
 #pragma unroll
       for (int f = 0; f < C::F; ++f) {
         Proj pr = project_pixel(cam, sm + C::oP + f * 12, g);
@@ -456,7 +570,7 @@ VSL_HD void phase_windows_avg(const PhotoParams& p, const GeoConst& g, const Til
       float idl[C::F];
 #pragma unroll
       for (int f = 0; f < C::F; ++f) idl[f] = Id[f * C::WN + i];
-      best = add_rn(mean_frames<C::F>(idl), mul_rn(p.noise[s][(size_t)t.b * HW + gy * p.W + gx], 1e-5f));
+      best = add_rn(mean_frames<C::F>(idl), mul_rn(sm[C::oNz + i], 1e-5f));
     }
     float l[C::F], lraw[C::F];
 #pragma unroll
@@ -517,10 +631,9 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
     float best = INFINITY;
     int bidx = -1;
     if (p.automask) {
-      const float* nz = p.noise[s] + (size_t)t.b * C::F * HW + gy * p.W + gx;
 #pragma unroll
       for (int f = 0; f < C::F; ++f) {
-        float cand = add_rn(Id[f * C::WN + i], mul_rn(nz[f * HW], 1e-5f));
+        float cand = add_rn(Id[f * C::WN + i], mul_rn(sm[C::oNz + f * C::WN + i], 1e-5f));
         if (cand < best) { best = cand; bidx = f; }
       }
     }
@@ -601,9 +714,8 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
     SsimOut so[3];
     if (inside) {
       if (p.automask) {
-        const float* nz = p.noise[s] + (size_t)t.b * 2 * HW + gy * p.W + gx;
-        float c0 = add_rn(Id[i], mul_rn(nz[0], 1e-5f));
-        float c1 = add_rn(Id[C::WN + i], mul_rn(nz[HW], 1e-5f));
+        float c0 = add_rn(Id[i], mul_rn(sm[C::oNz + i], 1e-5f));
+        float c1 = add_rn(Id[C::WN + i], mul_rn(sm[C::oNz + C::WN + i], 1e-5f));
         best = c1 < c0 ? c1 : c0;
       }
       l = lraw = reproj_window<C, 2>(X + XL::pair_base(0, 0) + f, 2 * C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
@@ -653,8 +765,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
   const CoefRec* Rec = reinterpret_cast<const CoefRec*>(sm + C::oCoef);
   const float* G = sm + C::oG;
   const int HW = p.H * p.W;
-  const float* invK = p.invK + t.b * 16;
-  const float* disp = p.disp[s] + (size_t)t.b * p.hs[s] * p.ws[s];
+  const float* invK = sm + C::oInvK;
   const float kl1 = (p.no_ssim ? p.wpix * (1.0f / 3.0f) : p.wpix * (0.15f / 3.0f)) / (float)(C::AVG ? C::F : 1);
   for (int j = tid; j < C::IN; j += C::NT) {
     int iy = j / C::TW, ix = j - iy * C::TW;
@@ -694,9 +805,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
     Cam cam;
     cam.z = 0.f;
     if (used) {
-      float D = upsample_disp(disp, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s], p.identity_scale[s] != 0, gy,
-                              gx, g.arith);
-      cam = backproject_pixel(D, invK, gx, gy, g);
+      cam = backproject_z(sm[C::oZ + j], invK, gx, gy, g);
       const int center = (iy + 2) * C::RW + (ix + 2);
       const int wc = (iy + 1) * C::WW + (ix + 1);  // this pixel's own window
 #pragma unroll
