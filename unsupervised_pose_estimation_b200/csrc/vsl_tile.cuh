@@ -460,21 +460,33 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
       bool interior = ry >= 2 && ry < C::TH + 2 && rx >= 2 && rx < C::TW + 2 && gy < p.H && gx < p.W;
       int j = (ry - 2) * C::TW + (rx - 2);
       if (interior) sm[C::oZ + j] = cam.z;  // the adjoint re-forms the camera point from it
+      // all frames' taps are requested before any is consumed, so their latencies overlap
+      Proj pr[C::F];
+      Taps tp[C::F];
+      float tap[C::F][3][4];
 #pragma unroll
       for (int f = 0; f < C::F; ++f) {
-        Proj pr = project_pixel(cam, sm + C::oP + f * 12, g);
-        Taps tp = bilinear_taps(pr, p.W, p.H);
-        const typename C::Img* img = (const typename C::Img*)p.src[f] + (size_t)t.b * 3 * HW + pr.y0 * p.W + pr.x0;
-        int dx = tp.x1ok ? 1 : 0, dy = tp.y1ok ? p.W : 0;
+        pr[f] = project_pixel(cam, sm + C::oP + f * 12, g);
+        tp[f] = bilinear_taps(pr[f], p.W, p.H);
+        const typename C::Img* img = (const typename C::Img*)p.src[f] + (size_t)t.b * 3 * HW + pr[f].y0 * p.W + pr[f].x0;
+        int dx = tp[f].x1ok ? 1 : 0, dy = tp[f].y1ok ? p.W : 0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const typename C::Img* q = img + c * HW;
-          float vnw = ldimg(q, 0), vne = ldimg(q, dx), vsw = ldimg(q, dy), vse = ldimg(q, dy + dx);
-          val[f][c] = bilinear_value(tp, vnw, vne, vsw, vse, g.arith);
+          tap[f][c][0] = ldimg(q, 0); tap[f][c][1] = ldimg(q, dx);
+          tap[f][c][2] = ldimg(q, dy); tap[f][c][3] = ldimg(q, dy + dx);
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < C::F; ++f) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float vnw = tap[f][c][0], vne = tap[f][c][1], vsw = tap[f][c][2], vse = tap[f][c][3];
+          val[f][c] = bilinear_value(tp[f], vnw, vne, vsw, vse, g.arith);
+          // grid_sampler_2d_backward's d out / d(ix, iy); zero where the border clip is active
+          float ddx = pr[f].inx ? ((vne - vnw) * tp[f].wy1 + (vse - vsw) * tp[f].wy0) : 0.f;
+          float ddy = pr[f].iny ? ((vsw - vnw) * tp[f].wx1 + (vse - vne) * tp[f].wx0) : 0.f;
           if (interior) {
-            // grid_sampler_2d_backward's d out / d(ix, iy); zero where the border clip is active
-            float ddx = pr.inx ? ((vne - vnw) * tp.wy1 + (vse - vsw) * tp.wy0) : 0.f;
-            float ddy = pr.iny ? ((vsw - vnw) * tp.wx1 + (vse - vne) * tp.wx0) : 0.f;
             G[(f * 6 + c) * C::IN + j] = ddx;
             G[(f * 6 + 3 + c) * C::IN + j] = ddy;
           }

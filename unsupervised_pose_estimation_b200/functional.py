@@ -253,6 +253,9 @@ class _FusedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, n_pmask, *leaves):
         S, F = len(plan.scales), plan.num_src
+        # the masks are non-differentiable outputs: without this autograd hands backward() a zero-filled
+        # [B,H,W] tensor per mask (four 5.9 MB fill kernels per step at config 1)
+        ctx.set_materialize_grads(False)
         pmasks = leaves[len(leaves) - n_pmask:] if n_pmask else ()   # --predictive_mask, one [B,F,H,W] per scale
         leaves = leaves[:len(leaves) - n_pmask] if n_pmask else leaves
         disps, Ps = leaves[:S], leaves[S:]   # Ps: projection matrices [B,3,4], or poses T [B,4,4] if use_T
@@ -350,6 +353,8 @@ class _FusedLoss(torch.autograd.Function):
     def backward(ctx, gvec, *_gmasks):
         plan = ctx.plan
         S, F, B = len(plan.scales), plan.num_src, plan.batch
+        if gvec is None:  # no loss entry was used (grads are not materialised, see forward)
+            return (None,) * (9 + S + (S if ctx.use_T == "per_scale" else 1) * F + ctx.n_pmask)
         dev = gvec.device
         up = _dev(gvec, "upstream gradient")
         n_levels = [int(np.prod(sh)) for sh in plan.level_shapes]
