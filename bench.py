@@ -336,46 +336,106 @@ def main():
     # ---- e2e: host buffers in, loss dict out ---------------------------------------------------
     # Per step: H2D of the step's inputs from pinned host memory (copy stream, into the staging slot the
     # step's graph reads), the step, D2H read of the loss dict.  The copies of step i+1 overlap step i.
+    # Two forms of the host buffers:
+    #   "u8"  (headline): the level-0 frames as 8-bit HWC arrays, as the reference's dataset holds them before
+    #         transforms.ToTensor(); the pyramid and the /255 conversion run on the GPU inside the step
+    #         (input_pipeline.LossInputPipeline, bit-exact with Pillow / torchvision);
+    #   "f32": the fp32 ("color", f, s) tensors the reference's DataLoader hands to process_batch.
     from unsupervised_pose_estimation_b200.staging import HostBatchStager
+    from unsupervised_pose_estimation_b200.input_pipeline import LossInputPipeline
     wl_h = Workload(cfg, args.family, device, ring, pinned=True, bf16_images=args.bf16_images)
-    host_batches = [dict(list(h["inputs"].items()) + list(h["leaves"].items())) for h in wl_h.host]
-    stager = HostBatchStager(device, depth=2)
     is_leaf = lambda k: isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam")
-    slot_steps = {}
+    is_color = lambda k: isinstance(k, tuple) and k[0] == "color"
+    img_dtype = torch.bfloat16 if args.bf16_images else torch.float32
 
-    def slot_step(dev):
-        key = id(dev)
-        if key not in slot_steps:
-            inputs = {k: v for k, v in dev.items() if not is_leaf(k)}
-            leaves = {k: v.requires_grad_(True) for k, v in dev.items() if is_leaf(k)}
-            if args.no_graph:
-                slot_steps[key] = lambda: wl_h.step({"inputs": inputs, "leaves": leaves})
-            else:
-                slot_steps[key] = GraphedLossStep(wl_h.path, inputs, leaves).replay
-        return slot_steps[key]
+    def host_batches_for(mode):
+        out = []
+        for h in wl_h.host:
+            hb = dict(list(h["inputs"].items()) + list(h["leaves"].items()))
+            if mode == "u8":
+                frames = {k[1]: v for k, v in hb.items() if is_color(k) and k[2] == 0}
+                hb = {k: v for k, v in hb.items() if not is_color(k)}
+                for f, v in frames.items():   # 8-bit HWC, what np.asarray(pil_image) gives
+                    hb[("color_u8", f)] = (v.float().permute(0, 2, 3, 1) * 255).round().clamp(0, 255) \
+                        .to(torch.uint8).contiguous().pin_memory()
+            out.append(hb)
+        return out
 
-    def e2e_loop(n):
-        stager.submit(host_batches[0])
-        for i in range(n):
-            if i + 1 < n:
-                stager.submit(host_batches[(i + 1) % ring])   # next step's H2D, overlaps this step
-            dev = stager.take()
-            losses, _ = slot_step(dev)()
-            stager.release()
-            vec = torch.stack([losses[k] for k in sorted(losses)]).cpu()  # D2H read of the result (syncs)
-        return vec
+    def run_e2e(mode):
+        host_batches = host_batches_for(mode)
+        stager = HostBatchStager(device, depth=2)
+        slot_steps = {}
 
-    e2e_loop(4)
-    barrier()
-    e0.record()
-    vec = e2e_loop(args.steps)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = world * n0 * args.steps / (e2e_ms * 1e-3)
+        def slot_step(dev):
+            key = id(dev)
+            if key not in slot_steps:
+                inputs = {k: v for k, v in dev.items() if not is_leaf(k) and k[0] != "color_u8"}
+                leaves = {k: v.requires_grad_(True) for k, v in dev.items() if is_leaf(k)}
+                pre = None
+                if mode == "u8":
+                    pipe = LossInputPipeline(wl_h.opt, device, img_dtype)
+                    frames = {k[1]: v for k, v in dev.items() if k[0] == "color_u8"}
+                    pre = lambda: pipe(frames, inputs)
+                    pre()
+                if args.no_graph:
+                    def eager():
+                        if pre is not None:
+                            pre()
+                        return wl_h.step({"inputs": inputs, "leaves": leaves})
+                    slot_steps[key] = eager
+                else:
+                    slot_steps[key] = GraphedLossStep(wl_h.path, inputs, leaves, pre=pre).replay
+            return slot_steps[key]
+
+        # D2H read of every step's loss dict: copied into pinned memory right behind the step and read on the
+        # host one step later, after step i+1 has been enqueued (how a training loop logs without stalling)
+        result = [torch.empty(9, dtype=torch.float32).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_loop(n):
+            checksum, pending = 0.0, None
+            stager.submit(host_batches[0])
+            for i in range(n):
+                dev = stager.take()
+                losses, _ = slot_step(dev)()                       # enqueue step i
+                stager.release()
+                vec = torch.stack([losses[k] for k in sorted(losses)])
+                result[i % 2][:vec.numel()].copy_(vec, non_blocking=True)
+                done[i % 2].record()
+                if i + 1 < n:
+                    stager.submit(host_batches[(i + 1) % ring])   # step i+1's H2D (copy stream) overlaps step i
+                if pending is not None:
+                    done[pending].synchronize()
+                    checksum += float(result[pending][:vec.numel()].sum())   # the host really reads every result
+                pending = i % 2
+            done[pending].synchronize()
+            checksum += float(result[pending][:vec.numel()].sum())
+            assert checksum == checksum, "NaN loss"
+            return vec
+
+        e2e_loop(4)
+        barrier()
+        e0.record()
+        vec = e2e_loop(args.steps)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        return {"value": world * n0 * args.steps / (ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": stager.bytes_per_batch, "d2h_bytes_per_step": int(vec.numel() * 4),
+                "ms_per_step": ms / args.steps}
+
+    e2e_u8 = run_e2e("u8")
+    e2e_u8.update({
+        "host_buffers": "8-bit HWC level-0 frames + fp32 disp pyramid, poses, K/inv_K (pinned)",
+        "gpu_launches_per_step": 5 + 2 * (F + 1) + 2,
+        "note": "pyramid (Pillow-exact LANCZOS) + ToTensor on the GPU inside the step; H2D of step i+1 (copy stream) "
+                "overlaps the kernels of step i; loss dict read back every step",
+        "numa_node_rank0": numa_node})
+    e2e_f32 = run_e2e("f32")
+    e2e_f32["host_buffers"] = "fp32 (\"color\", f, s) tensors as the reference's DataLoader yields them + disp, poses, K/inv_K"
 
     # ---- informational (N > 1): the one exchange of data-parallel training with this loss, outside the path:
     # an all-reduce of the depth/pose-net gradients (28,641,888 fp32 parameters)
@@ -409,10 +469,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, cfg),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": stager.bytes_per_batch,
-                    "d2h_bytes_per_step": int(vec.numel() * 4), "ms_per_step": e2e_ms / args.steps,
-                    "note": "H2D of step i+1 (copy stream, pinned) overlaps the kernels of step i; loss dict read back every step",
-                    "numa_node_rank0": numa_node},
+            "e2e": e2e_u8,
+            "e2e_f32_host_tensors": e2e_f32,
             "gpu_launches": 5 * args.steps,
             "kernels_per_step": ["k_smooth_mean", "k_smooth_terms", "k_photometric", "k_epilogue", "k_combine"],
             "host_wall_ms_per_step": 1e3 * t_wall / args.steps,

@@ -222,6 +222,39 @@ int vsl_smooth_loss_forward(int batch, int height, int width, const float* disp,
 int vsl_smooth_loss_backward(int batch, int height, int width, const float* disp, const float* img,
                              const float* grad_loss, float* grad_disp, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Input pipeline: 8-bit frames -> the ("color", f, s) pyramid.
+ * Replaces MonoDataset.preprocess (datasets/mono_dataset2.py:103-124): level s =
+ * transforms.Resize((H // 2^s, W // 2^s), Image.ANTIALIAS)(level s-1) on 8-bit PIL images
+ * (:85-89), then transforms.ToTensor() (:113), followed by the fp32 host->device copy of
+ * trainer.py:373-374.  The host ships the level-0 frames as uint8 HWC (what np.asarray(PIL
+ * image) gives, a quarter of the fp32 bytes and no pyramid); the GPU reproduces Pillow's 8-bit
+ * LANCZOS resampling (Resample.c, horizontal pass then vertical pass, each rounded to 8 bits,
+ * 22-bit fixed-point coefficients) and the /255 conversion bit for bit.
+ * ------------------------------------------------------------------------------------ */
+typedef struct VslPyramidDesc {
+  int32_t abi_version;  /* VSL_ABI_VERSION                                                   */
+  int32_t batch;        /* frames per call                                                   */
+  int32_t height, width;/* level 0; multiples of 2^(num_levels-1)                            */
+  int32_t num_levels;   /* 1..VSL_MAX_SCALES (opt.scales = range(num_levels))                */
+  int32_t out_dtype;    /* VSL_DTYPE_F32 or VSL_DTYPE_BF16 (image storage of the loss path)  */
+} VslPyramidDesc;
+/* workspace: coefficient tables + the 8-bit levels s >= 1; 256-byte aligned, caller-owned */
+size_t vsl_pyramid_workspace_bytes(const VslPyramidDesc* desc);
+/* once per (shape, workspace): evaluates Pillow's precompute_coeffs / normalize_coeffs_8bpc on the
+ * host in double precision and copies the tables into the workspace (enqueued on `stream`) */
+int vsl_pyramid_plan(const VslPyramidDesc* desc, void* workspace, size_t workspace_bytes, void* stream);
+/* frames_hwc: [B,H,W,3] uint8 (device).  levels[s]: [B,3,H>>s,W>>s] out_dtype, or null to skip that
+ * tensor (the 8-bit level is still formed, later levels need it).  levels_u8 (optional, may be null):
+ * levels_u8[s] for s >= 1 receives the 8-bit level [B,H>>s,W>>s,3]. */
+int vsl_pyramid_forward(const VslPyramidDesc* desc, const uint8_t* frames_hwc, void* const levels[VSL_MAX_SCALES],
+                        uint8_t* const levels_u8[VSL_MAX_SCALES], void* workspace, size_t workspace_bytes,
+                        void* stream);
+/* host-only helper (no device work): the coefficient table of one axis, bounds [out_size][2] = (first
+ * input index, tap count), coefs [out_size][13]; ksize_capacity must be 13.  Lets tests compare the
+ * tables with Pillow's without a GPU. */
+int vsl_pyramid_coefficients(int in_size, int out_size, int32_t* bounds, int32_t* coefs, int ksize_capacity);
+
 #ifdef __cplusplus
 }
 #endif

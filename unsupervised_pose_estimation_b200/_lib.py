@@ -45,6 +45,7 @@ EXPORTED_SYMBOLS = [
     "vsl_ssim_forward", "vsl_ssim_workspace_bytes", "vsl_ssim_backward",
     "vsl_reprojection_loss_forward", "vsl_reprojection_loss_backward",
     "vsl_smooth_workspace_bytes", "vsl_smooth_loss_forward", "vsl_smooth_loss_backward",
+    "vsl_pyramid_workspace_bytes", "vsl_pyramid_plan", "vsl_pyramid_forward", "vsl_pyramid_coefficients",
 ]
 
 
@@ -67,6 +68,13 @@ class VslLossBuffers(Structure):
         ("losses", c_void_p), ("mask", c_void_p * VSL_MAX_SCALES),
         ("grad_disp_photo", c_void_p * VSL_MAX_SCALES), ("grad_disp_smooth", c_void_p * VSL_MAX_SCALES),
         ("smooth_norm", c_void_p), ("grad_P", c_void_p), ("grad_predictive_mask", c_void_p * VSL_MAX_SCALES),
+    ]
+
+
+class VslPyramidDesc(Structure):
+    _fields_ = [
+        ("abi_version", c_int32), ("batch", c_int32), ("height", c_int32), ("width", c_int32),
+        ("num_levels", c_int32), ("out_dtype", c_int32),
     ]
 
 
@@ -132,6 +140,12 @@ def load():
     lib.vsl_smooth_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.vsl_smooth_loss_forward.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]
     lib.vsl_smooth_loss_backward.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, vp]
+    lib.vsl_pyramid_workspace_bytes.restype = c_size_t
+    lib.vsl_pyramid_workspace_bytes.argtypes = [POINTER(VslPyramidDesc)]
+    lib.vsl_pyramid_plan.argtypes = [POINTER(VslPyramidDesc), vp, c_size_t, vp]
+    lib.vsl_pyramid_forward.argtypes = [POINTER(VslPyramidDesc), vp, POINTER(c_void_p * VSL_MAX_SCALES),
+                                        POINTER(c_void_p * VSL_MAX_SCALES), vp, c_size_t, vp]
+    lib.vsl_pyramid_coefficients.argtypes = [c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_int]
     _LIB = lib
     return lib
 

@@ -1,0 +1,321 @@
+// On-GPU input pipeline for the loss path: 8-bit frames -> the ("color", f, s) pyramid.
+//
+// The reference builds the pyramid on the CPU in its dataset (datasets/mono_dataset2.py:85-89, 103-124):
+// level s = transforms.Resize((H // 2^s, W // 2^s), Image.ANTIALIAS)(level s-1) on PIL images, then
+// transforms.ToTensor() (HWC uint8 -> CHW float32 / 255), and ships fp32 tensors to the GPU
+// (trainer.py:373-374).  Here the host ships the 8-bit level-0 frames (a quarter of the bytes, and no
+// pyramid) and the GPU reproduces Pillow's 8-bit LANCZOS resampling bit for bit:
+//   * coefficient tables: Pillow's precompute_coeffs + normalize_coeffs_8bpc, evaluated on the host in
+//     double precision exactly like Pillow's C code (vsl_pyramid_plan, once per shape);
+//   * k_lanczos_half: horizontal pass (rounded to 8 bits) then vertical pass (rounded to 8 bits) of one
+//     output tile, integer arithmetic with 22 fractional bits, like ImagingResampleHorizontal/Vertical_8bpc;
+//   * ToTensor: v / 255 as an IEEE division.
+// Byte/integer work, HBM-bound and tiny next to the loss kernels; no tensor cores.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/vsl.h"
+#include "vsl_math.cuh"
+
+namespace vsl {
+
+extern thread_local int g_last_cuda_error;
+
+#define VSL_CUDA_OK_IN(expr)                      \
+  do {                                            \
+    cudaError_t e__ = (expr);                     \
+    if (e__ != cudaSuccess) {                     \
+      g_last_cuda_error = (int)e__;               \
+      return VSL_ERR_CUDA;                        \
+    }                                             \
+  } while (0)
+
+constexpr int kPrecisionBits = 32 - 8 - 2;  // Pillow: PRECISION_BITS
+constexpr int kKsize = 13;                  // ceil(3 * 2) * 2 + 1 taps reserved per output for a 2:1 LANCZOS
+
+// One axis of one level: for output index o, input taps [lo, lo + n) with integer weights w[o][0..n).
+struct AxisTable {
+  const int32_t* bounds;  // [out][2] = (lo, n)
+  const int32_t* coefs;   // [out][kKsize]
+};
+
+struct PyramidPlan {  // offsets (bytes) into the caller's workspace; identical in workspace_bytes() and the launchers
+  size_t off_xb[VSL_MAX_SCALES], off_xc[VSL_MAX_SCALES], off_yb[VSL_MAX_SCALES], off_yc[VSL_MAX_SCALES];
+  size_t off_u8[VSL_MAX_SCALES];  // 8-bit level s >= 1, HWC
+  size_t total;
+};
+
+static bool pyr_desc_ok(const VslPyramidDesc* d) {
+  if (!d || d->abi_version != VSL_ABI_VERSION) return false;
+  if (d->batch < 1 || d->num_levels < 1 || d->num_levels > VSL_MAX_SCALES) return false;
+  if (d->height < 2 || d->width < 2) return false;
+  const int e = d->num_levels - 1;
+  if (((d->height >> e) << e) != d->height || ((d->width >> e) << e) != d->width) return false;
+  if ((d->height >> e) < 1 || (d->width >> e) < 1) return false;
+  if (d->out_dtype != VSL_DTYPE_F32 && d->out_dtype != VSL_DTYPE_BF16) return false;
+  return true;
+}
+
+static PyramidPlan make_pyr_plan(const VslPyramidDesc* d) {
+  PyramidPlan pl = {};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  for (int s = 1; s < d->num_levels; ++s) {
+    const int hs = d->height >> s, ws = d->width >> s;
+    pl.off_xb[s] = take((size_t)ws * 2 * 4);
+    pl.off_xc[s] = take((size_t)ws * kKsize * 4);
+    pl.off_yb[s] = take((size_t)hs * 2 * 4);
+    pl.off_yc[s] = take((size_t)hs * kKsize * 4);
+    pl.off_u8[s] = take((size_t)d->batch * hs * ws * 3);
+  }
+  pl.total = off;
+  return pl;
+}
+
+// Pillow's lanczos_filter / sinc_filter (Resample.c), double precision
+static double sinc_filter(double x) {
+  if (x == 0.0) return 1.0;
+  x = x * M_PI;
+  return sin(x) / x;
+}
+static double lanczos_filter(double x) {
+  if (-3.0 <= x && x < 3.0) return sinc_filter(x) * sinc_filter(x / 3);
+  return 0.0;
+}
+// Pillow's precompute_coeffs (box = the whole axis) followed by normalize_coeffs_8bpc
+static bool axis_coeffs(int in_size, int out_size, std::vector<int32_t>& bounds, std::vector<int32_t>& coefs) {
+  const double scale = (double)in_size / (double)out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 3.0 * filterscale;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  if (ksize > kKsize) return false;
+  bounds.assign((size_t)out_size * 2, 0);
+  coefs.assign((size_t)out_size * kKsize, 0);
+  const double ss = 1.0 / filterscale;
+  std::vector<double> k(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = lanczos_filter((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x) {
+      if (ww != 0.0) k[x] /= ww;
+      coefs[(size_t)xx * kKsize + x] = k[x] < 0 ? (int32_t)(-0.5 + k[x] * (1 << kPrecisionBits))
+                                                : (int32_t)(0.5 + k[x] * (1 << kPrecisionBits));
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  return true;
+}
+
+__device__ __forceinline__ uint8_t clip8(int acc) {  // Pillow: clip8_lookups[acc >> PRECISION_BITS]
+  int v = acc >> kPrecisionBits;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+template <class Out> __device__ __forceinline__ void store_tensor(Out* p, size_t i, uint8_t v);
+template <> __device__ __forceinline__ void store_tensor<float>(float* p, size_t i, uint8_t v) {
+  p[i] = __fdiv_rn((float)v, 255.0f);  // transforms.ToTensor(): .div(255)
+}
+template <> __device__ __forceinline__ void store_tensor<bf16_t>(bf16_t* p, size_t i, uint8_t v) {
+  // bf16 image storage (BASELINE config 3): round-to-nearest-even of the fp32 value, like Tensor.bfloat16()
+  const uint32_t u = __float_as_uint(__fdiv_rn((float)v, 255.0f));
+  p[i].bits = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+
+// level 0: HWC uint8 -> CHW tensor
+template <class Out>
+__global__ void __launch_bounds__(256) k_u8_to_tensor(const uint8_t* __restrict__ in, Out* __restrict__ out, int hw,
+                                                     size_t total_px) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // pixel index over [B, H*W]
+  if (i >= total_px) return;
+  const size_t b = i / hw, o = i - b * hw;
+  const uint8_t* q = in + i * 3;
+  Out* dst = out + b * 3 * hw + o;
+  store_tensor<Out>(dst, 0, q[0]);
+  store_tensor<Out>(dst, (size_t)hw, q[1]);
+  store_tensor<Out>(dst, (size_t)2 * hw, q[2]);
+}
+
+// the same for four consecutive pixels per thread: 3 x 32-bit loads, one float4 (or 4 x bf16) store per plane.
+// Needs H*W % 4 == 0 (then every 12-byte group and every plane segment is aligned).
+__device__ __forceinline__ void store4(float* p, const uint8_t v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(__fdiv_rn((float)v[0], 255.0f), __fdiv_rn((float)v[1], 255.0f),
+                                              __fdiv_rn((float)v[2], 255.0f), __fdiv_rn((float)v[3], 255.0f));
+}
+__device__ __forceinline__ void store4(bf16_t* p, const uint8_t v[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) store_tensor<bf16_t>(p, i, v[i]);
+}
+template <class Out>
+__global__ void __launch_bounds__(256) k_u8_to_tensor_x4(const uint8_t* __restrict__ in, Out* __restrict__ out, int hw,
+                                                        size_t total_quads) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // group of 4 pixels
+  if (i >= total_quads) return;
+  const size_t px = i * 4;
+  const size_t b = px / hw, o = px - b * hw;
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(in + px * 3);
+  const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];  // bytes r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+  const uint8_t r[4] = {(uint8_t)w0, (uint8_t)(w0 >> 24), (uint8_t)(w1 >> 16), (uint8_t)(w2 >> 8)};
+  const uint8_t g[4] = {(uint8_t)(w0 >> 8), (uint8_t)w1, (uint8_t)(w1 >> 24), (uint8_t)(w2 >> 16)};
+  const uint8_t bl[4] = {(uint8_t)(w0 >> 16), (uint8_t)(w1 >> 8), (uint8_t)w2, (uint8_t)(w2 >> 24)};
+  Out* dst = out + b * 3 * hw + o;
+  store4(dst, r);
+  store4(dst + hw, g);
+  store4(dst + 2 * (size_t)hw, bl);
+}
+
+// level s-1 (HWC uint8, hi x wi) -> level s (HWC uint8, hi/2 x wi/2) + CHW tensor.  One CTA: 32 x 8 outputs.
+constexpr int kTX = 32, kTY = 8, kRowsMax = 2 * kTY + kKsize + 1;
+template <class Out>
+__global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
+                                                     Out* __restrict__ out_t, AxisTable tx, AxisTable ty, int hi, int wi) {
+  __shared__ uint8_t hrow[kRowsMax][kTX][3];  // horizontal pass of the input rows this tile's vertical taps touch
+  const int ho = hi >> 1, wo = wi >> 1;
+  const int b = blockIdx.z, x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
+  const int ylast = min(y0 + kTY, ho) - 1;
+  const int row_lo = ty.bounds[2 * y0];
+  const int row_hi = ty.bounds[2 * ylast] + ty.bounds[2 * ylast + 1];  // exclusive
+  const int nrows = row_hi - row_lo;                                    // <= kRowsMax (2 * 7 + 13)
+  const uint8_t* src = in + (size_t)b * hi * wi * 3;
+  for (int item = threadIdx.x; item < nrows * kTX; item += 256) {
+    const int r = item / kTX, xx = item - r * kTX;
+    const int xo = x0 + xx;
+    if (xo >= wo) continue;
+    const int lo = tx.bounds[2 * xo], n = tx.bounds[2 * xo + 1];
+    const int32_t* k = tx.coefs + (size_t)xo * kKsize;
+    const uint8_t* q = src + ((size_t)(row_lo + r) * wi + lo) * 3;
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+    for (int j = 0; j < n; ++j) {
+      const int w = k[j];
+      a0 += q[3 * j] * w; a1 += q[3 * j + 1] * w; a2 += q[3 * j + 2] * w;
+    }
+    hrow[r][xx][0] = clip8(a0); hrow[r][xx][1] = clip8(a1); hrow[r][xx][2] = clip8(a2);
+  }
+  __syncthreads();
+  const int xx = threadIdx.x & (kTX - 1), yy = threadIdx.x / kTX;
+  const int xo = x0 + xx, yo = y0 + yy;
+  if (xo >= wo || yo >= ho) return;
+  const int lo = ty.bounds[2 * yo] - row_lo, n = ty.bounds[2 * yo + 1];
+  const int32_t* k = ty.coefs + (size_t)yo * kKsize;
+  int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int j = 0; j < n; ++j) {
+    const int w = k[j];
+    a0 += hrow[lo + j][xx][0] * w; a1 += hrow[lo + j][xx][1] * w; a2 += hrow[lo + j][xx][2] * w;
+  }
+  const uint8_t v0 = clip8(a0), v1 = clip8(a1), v2 = clip8(a2);
+  const size_t o = (size_t)yo * wo + xo, hw = (size_t)ho * wo;
+  uint8_t* d8 = out_u8 + ((size_t)b * hw + o) * 3;
+  d8[0] = v0; d8[1] = v1; d8[2] = v2;
+  if (out_t) {
+    Out* dt = out_t + (size_t)b * 3 * hw + o;
+    store_tensor<Out>(dt, 0, v0);
+    store_tensor<Out>(dt, hw, v1);
+    store_tensor<Out>(dt, 2 * hw, v2);
+  }
+}
+
+template <class Out>
+static int pyramid_forward_impl(const VslPyramidDesc* d, const PyramidPlan& pl, const uint8_t* frames,
+                                void* const levels[VSL_MAX_SCALES], uint8_t* ws, cudaStream_t st) {
+  const size_t px0 = (size_t)d->batch * d->height * d->width;
+  if (levels[0]) {
+    const int hw = d->height * d->width;
+    if (hw % 4 == 0 && ((uintptr_t)frames & 3u) == 0 && ((uintptr_t)levels[0] & 15u) == 0)
+      k_u8_to_tensor_x4<Out><<<(unsigned)((px0 / 4 + 255) / 256), 256, 0, st>>>(frames, (Out*)levels[0], hw, px0 / 4);
+    else
+      k_u8_to_tensor<Out><<<(unsigned)((px0 + 255) / 256), 256, 0, st>>>(frames, (Out*)levels[0], hw, px0);
+    VSL_CUDA_OK_IN(cudaGetLastError());
+  }
+  const uint8_t* prev = frames;
+  for (int s = 1; s < d->num_levels; ++s) {
+    const int hi = d->height >> (s - 1), wi = d->width >> (s - 1);
+    AxisTable tx = {(const int32_t*)(ws + pl.off_xb[s]), (const int32_t*)(ws + pl.off_xc[s])};
+    AxisTable ty = {(const int32_t*)(ws + pl.off_yb[s]), (const int32_t*)(ws + pl.off_yc[s])};
+    uint8_t* cur = ws + pl.off_u8[s];
+    dim3 grid(((wi >> 1) + kTX - 1) / kTX, ((hi >> 1) + kTY - 1) / kTY, d->batch);
+    k_lanczos_half<Out><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], tx, ty, hi, wi);
+    VSL_CUDA_OK_IN(cudaGetLastError());
+    prev = cur;
+  }
+  return VSL_OK;
+}
+
+}  // namespace vsl
+
+using namespace vsl;
+
+extern "C" {
+
+size_t vsl_pyramid_workspace_bytes(const VslPyramidDesc* desc) {
+  if (!pyr_desc_ok(desc)) return 0;
+  const size_t t = make_pyr_plan(desc).total;
+  return t ? t : 256;
+}
+
+int vsl_pyramid_plan(const VslPyramidDesc* d, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pyr_desc_ok(d)) return VSL_ERR_BAD_DESC;
+  if (!workspace) return VSL_ERR_NULL_POINTER;
+  if (((uintptr_t)workspace & 255u) != 0) return VSL_ERR_MISALIGNED;
+  const PyramidPlan pl = make_pyr_plan(d);
+  if (workspace_bytes < pl.total) return VSL_ERR_WORKSPACE;
+  uint8_t* ws = (uint8_t*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int32_t> bounds, coefs;
+  for (int s = 1; s < d->num_levels; ++s) {
+    const int hi = d->height >> (s - 1), wi = d->width >> (s - 1);
+    // pageable source: the runtime stages the bytes before cudaMemcpyAsync returns, so the vectors may be reused
+    if (!axis_coeffs(wi, wi >> 1, bounds, coefs)) return VSL_ERR_UNSUPPORTED;
+    VSL_CUDA_OK_IN(cudaMemcpyAsync(ws + pl.off_xb[s], bounds.data(), bounds.size() * 4, cudaMemcpyHostToDevice, st));
+    VSL_CUDA_OK_IN(cudaMemcpyAsync(ws + pl.off_xc[s], coefs.data(), coefs.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!axis_coeffs(hi, hi >> 1, bounds, coefs)) return VSL_ERR_UNSUPPORTED;
+    VSL_CUDA_OK_IN(cudaMemcpyAsync(ws + pl.off_yb[s], bounds.data(), bounds.size() * 4, cudaMemcpyHostToDevice, st));
+    VSL_CUDA_OK_IN(cudaMemcpyAsync(ws + pl.off_yc[s], coefs.data(), coefs.size() * 4, cudaMemcpyHostToDevice, st));
+  }
+  return VSL_OK;
+}
+
+int vsl_pyramid_coefficients(int in_size, int out_size, int32_t* bounds, int32_t* coefs, int ksize_capacity) {
+  if (in_size < 1 || out_size < 1 || !bounds || !coefs) return VSL_ERR_BAD_DESC;
+  if (ksize_capacity != kKsize) return VSL_ERR_BAD_DESC;
+  std::vector<int32_t> b, c;
+  if (!axis_coeffs(in_size, out_size, b, c)) return VSL_ERR_UNSUPPORTED;
+  for (size_t i = 0; i < b.size(); ++i) bounds[i] = b[i];
+  for (size_t i = 0; i < c.size(); ++i) coefs[i] = c[i];
+  return VSL_OK;
+}
+
+int vsl_pyramid_forward(const VslPyramidDesc* d, const uint8_t* frames_hwc, void* const levels[VSL_MAX_SCALES],
+                        uint8_t* const levels_u8[VSL_MAX_SCALES], void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pyr_desc_ok(d)) return VSL_ERR_BAD_DESC;
+  if (!frames_hwc || !levels || !workspace) return VSL_ERR_NULL_POINTER;
+  if (((uintptr_t)workspace & 255u) != 0) return VSL_ERR_MISALIGNED;
+  const PyramidPlan pl = make_pyr_plan(d);
+  if (workspace_bytes < pl.total) return VSL_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = d->out_dtype == VSL_DTYPE_BF16
+               ? pyramid_forward_impl<bf16_t>(d, pl, frames_hwc, levels, (uint8_t*)workspace, st)
+               : pyramid_forward_impl<float>(d, pl, frames_hwc, levels, (uint8_t*)workspace, st);
+  if (rc != VSL_OK) return rc;
+  if (levels_u8) {  // optional copies of the 8-bit levels (what PIL would hold), for checking / logging
+    for (int s = 1; s < d->num_levels; ++s)
+      if (levels_u8[s])
+        VSL_CUDA_OK_IN(cudaMemcpyAsync(levels_u8[s], (uint8_t*)workspace + pl.off_u8[s],
+                                       (size_t)d->batch * (d->height >> s) * (d->width >> s) * 3,
+                                       cudaMemcpyDeviceToDevice, st));
+  }
+  return VSL_OK;
+}
+
+}  // extern "C"

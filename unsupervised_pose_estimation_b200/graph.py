@@ -16,7 +16,7 @@ import torch
 
 
 class GraphedLossStep:
-    def __init__(self, path, inputs, leaves, loss_key="loss", warmup=3):
+    def __init__(self, path, inputs, leaves, loss_key="loss", warmup=3, pre=None):
         self.path, self.inputs, self.leaves = path, inputs, leaves
         self.keys = list(leaves.keys())
         dev = next(iter(leaves.values())).device
@@ -24,6 +24,8 @@ class GraphedLossStep:
             raise RuntimeError("kernel timing events cannot be recorded inside a captured graph")
 
         def run():
+            if pre is not None:
+                pre()   # e.g. the on-GPU input pipeline (input_pipeline.LossInputPipeline) filling `inputs`
             outputs = dict(leaves)
             path.generate_images_pred(inputs, outputs)
             losses = path.compute_losses(inputs, outputs)

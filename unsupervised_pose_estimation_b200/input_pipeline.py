@@ -1,0 +1,127 @@
+"""On-GPU input pipeline of the loss path: 8-bit frames in, the ``("color", f, s)`` pyramid out.
+
+The reference prepares its colour inputs on the CPU, inside ``MonoDataset`` (datasets/mono_dataset2.py):
+``preprocess`` (:103-124) resizes every frame to the four pyramid levels with
+``transforms.Resize(..., interpolation=Image.ANTIALIAS)`` (each level from the previous one, :85-89), runs
+``transforms.ToTensor()`` on each, and ``Trainer.process_batch`` then copies the fp32 tensors to the device
+(trainer.py:373-374).  For the loss path that is 59 MB per step at config 1 and the step becomes PCIe-bound.
+
+``FramePyramid`` moves that work behind the copy: the host hands over the level-0 frames as uint8 HWC
+(``np.asarray(pil_image)`` — 13 MB per step at config 1) and the GPU reproduces Pillow's 8-bit LANCZOS
+resampling and the ``/255`` conversion bit for bit (``vsl_pyramid_forward``, csrc/vsl_input.cu), writing the
+same ``("color", f, s)`` tensors the reference's dataset would have produced.  CUDA only, like the rest of the
+package: there is no CPU path.
+
+    pyr = FramePyramid(batch=12, height=192, width=640, num_levels=4, device="cuda")
+    levels = pyr(frame_u8)                      # list of [B,3,H>>s,W>>s] float32 tensors (static buffers)
+    inputs = preprocess({0: u8_0, -1: u8_m1, 1: u8_p1}, pyramids)   # the reference's key layout
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import VSL_ABI_VERSION, VSL_MAX_SCALES, VslPyramidDesc, check
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class FramePyramid:
+    """One frame slot: ``num_levels`` static output tensors + the workspace (coefficient tables, 8-bit levels).
+
+    ``levels`` selects which tensors are written (default: all); the loss path needs every level of the target
+    frame but only level 0 of the source frames (trainer.py:502, :534-537).
+    """
+
+    def __init__(self, batch, height, width, num_levels=4, device="cuda", dtype=torch.float32, levels=None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.VslError("FramePyramid runs on CUDA only (the reference's CPU pyramid is its own dataset code)")
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("dtype must be float32 or bfloat16")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib = _lib.load()
+        self.batch, self.height, self.width, self.num_levels = batch, height, width, num_levels
+        self.wanted = sorted(range(num_levels) if levels is None else levels)
+        last = max(self.wanted) + 1   # levels past the last wanted one are never formed
+        self.desc = VslPyramidDesc(VSL_ABI_VERSION, batch, height, width, last,
+                                   _lib.DTYPE_BF16 if dtype == torch.bfloat16 else _lib.DTYPE_F32)
+        self.ws_bytes = int(self.lib.vsl_pyramid_workspace_bytes(ctypes.byref(self.desc)))
+        if self.ws_bytes == 0:
+            raise ValueError("bad pyramid shape: %dx%d must be multiples of 2^%d" % (height, width, last - 1))
+        with torch.cuda.device(self.device):
+            self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=self.device)
+            off = (-self.ws.data_ptr()) % 256
+            self.ws_ptr = self.ws.data_ptr() + off
+            self.out = {s: torch.empty(batch, 3, height >> s, width >> s, dtype=dtype, device=self.device)
+                        for s in self.wanted}
+            check(self.lib.vsl_pyramid_plan(ctypes.byref(self.desc), ctypes.c_void_p(self.ws_ptr), self.ws_bytes,
+                                            _stream()), "vsl_pyramid_plan")
+            torch.cuda.current_stream().synchronize()  # the tables come from temporary host memory
+
+    def __call__(self, frame_u8, want_u8=False):
+        """frame_u8: [B,H,W,3] uint8 CUDA tensor.  Returns {level: tensor}; with want_u8 also the 8-bit levels."""
+        if frame_u8.device != self.device or frame_u8.dtype != torch.uint8 or not frame_u8.is_contiguous():
+            raise _lib.VslError("frames must be contiguous uint8 tensors on %s (got %s %s)"
+                                % (self.device, frame_u8.dtype, frame_u8.device))
+        if tuple(frame_u8.shape) != (self.batch, self.height, self.width, 3):
+            raise ValueError("frame has shape %s, expected %s"
+                             % (tuple(frame_u8.shape), (self.batch, self.height, self.width, 3)))
+        lv = (ctypes.c_void_p * VSL_MAX_SCALES)()
+        for s, t in self.out.items():
+            lv[s] = t.data_ptr()
+        u8 = None
+        u8p = None
+        if want_u8:
+            u8 = {s: torch.empty(self.batch, self.height >> s, self.width >> s, 3, dtype=torch.uint8, device=self.device)
+                  for s in range(1, self.desc.num_levels)}
+            u8p = (ctypes.c_void_p * VSL_MAX_SCALES)()
+            for s, t in u8.items():
+                u8p[s] = t.data_ptr()
+        check(self.lib.vsl_pyramid_forward(ctypes.byref(self.desc), ctypes.c_void_p(frame_u8.data_ptr()),
+                                           ctypes.byref(lv), ctypes.byref(u8p) if u8p is not None else None,
+                                           ctypes.c_void_p(self.ws_ptr), self.ws_bytes, _stream()),
+              "vsl_pyramid_forward")
+        return (self.out, u8) if want_u8 else self.out
+
+
+class LossInputPipeline:
+    """``MonoDataset.preprocess`` + the host->device copy for the frames the loss path reads.
+
+    ``frame_ids`` as in the options (first entry is the target, trainer.py:502); the target frame gets every
+    level, the source frames level 0 only (``all_levels=True`` forms every level of every frame, like the
+    reference's dataset does for the networks' benefit).
+    """
+
+    def __init__(self, opt, device="cuda", dtype=torch.float32, all_levels=False):
+        self.frame_ids = list(opt.frame_ids)
+        n = len(opt.scales)
+        self.pyramids = {
+            f: FramePyramid(opt.batch_size, opt.height, opt.width, n, device, dtype,
+                            levels=None if (all_levels or i == 0) else [0])
+            for i, f in enumerate(self.frame_ids)}
+
+    def __call__(self, frames_u8, inputs=None):
+        """frames_u8: {frame_id: [B,H,W,3] uint8 CUDA tensor}.  Fills / returns ``inputs[("color", f, s)]``."""
+        inputs = {} if inputs is None else inputs
+        for f in self.frame_ids:
+            for s, t in self.pyramids[f](frames_u8[f]).items():
+                inputs[("color", f, s)] = t
+        return inputs
+
+
+def pyramid_coefficients(in_size, out_size):
+    """Host-only: the integer coefficient table of one axis as the library computes it (bounds, coefs)."""
+    import numpy as np
+    lib = _lib.load()
+    bounds = np.zeros((out_size, 2), np.int32)
+    coefs = np.zeros((out_size, 13), np.int32)
+    check(lib.vsl_pyramid_coefficients(in_size, out_size, bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                       coefs.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 13),
+          "vsl_pyramid_coefficients")
+    return bounds, coefs
