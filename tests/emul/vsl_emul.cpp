@@ -88,6 +88,7 @@ extern "C" int vsl_emul_photometric(int B, int H, int W, int S, int F, const int
     p.hs[s] = H >> e; p.ws[s] = W >> e;
     p.scale_h[s] = (float)p.hs[s] / (float)H; p.scale_w[s] = (float)p.ws[s] / (float)W;
     p.identity_scale[s] = e == 0;
+    p.level_shift[s] = e;
     p.disp[s] = disp[s]; p.noise[s] = noise[s]; p.mask[s] = mask[s];
     gD[s].assign((size_t)B * H * W, 0.f);
     p.gD[s] = gD[s].data();

@@ -1,10 +1,10 @@
 // Fused view-synthesis loss for sm_100a: kernels + C ABI (include/vsl.h).
 //
 // Launch sequence of vsl_loss_forward_backward (one stream, no host sync):
-//   k_smooth_mean   per-image mean of disp_s                     (trainer.py:676)
-//   k_smooth_terms  edge-aware smoothness terms + d/d(norm disp)  (layers.py:286-299)
 //   k_photometric   warp + SSIM/L1 + automask min + adjoint       (trainer.py:491-674)  <- the hot kernel
-//   k_epilogue      sums the tiles' up-sample-adjoint partials (s >= 1), deterministic reductions, loss dict
+//                   + the edge-aware smoothness terms of every level on the tile's own pixels (layers.py:286-299)
+//   k_epilogue      sums the tiles' up-sample-adjoint partials (s >= 1), deterministic reductions (losses, dL/dP,
+//                   per-image mean of disp_s and smoothness sums, trainer.py:676-680), loss dict
 // and of vsl_loss_combine_grads (the backward):
 //   k_combine       smoothness chain rule through the per-image mean + upstream weights
 #include <cuda_runtime.h>
@@ -37,8 +37,6 @@ struct SmallParams {  // smoothness + epilogue
   const float* gpart[kMaxScales]; // per-CTA partial up-sample adjoints (null for identity scales)
   float* norm;                    // [S][B][2]: 1/(mean disp + 1e-7), sum(g*d) * inv^2 / n   (for k_combine)
   int tw, th, tiles_x, tiles_y;
-  float* mean_part;               // [S][B][chunks0]
-  float* smooth_part;             // [S][B][chunks0][3]  (sum_x, sum_y, sum g*d)
   const float* partials;          // photometric partials [numCTA][S][kPartial]
   float* lossb;                   // [S][B]
   float* smoothb;                 // [S][B][2]
@@ -80,109 +78,6 @@ __device__ __forceinline__ float warp_sum32(float (&v)[32], int lane) {
   butterfly_step<4>(v, lane);
   butterfly_step<2>(v, lane);
   return v[0];
-}
-
-// block-wide sum in a fixed order; result valid in every thread
-template <int NT>
-__device__ __forceinline__ float block_sum(float v, float* scratch) {
-  v = warp_sum(v);
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) scratch[w] = v;
-  __syncthreads();
-  float r = 0.f;
-#pragma unroll
-  for (int i = 0; i < NT / 32; ++i) r += scratch[i];
-  return r;
-}
-
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSmallNT) k_smooth_mean(const SmallParams p) {
-  __shared__ float scratch[kSmallNT / 32];
-  int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
-  int n = p.hs[s] * p.ws[s];
-  if (chunk * kChunk >= n) return;
-  const float* d = p.disp[s] + (size_t)b * n;
-  float acc = 0.f;
-  for (int i = chunk * kChunk + threadIdx.x; i < min(n, (chunk + 1) * kChunk); i += kSmallNT) acc += d[i];
-  acc = block_sum<kSmallNT>(acc, scratch);
-  if (threadIdx.x == 0) p.mean_part[(s * p.B + b) * p.chunks0 + chunk] = acc;
-}
-
-__device__ __forceinline__ float image_mean(const SmallParams& p, int s, int b, float* scratch) {
-  int n = p.hs[s] * p.ws[s];
-  int nchunk = (n + kChunk - 1) / kChunk;
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < nchunk; i += kSmallNT) acc += p.mean_part[(s * p.B + b) * p.chunks0 + i];
-  return block_sum<kSmallNT>(acc, scratch) / (float)n;
-}
-
-// edge weight exp(-mean_c |img(a) - img(b)|)  (layers.py:293-297)
-template <class Img>
-__device__ __forceinline__ float edge_weight(const Img* img, int n, int ia, int ib) {
-  float g = fabsf(ldimg(img, ia) - ldimg(img, ib)) + fabsf(ldimg(img, n + ia) - ldimg(img, n + ib)) +
-            fabsf(ldimg(img, 2 * n + ia) - ldimg(img, 2 * n + ib));
-  return expf(-g * (1.0f / 3.0f));
-}
-__device__ __forceinline__ float sgnf(float t) { return t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f); }
-
-// signed, weighted difference across one edge: sgn(dhat_a - dhat_b) * exp(-mean_c|img_a - img_b|), and |.| term
-template <class Img>
-__device__ __forceinline__ void edge_term(const float* __restrict__ d, const Img* __restrict__ img, int n, int ia, int ib,
-                                          float inv, float& signed_w, float& abs_term) {
-  float e = edge_weight(img, n, ia, ib), t = (d[ia] - d[ib]) * inv;
-  signed_w = sgnf(t) * e;
-  abs_term = fabsf(t) * e;
-}
-
-// Each pixel owns its right and its down edge: their terms are computed once, kept in shared memory for
-// the chunk, and the left / up neighbours' terms are read back from there (re-computed only when the
-// neighbour lies in another chunk), instead of evaluating all four incident edges per pixel.
-template <class Img>
-__global__ void __launch_bounds__(kSmallNT) k_smooth_terms(const SmallParams p) {
-  __shared__ float scratch[kSmallNT / 32];
-  __shared__ float ex[kChunk], ey[kChunk];  // signed weights of the right / down edge of every pixel of the chunk
-  int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
-  int h = p.hs[s], w = p.ws[s], n = h * w;
-  if (chunk * kChunk >= n) return;
-  float inv = 1.0f / (image_mean(p, s, b, scratch) + 1e-7f);
-  const float* d = p.disp[s] + (size_t)b * n;
-  const Img* img = (const Img*)p.img[s] + (size_t)b * 3 * n;
-  float* g_out = p.gsmooth[s] + (size_t)b * n;
-  const float cx = 1.0f / ((float)p.B * h * (w - 1)), cy = 1.0f / ((float)p.B * (h - 1) * w);
-  const int i0 = chunk * kChunk, i1 = min(n, i0 + kChunk);
-  float sx = 0.f, sy = 0.f, sgd = 0.f;
-  for (int i = i0 + threadIdx.x; i < i1; i += kSmallNT) {
-    int v = i / w, u = i - v * w;
-    float wx = 0.f, wy = 0.f, a;
-    if (u + 1 < w) { edge_term(d, img, n, i, i + 1, inv, wx, a); sx += a; }
-    if (v + 1 < h) { edge_term(d, img, n, i, i + w, inv, wy, a); sy += a; }
-    ex[i - i0] = wx;
-    ey[i - i0] = wy;
-  }
-  __syncthreads();
-  for (int i = i0 + threadIdx.x; i < i1; i += kSmallNT) {
-    int v = i / w, u = i - v * w;
-    float g = ex[i - i0] * cx + ey[i - i0] * cy, wl = 0.f, wu = 0.f, a;
-    if (u > 0) {
-      if (i - 1 >= i0) wl = ex[i - 1 - i0];
-      else edge_term(d, img, n, i - 1, i, inv, wl, a);
-    }
-    if (v > 0) {
-      if (i - w >= i0) wu = ey[i - w - i0];
-      else edge_term(d, img, n, i - w, i, inv, wu, a);
-    }
-    g -= wl * cx + wu * cy;
-    g_out[i] = g;  // d smooth / d(norm disp); the chain through the per-image mean is applied by k_combine
-    sgd += g * d[i];
-  }
-  sx = block_sum<kSmallNT>(sx, scratch);
-  sy = block_sum<kSmallNT>(sy, scratch);
-  sgd = block_sum<kSmallNT>(sgd, scratch);
-  if (threadIdx.x == 0) {
-    float* o = p.smooth_part + ((size_t)(s * p.B + b) * p.chunks0 + chunk) * 3;
-    o[0] = sx; o[1] = sy; o[2] = sgd;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -240,6 +135,17 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
     stage_wait<1>();                         // this scale's disp window (committed one scale earlier)
     __syncthreads();
     phase_warp<C>(p, g, t, sm, s, tid);
+    {
+      // smoothness of this level on the tile's own level pixels (reads the staged disp window before it is
+      // replaced); per-warp sums parked in shared memory until the scale's block reduction
+      float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+      phase_smooth<C>(p, t, sm, s, tid, sacc);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float tot = warp_sum(sacc[k]);
+        if ((tid & 31) == 0) sm[C::oRedS + (tid >> 5) * 4 + k] = tot;
+      }
+    }
     stage_wait<0>();
     __syncthreads();
     if (s + 1 < p.S) phase_stage_disp<C>(p, t, sm, s + 1, tid);  // the adjoint reads the saved depth, not disp
@@ -262,11 +168,12 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
       if (k0 + l < C::kPartial) red[w * C::kPartial + k0 + l] = tot;
     }
     __syncthreads();
-    if (tid < C::kPartial) {
+    if (tid < C::kPartialAll) {
       float r = 0.f;
 #pragma unroll
-      for (int i = 0; i < C::NT / 32; ++i) r += red[i * C::kPartial + tid];
-      p.partials[((size_t)t.cta * p.S + s) * C::kPartial + tid] = r;
+      for (int i = 0; i < C::NT / 32; ++i)
+        r += tid < C::kPartial ? red[i * C::kPartial + tid] : sm[C::oRedS + i * 4 + (tid - C::kPartial)];
+      p.partials[((size_t)t.cta * p.S + s) * C::kPartialAll + tid] = r;
     }
     if (!p.identity_scale[s]) {  // block-uniform; the tile's d/d(up-sampled disp) is complete (sync above)
       phase_adjoint_rows<C>(p, t, sm, s, tid);
@@ -278,7 +185,6 @@ __global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
-  __shared__ float scratch[kSmallNT / 32];
   __shared__ bool is_last;
   int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   int h = p.hs[s], w = p.ws[s], n = h * w;
@@ -293,28 +199,14 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
       gp[i] = gather_adjoint_partials(p.gpart[s], b, i / w, i % w, r, p.tw, p.th, p.tiles_x, p.tiles_y);
   }
   if (chunk == 0) {
-    // per (scale, image): smoothness normalisation for the backward, photometric partials, smoothness sums
-    float inv = 1.0f / (image_mean(p, s, b, scratch) + 1e-7f);
-    float gd = 0.f, sx = 0.f, sy = 0.f;
-    for (int i = threadIdx.x; i < nchunk; i += kSmallNT) {
-      const float* sp = p.smooth_part + ((size_t)(s * p.B + b) * p.chunks0 + i) * 3;
-      sx += sp[0]; sy += sp[1]; gd += sp[2];
-    }
-    gd = block_sum<kSmallNT>(gd, scratch);
-    sx = block_sum<kSmallNT>(sx, scratch);
-    sy = block_sum<kSmallNT>(sy, scratch);
-    if (threadIdx.x == 0) {
-      p.norm[(s * p.B + b) * 2] = inv;
-      p.norm[(s * p.B + b) * 2 + 1] = gd * inv * inv / (float)n;
-      p.smoothb[(s * p.B + b) * 2] = sx;
-      p.smoothb[(s * p.B + b) * 2 + 1] = sy;
-    }
-    // photometric partials (loss sum, dL/dP) of image b at scale s: 8 lane-groups each add every 8th tile
-    // (independent loads, so they pipeline), then the 8 group sums are added in a fixed order
+    // per (scale, image): the tiles' partials (loss sum, dL/dP, smoothness sums) in fp64, tile order fixed:
+    // 8 lane-groups each add every 8th tile (independent loads, so they pipeline), then the 8 group sums
     __shared__ double gsum[kSmallNT / 32][40];
+    __shared__ double ssum[4];
     const float* base = p.partials + ((size_t)b * p.tiles_per_image * p.S + s) * p.kpartial;
     const int grp = threadIdx.x >> 5, k = threadIdx.x & 31;
-    for (int k0 = 0; k0 < p.kpartial; k0 += 32) {  // kpartial = 1 + 12 F <= 37
+    const int kphoto = p.kpartial - 4;  // 1 + 12 F photometric values, then sum d, sum |dx| e, sum |dy| e, sum g d
+    for (int k0 = 0; k0 < p.kpartial; k0 += 32) {  // kpartial <= 41
       double acc = 0.0;
       if (k0 + k < p.kpartial)
         for (int tl = grp; tl < p.tiles_per_image; tl += kSmallNT / 32)
@@ -328,11 +220,25 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
         for (int gi = 0; gi < kSmallNT / 32; ++gi) tot += gsum[gi][k];
         const int kk = k0 + k;
         if (kk == 0) p.lossb[s * p.B + b] = (float)tot;
-        else {
+        else if (kk < kphoto) {
           int f = (kk - 1) / 12, e = (kk - 1) % 12;
           p.gradP[((size_t)(s * p.F + f) * p.B + b) * 12 + e] = (float)tot;
+        } else {
+          ssum[kk - kphoto] = tot;
         }
       }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // norm = disp * inv, inv = 1 / (mean + 1e-7) (trainer.py:676-677); the tiles summed |d_a - d_b| e and
+      // g for inv > 0, so |inv| scales the sums and sgn(inv) the gradient (k_combine: g * norm[0] - norm[1])
+      const float mean = (float)(ssum[0] / (double)n);
+      const float inv = 1.0f / (mean + 1e-7f);
+      const float ainv = fabsf(inv);
+      p.norm[(s * p.B + b) * 2] = ainv;
+      p.norm[(s * p.B + b) * 2 + 1] = (inv < 0.f ? -1.f : 1.f) * (float)ssum[3] * inv * inv / (float)n;
+      p.smoothb[(s * p.B + b) * 2] = (float)(ssum[1] * (double)ainv);
+      p.smoothb[(s * p.B + b) * 2 + 1] = (float)(ssum[2] * (double)ainv);
     }
   }
   // last block done: assemble the loss dict (trainer.py:672-685)
@@ -508,7 +414,7 @@ static GeoConst make_geo(const VslDesc* d) {
 
 struct Plan {  // sizes derived from the descriptor; identical in workspace_bytes() and the launcher
   int tw, th, tiles_x, tiles_y, num_cta, kpartial, chunks0;
-  size_t off_partials, off_gpart[kMaxScales], off_mean, off_smooth, off_lossb, off_smoothb, off_counter, total;
+  size_t off_partials, off_gpart[kMaxScales], off_lossb, off_smoothb, off_counter, total;
 };
 
 static Plan make_plan(const VslDesc* d) {
@@ -518,7 +424,7 @@ static Plan make_plan(const VslDesc* d) {
   pl.tiles_x = (d->width + pl.tw - 1) / pl.tw;
   pl.tiles_y = (d->height + pl.th - 1) / pl.th;
   pl.num_cta = pl.tiles_x * pl.tiles_y * d->batch;
-  pl.kpartial = 1 + d->num_src * 12;
+  pl.kpartial = 1 + d->num_src * 12 + 4;  // TileCfg::kPartialAll
   pl.chunks0 = (d->height * d->width + kChunk - 1) / kChunk;
   size_t off = 0;
   auto take = [&](size_t floats) { size_t o = off; off += (floats + 63) / 64 * 64; return o; };
@@ -527,8 +433,6 @@ static Plan make_plan(const VslDesc* d) {
     int r = 1 << d->scale_ids[s];
     pl.off_gpart[s] = r == 1 ? 0 : take((size_t)pl.num_cta * (pl.tw / r + 2) * (pl.th / r + 2));
   }
-  pl.off_mean = take((size_t)d->num_scales * d->batch * pl.chunks0);
-  pl.off_smooth = take((size_t)d->num_scales * d->batch * pl.chunks0 * 3);
   pl.off_lossb = take((size_t)d->num_scales * d->batch);
   pl.off_smoothb = take((size_t)d->num_scales * d->batch * 2);
   pl.off_counter = take(64);
@@ -667,6 +571,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     pp.scale_h[s] = sp.scale_h[s] = (float)hs / (float)d->height;
     pp.scale_w[s] = sp.scale_w[s] = (float)wsz / (float)d->width;
     pp.identity_scale[s] = sp.identity_scale[s] = (e == 0);
+    pp.level_shift[s] = e;
     pp.disp[s] = sp.disp[s] = buf->disp[s];
     pp.noise[s] = buf->noise[s];
     pp.mask[s] = automask ? buf->mask[s] : nullptr;
@@ -678,11 +583,11 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     sp.gpart[s] = pp.gpart[s];
     sp.img[s] = buf->target[s];
     sp.gsmooth[s] = buf->grad_disp_smooth[s];
+    pp.tgts[s] = buf->target[s];
+    pp.gsmooth[s] = buf->grad_disp_smooth[s];
     sp.gphoto[s] = buf->grad_disp_photo[s];
     sp.scale_id[s] = e + d->smooth_level_bias;
   }
-  sp.mean_part = ws + pl.off_mean;
-  sp.smooth_part = ws + pl.off_smooth;
   sp.partials = pp.partials;
   sp.lossb = ws + pl.off_lossb;
   sp.smoothb = ws + pl.off_smoothb;
@@ -697,12 +602,6 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   sp.smooth_weight = d->smooth_weight;
 
   VSL_CUDA_OK(cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), st));
-  dim3 sgrid(pl.chunks0, d->batch, S);
-  k_smooth_mean<<<sgrid, kSmallNT, 0, st>>>(sp);
-  VSL_CUDA_OK(cudaGetLastError());
-  if (d->image_dtype == VSL_DTYPE_BF16) k_smooth_terms<bf16_t><<<sgrid, kSmallNT, 0, st>>>(sp);
-  else k_smooth_terms<float><<<sgrid, kSmallNT, 0, st>>>(sp);
-  VSL_CUDA_OK(cudaGetLastError());
   if (event_before) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_before, st));
   int rc;
   if (pmask) {  // --predictive_mask kernels: run-time rounding selectors only (one instantiation each)

@@ -177,25 +177,36 @@ __global__ void __launch_bounds__(256) k_u8_to_tensor_x4(const uint8_t* __restri
 }
 
 // level s-1 (HWC uint8, hi x wi) -> level s (HWC uint8, hi/2 x wi/2) + CHW tensor.  One CTA: 32 x 8 outputs.
-constexpr int kTX = 32, kTY = 8, kRowsMax = 2 * kTY + kKsize + 1;
+// The input rows/columns the tile's taps touch are first copied to shared memory with coalesced byte loads
+// (each input byte is read once per CTA instead of ~5 times by overlapping taps), then the two passes run
+// out of shared memory.
+constexpr int kTX = 32, kTY = 8, kRowsMax = 2 * kTY + kKsize + 1, kColsMax = 2 * kTX + kKsize + 1;
 template <class Out>
 __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
                                                      Out* __restrict__ out_t, AxisTable tx, AxisTable ty, int hi, int wi) {
-  __shared__ uint8_t hrow[kRowsMax][kTX][3];  // horizontal pass of the input rows this tile's vertical taps touch
+  __shared__ uint8_t tin[kRowsMax][kColsMax * 3];  // input window of the tile
+  __shared__ uint8_t hrow[kRowsMax][kTX][3];       // its horizontal pass, rounded to 8 bits
   const int ho = hi >> 1, wo = wi >> 1;
   const int b = blockIdx.z, x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
-  const int ylast = min(y0 + kTY, ho) - 1;
+  const int ylast = min(y0 + kTY, ho) - 1, xlast = min(x0 + kTX, wo) - 1;
   const int row_lo = ty.bounds[2 * y0];
   const int row_hi = ty.bounds[2 * ylast] + ty.bounds[2 * ylast + 1];  // exclusive
-  const int nrows = row_hi - row_lo;                                    // <= kRowsMax (2 * 7 + 13)
-  const uint8_t* src = in + (size_t)b * hi * wi * 3;
+  const int nrows = row_hi - row_lo;                                    // <= 2 * 7 + 13
+  const int col_lo = tx.bounds[2 * x0];
+  const int ncolb = (tx.bounds[2 * xlast] + tx.bounds[2 * xlast + 1] - col_lo) * 3;  // bytes per row, <= (2 * 31 + 13) * 3
+  const uint8_t* src = in + ((size_t)b * hi + row_lo) * wi * 3 + (size_t)col_lo * 3;
+  for (int item = threadIdx.x; item < nrows * ncolb; item += 256) {
+    const int r = item / ncolb, c = item - r * ncolb;
+    tin[r][c] = src[(size_t)r * wi * 3 + c];
+  }
+  __syncthreads();
   for (int item = threadIdx.x; item < nrows * kTX; item += 256) {
     const int r = item / kTX, xx = item - r * kTX;
     const int xo = x0 + xx;
     if (xo >= wo) continue;
-    const int lo = tx.bounds[2 * xo], n = tx.bounds[2 * xo + 1];
+    const int lo = tx.bounds[2 * xo] - col_lo, n = tx.bounds[2 * xo + 1];
     const int32_t* k = tx.coefs + (size_t)xo * kKsize;
-    const uint8_t* q = src + ((size_t)(row_lo + r) * wi + lo) * 3;
+    const uint8_t* q = &tin[r][lo * 3];
     int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
     for (int j = 0; j < n; ++j) {
       const int w = k[j];

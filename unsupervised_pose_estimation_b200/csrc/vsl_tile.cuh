@@ -19,6 +19,8 @@ constexpr int kMaxSrc = 4;
 
 struct PhotoParams {
   const void* tgt;                // [B,3,H,W]  fp32 or bf16 (TileCfg::Img)
+  const void* tgts[kMaxScales];   // target pyramid inputs[("color", 0, s)] [B,3,hs,ws] (smoothness edge weights)
+  float* gsmooth[kMaxScales];     // [B,hs,ws] d smooth_s / d(norm disp_s), or null: smoothness not evaluated here
   const void* src[kMaxSrc];       // [B,3,H,W]
   const float* disp[kMaxScales];  // [B,1,hs,ws]
   const float* invK;              // [B,4,4]
@@ -38,6 +40,7 @@ struct PhotoParams {
   int hs[kMaxScales], ws[kMaxScales];
   float scale_h[kMaxScales], scale_w[kMaxScales];
   int identity_scale[kMaxScales];  // up-sample is the identity (level size == H x W)
+  int level_shift[kMaxScales];     // log2(W / ws[s]): levels are exact power-of-two reductions (checked by the ABI)
   GeoConst g;
   float wpix;                     // 1 / (B*H*W): weight of one pixel in min_loss/s
   int automask;                   // 0: --disable_automasking (no identity candidates, no noise, no mask)
@@ -50,6 +53,7 @@ struct TileCfg {
   typedef Img_ Img;  // storage type of the colour images
   static constexpr bool PMASK = PMASK_;  // --predictive_mask compiled in (costs ~2 % when merely present)
   static constexpr int TW = TW_, TH = TH_, F = F_, NT = NT_;
+  static constexpr int kLogTW = TW_ == 32 ? 5 : (TW_ == 16 ? 4 : (TW_ == 64 ? 6 : -1));
   // --avg_reprojection (trainer.py:629-630, 649-650): the frames' losses are averaged before the minimum,
   // so when the warped average wins EVERY frame receives gradient: one coefficient record per frame
   static constexpr bool AVG = AVG_;
@@ -75,9 +79,15 @@ struct TileCfg {
   static constexpr int DW = TW + 4, DH = TH + 4;  // window of disp_s under the region (clamped to the level)
   static constexpr int oDisp = oNz + NZC * WN;  // [DH][DW]
   static constexpr int oZ = oDisp + DW * DH;    // depth of the interior pixels at the current scale [IN]
-  static constexpr int kFloats = oZ + IN;
+  static constexpr int oRedS = oZ + IN;         // per-warp smoothness sums [NT/32][4]
+  // target pyramid pixels under the tile's own pixels of a level s >= 1, +1 halo (smoothness edge weights)
+  static constexpr int SW = TW / 2 + 2, SH = TH / 2 + 2, SN = SW * SH;
+  static constexpr bool kStageImg = sizeof(Img_) == 4;  // fp32 images only (bf16 needs a conversion: read directly)
+  static constexpr int oImgS = oRedS + (NT / 32) * 4;   // [3][SN]
+  static constexpr int kFloats = oImgS + (kStageImg ? 3 * SN : 0);
   static constexpr int kBytes = kFloats * 4;
-  static constexpr int kPartial = 1 + F * 12;
+  static constexpr int kPartial = 1 + F * 12;   // photometric partials per (CTA, scale): loss, dL/dP
+  static constexpr int kPartialAll = kPartial + 4;  // + smoothness: sum d, sum |dx| e, sum |dy| e, sum g d
   static_assert(oCoef % 4 == 0, "CoefRec needs 16-byte alignment");
 };
 
@@ -126,9 +136,9 @@ VSL_HD void phase_pose(const PhotoParams& p, const GeoConst& g, const TileCtx& t
 // with a non-zero weight by ups_tap, but they keep every tap index in range).  H and W are multiples of r.
 template <class C>
 VSL_HD void disp_window(const PhotoParams& p, const TileCtx& t, int s, int& cy0, int& cx0, int& rows, int& cols) {
-  const int r = p.W / p.ws[s];
-  cy0 = t.y0 / r - 2; cx0 = t.x0 / r - 2;
-  rows = C::TH / r + 4; cols = C::TW / r + 4;
+  const int e = p.level_shift[s];
+  cy0 = (t.y0 >> e) - 2; cx0 = (t.x0 >> e) - 2;
+  rows = (C::TH >> e) + 4; cols = (C::TW >> e) + 4;
 }
 template <class C>
 VSL_HD void phase_stage_disp(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
@@ -142,6 +152,21 @@ VSL_HD void phase_stage_disp(const PhotoParams& p, const TileCtx& t, float* __re
     yy = yy < 0 ? 0 : (yy > hs - 1 ? hs - 1 : yy);
     xx = xx < 0 ? 0 : (xx > ws - 1 ? ws - 1 : xx);
     stage4(sm + C::oDisp + ry * C::DW + rx, disp + yy * ws + xx);
+  }
+  if (C::kStageImg && p.gsmooth[s] && !p.identity_scale[s]) {
+    // target pyramid level s under the tile's own level pixels, +1 halo, for phase_smooth
+    const int e = p.level_shift[s];
+    const int oy = (t.y0 >> e) - 1, ox = (t.x0 >> e) - 1, nrow = (C::TH >> e) + 2, ncol = (C::TW >> e) + 2;
+    const float* img = (const float*)p.tgts[s] + (size_t)t.b * 3 * hs * ws;
+    for (int i = tid; i < nrow * ncol; i += C::NT) {
+      const int ry = i / ncol, rx = i - ry * ncol;
+      int yy = oy + ry, xx = ox + rx;
+      yy = yy < 0 ? 0 : (yy > hs - 1 ? hs - 1 : yy);
+      xx = xx < 0 ? 0 : (xx > ws - 1 ? ws - 1 : xx);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        stage4(sm + C::oImgS + c * C::SN + ry * C::SW + rx, img + (size_t)c * hs * ws + yy * ws + xx);
+    }
   }
   stage_commit();
 }
@@ -502,6 +527,77 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
 #pragma unroll
       for (int c = 0; c < 3; ++c) X[XL::single_base(c) + i] = val[C::F - 1][c];
     }
+  }
+}
+
+// ---- phase: edge-aware smoothness of disp_s on the CTA's own pixels of level s -----------------------
+// get_smooth_loss (layers.py:286-299) with the normalisation of trainer.py:676-677 factored out: the
+// per-image mean of disp_s is only known once every tile is done, and norm = disp * inv with
+// inv = 1 / (mean + 1e-7), so |norm_a - norm_b| = |inv| |d_a - d_b|.  The tile accumulates the un-normalised
+// sums; k_epilogue applies inv, k_combine the chain rule through the mean.  Per level pixel: the four
+// incident edges (the left / up ones are re-evaluated rather than exchanged between threads).
+//   acc[0] += d, acc[1] += |d - d_right| e, acc[2] += |d - d_down| e, acc[3] += g d
+//   g = d smooth / d norm (for inv > 0) = cx (w_right - w_left) + cy (w_down - w_up), w = sgn(delta) e
+VSL_HD float smooth_edge_weight(const float a[3], const float b[3]) {  // exp(-mean_c |img_a - img_b|), layers.py:293-297
+  float g = fabsf(a[0] - b[0]) + fabsf(a[1] - b[1]) + fabsf(a[2] - b[2]);
+  return expf(-g * (1.0f / 3.0f));
+}
+VSL_HD float sgn_of(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+template <class C>
+VSL_HD void phase_smooth(const PhotoParams& p, const TileCtx& t, const float* __restrict__ sm, int s, int tid,
+                         float (&acc)[4]) {
+  if (!p.gsmooth[s]) return;
+  static_assert((C::TW & (C::TW - 1)) == 0, "tile width must be a power of two");
+  const int e = p.level_shift[s];
+  const int cw = C::TW >> e, ch = C::TH >> e;  // the tile's own pixels at this level
+  const int hs = p.hs[s], ws = p.ws[s], n = hs * ws;
+  int cy0, cx0, rows, cols;
+  disp_window<C>(p, t, s, cy0, cx0, rows, cols);
+  const typename C::Img* img = (const typename C::Img*)p.tgts[s] + (size_t)t.b * 3 * n;
+  float* g_out = p.gsmooth[s] + (size_t)t.b * n;
+  const float cx = 1.0f / ((float)p.B * hs * (ws - 1)), cy = 1.0f / ((float)p.B * (hs - 1) * ws);
+  const bool from_tile = p.identity_scale[s] != 0;  // level 0: the target tile is in shared memory
+  const float* T = sm + C::oT;
+  for (int i = tid; i < cw * ch; i += C::NT) {
+    const int iy = i >> (C::kLogTW - e), ix = i & (cw - 1);  // cw is a power of two: the compiler cannot know, the mask helps
+    const int y = (t.y0 >> e) + iy, x = (t.x0 >> e) + ix;
+    if (y >= hs || x >= ws) continue;
+    const int o = y * ws + x;
+    const float* d = sm + C::oDisp + (y - cy0) * C::DW + (x - cx0);
+    auto pixel = [&](int dy, int dx, float v[3]) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        v[c] = from_tile ? T[c * C::RN + (iy + 2 + dy) * C::RW + (ix + 2 + dx)]
+               : C::kStageImg ? sm[C::oImgS + c * C::SN + (iy + 1 + dy) * C::SW + (ix + 1 + dx)]
+                              : ldimg(img, (size_t)c * n + o + dy * ws + dx);
+    };
+    float c0[3], cn[3];
+    pixel(0, 0, c0);
+    const float d0 = d[0];
+    float g = 0.f;
+    if (x + 1 < ws) {
+      pixel(0, 1, cn);
+      const float e = smooth_edge_weight(c0, cn), dl = d0 - d[1];
+      acc[1] += fabsf(dl) * e;
+      g += cx * sgn_of(dl) * e;
+    }
+    if (y + 1 < hs) {
+      pixel(1, 0, cn);
+      const float e = smooth_edge_weight(c0, cn), dl = d0 - d[C::DW];
+      acc[2] += fabsf(dl) * e;
+      g += cy * sgn_of(dl) * e;
+    }
+    if (x > 0) {
+      pixel(0, -1, cn);
+      g -= cx * sgn_of(d[-1] - d0) * smooth_edge_weight(cn, c0);
+    }
+    if (y > 0) {
+      pixel(-1, 0, cn);
+      g -= cy * sgn_of(d[-C::DW] - d0) * smooth_edge_weight(cn, c0);
+    }
+    g_out[o] = g;
+    acc[0] += d0;
+    acc[3] += g * d0;
   }
 }
 

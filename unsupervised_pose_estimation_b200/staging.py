@@ -6,6 +6,11 @@
 be pinned for the copies to overlap), ``take()`` makes the compute stream wait for the oldest submitted
 batch and returns its device tensors.  With one batch in flight the copies of step i+1 overlap the loss
 kernels of step i, so a step costs max(copy, compute) instead of their sum.
+
+``submit(host_batch, post=fn)`` also runs ``fn(device_batch)`` on the copy stream right behind the copies:
+the on-GPU input pipeline (``input_pipeline.LossInputPipeline``: 8-bit frames -> colour pyramid) goes there,
+so its small, latency-bound kernels run next to the previous step's loss kernels (the copy stream has the
+higher priority, its blocks take the first SM slots that free up) instead of in front of this step's.
 """
 from __future__ import annotations
 
@@ -18,7 +23,7 @@ class HostBatchStager:
     def __init__(self, device, depth=2):
         self.device = torch.device(device)
         self.depth = depth
-        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self.slots = [None] * depth
         self.ready = [torch.cuda.Event() for _ in range(depth)]
         self.free = [None] * depth      # recorded on the compute stream when a slot's consumer is done
@@ -29,8 +34,8 @@ class HostBatchStager:
     def _alloc_like(self, host_batch):
         return {k: torch.empty_like(v, device=self.device) for k, v in host_batch.items()}
 
-    def submit(self, host_batch):
-        """Enqueue the copies of one batch (dict of pinned CPU tensors)."""
+    def submit(self, host_batch, post=None):
+        """Enqueue the copies of one batch (dict of pinned CPU tensors), then ``post(device_batch)``."""
         if len(self.queue) >= self.depth:
             raise RuntimeError("all %d staging slots are in flight; call take() first" % self.depth)
         k = self.next_slot
@@ -43,6 +48,8 @@ class HostBatchStager:
                 self.copy_stream.wait_event(self.free[k])  # do not overwrite a slot still being read
             for key, v in host_batch.items():
                 dst[key].copy_(v, non_blocking=True)
+            if post is not None:
+                post(dst)
             self.ready[k].record(self.copy_stream)
         self.bytes_per_batch = sum(v.numel() * v.element_size() for v in host_batch.values())
         self.queue.append(k)
