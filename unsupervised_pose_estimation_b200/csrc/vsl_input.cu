@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict_
                                                      Out* __restrict__ out_t, AxisTable tx, AxisTable ty, int hi, int wi) {
   __shared__ uint8_t tin[kRowsMax][kColsMax * 3];  // input window of the tile
   __shared__ uint8_t hrow[kRowsMax][kTX][3];       // its horizontal pass, rounded to 8 bits
+  __shared__ int32_t kx[kTX][kKsize], ky[kTY][kKsize];  // the tile's coefficient rows (13 words: conflict-free)
+  __shared__ int bx[kTX][2], by[kTY][2];
   const int ho = hi >> 1, wo = wi >> 1;
   const int b = blockIdx.z, x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
   const int ylast = min(y0 + kTY, ho) - 1, xlast = min(x0 + kTX, wo) - 1;
@@ -195,17 +197,29 @@ __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict_
   const int col_lo = tx.bounds[2 * x0];
   const int ncolb = (tx.bounds[2 * xlast] + tx.bounds[2 * xlast + 1] - col_lo) * 3;  // bytes per row, <= (2 * 31 + 13) * 3
   const uint8_t* src = in + ((size_t)b * hi + row_lo) * wi * 3 + (size_t)col_lo * 3;
-  for (int item = threadIdx.x; item < nrows * ncolb; item += 256) {
-    const int r = item / ncolb, c = item - r * ncolb;
-    tin[r][c] = src[(size_t)r * wi * 3 + c];
+  for (int item = threadIdx.x; item < kTX * kKsize; item += 256) {
+    const int o = item / kKsize, j = item - o * kKsize;
+    kx[o][j] = x0 + o < wo ? tx.coefs[(size_t)(x0 + o) * kKsize + j] : 0;
+    if (o < kTY) ky[o][j] = y0 + o < ho ? ty.coefs[(size_t)(y0 + o) * kKsize + j] : 0;
+  }
+  if (threadIdx.x < kTX * 2) {
+    const int o = threadIdx.x >> 1, w = threadIdx.x & 1;
+    bx[o][w] = x0 + o < wo ? tx.bounds[2 * (x0 + o) + w] : 0;
+    if (o < kTY) by[o][w] = y0 + o < ho ? ty.bounds[2 * (y0 + o) + w] : 0;
+  }
+  if ((int)threadIdx.x < ncolb) {  // ncolb <= 225: one thread per byte column, independent loads down the rows
+    const uint8_t* q = src + threadIdx.x;
+    const size_t pitch = (size_t)wi * 3;
+#pragma unroll 5
+    for (int r = 0; r < nrows; ++r) tin[r][threadIdx.x] = q[r * pitch];
   }
   __syncthreads();
   for (int item = threadIdx.x; item < nrows * kTX; item += 256) {
     const int r = item / kTX, xx = item - r * kTX;
     const int xo = x0 + xx;
     if (xo >= wo) continue;
-    const int lo = tx.bounds[2 * xo] - col_lo, n = tx.bounds[2 * xo + 1];
-    const int32_t* k = tx.coefs + (size_t)xo * kKsize;
+    const int lo = bx[xx][0] - col_lo, n = bx[xx][1];
+    const int32_t* k = kx[xx];
     const uint8_t* q = &tin[r][lo * 3];
     int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
     for (int j = 0; j < n; ++j) {
@@ -218,8 +232,8 @@ __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict_
   const int xx = threadIdx.x & (kTX - 1), yy = threadIdx.x / kTX;
   const int xo = x0 + xx, yo = y0 + yy;
   if (xo >= wo || yo >= ho) return;
-  const int lo = ty.bounds[2 * yo] - row_lo, n = ty.bounds[2 * yo + 1];
-  const int32_t* k = ty.coefs + (size_t)yo * kKsize;
+  const int lo = by[yy][0] - row_lo, n = by[yy][1];
+  const int32_t* k = ky[yy];
   int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
   for (int j = 0; j < n; ++j) {
     const int w = k[j];

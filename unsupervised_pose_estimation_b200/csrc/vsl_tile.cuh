@@ -1015,25 +1015,32 @@ VSL_HD void adjoint_cols_r(const PhotoParams& p, const TileCtx& t, float* __rest
 }
 template <class C>
 VSL_HD void phase_adjoint_rows(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
-  const int r = p.W / p.ws[s];
+  const int r = 1 << p.level_shift[s];
   if (r == 2) adjoint_rows_r<C, 2>(p, t, sm, s, tid);
   else if (r == 4) adjoint_rows_r<C, 4>(p, t, sm, s, tid);
   else adjoint_rows_r<C, 8>(p, t, sm, s, tid);
 }
 template <class C>
 VSL_HD void phase_adjoint_cols(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int s, int tid) {
-  const int r = p.W / p.ws[s];
+  const int r = 1 << p.level_shift[s];
   if (r == 2) adjoint_cols_r<C, 2>(p, t, sm, s, tid);
   else if (r == 4) adjoint_cols_r<C, 4>(p, t, sm, s, tid);
   else adjoint_cols_r<C, 8>(p, t, sm, s, tid);
 }
 
+VSL_HD int ilog2(int v) {  // v a power of two
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
 // sum of the tile partials that touch coarse pixel (jy, jx) of image b; tiles in row-major order
 VSL_HD float gather_adjoint_partials(const float* __restrict__ gpart, int b, int jy, int jx, int r, int tw, int th,
                                      int tiles_x, int tiles_y) {
-  const int cw = tw / r, ch = th / r, ncx = cw + 2, ncy = ch + 2;
-  int ty_hi = (jy + 1) / ch, tx_hi = (jx + 1) / cw;
-  int ty_lo = jy - ch <= 0 ? 0 : (jy - ch + ch - 1) / ch, tx_lo = jx - cw <= 0 ? 0 : (jx - cw + cw - 1) / cw;
+  // tw, th and r are powers of two: the tile indices are shifts, not divisions
+  const int lr = ilog2(r), lcw = ilog2(tw) - lr, lch = ilog2(th) - lr;
+  const int cw = 1 << lcw, ch = 1 << lch, ncx = cw + 2, ncy = ch + 2;
+  int ty_hi = (jy + 1) >> lch, tx_hi = (jx + 1) >> lcw;
+  int ty_lo = jy - ch <= 0 ? 0 : (jy - 1) >> lch, tx_lo = jx - cw <= 0 ? 0 : (jx - 1) >> lcw;
   if (ty_hi >= tiles_y) ty_hi = tiles_y - 1;
   if (tx_hi >= tiles_x) tx_hi = tiles_x - 1;
   float acc = 0.f;
