@@ -487,8 +487,8 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "note": "bytes_min roofline as SURVEY.md 8d defines it; the fused kernel is instruction-issue bound "
-                                 "(~420 warp-instructions per target pixel, issue slots 59 % busy), not HBM bound: "
-                                 "see DESIGN.md section 4 and profiles/"},
+                                 "(~400 warp-instructions per target pixel, see roofline_issue), not HBM bound: "
+                                 "DESIGN.md section 4 and profiles/"},
             "clocks": clocks,
         }
         winst = getattr(profiled_traffic_bytes, "warp_instructions", None)

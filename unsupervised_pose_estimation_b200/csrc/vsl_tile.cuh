@@ -146,8 +146,10 @@ VSL_HD void phase_stage_disp(const PhotoParams& p, const TileCtx& t, float* __re
   disp_window<C>(p, t, s, cy0, cx0, rows, cols);
   const int hs = p.hs[s], ws = p.ws[s];
   const float* disp = p.disp[s] + (size_t)t.b * hs * ws;
-  for (int i = tid; i < rows * cols; i += C::NT) {
-    const int ry = i / cols, rx = i - ry * cols;
+  // 64 threads per row (cols <= TW + 4 <= 64): no division by the run-time window width
+  static_assert(C::DW <= 64 && C::NT % 64 == 0, "one row of the disp window per 64 threads");
+  for (int ry = tid >> 6, rx = tid & 63; ry < rows; ry += C::NT / 64) {
+    if (rx >= cols) continue;
     int yy = cy0 + ry, xx = cx0 + rx;
     yy = yy < 0 ? 0 : (yy > hs - 1 ? hs - 1 : yy);
     xx = xx < 0 ? 0 : (xx > ws - 1 ? ws - 1 : xx);
@@ -158,8 +160,9 @@ VSL_HD void phase_stage_disp(const PhotoParams& p, const TileCtx& t, float* __re
     const int e = p.level_shift[s];
     const int oy = (t.y0 >> e) - 1, ox = (t.x0 >> e) - 1, nrow = (C::TH >> e) + 2, ncol = (C::TW >> e) + 2;
     const float* img = (const float*)p.tgts[s] + (size_t)t.b * 3 * hs * ws;
-    for (int i = tid; i < nrow * ncol; i += C::NT) {
-      const int ry = i / ncol, rx = i - ry * ncol;
+    static_assert(C::SW <= 32, "one row of the image window per warp");
+    for (int ry = tid >> 5, rx = tid & 31; ry < nrow; ry += C::NT / 32) {
+      if (rx >= ncol) continue;
       int yy = oy + ry, xx = ox + rx;
       yy = yy < 0 ? 0 : (yy > hs - 1 ? hs - 1 : yy);
       xx = xx < 0 ? 0 : (xx > ws - 1 ? ws - 1 : xx);
