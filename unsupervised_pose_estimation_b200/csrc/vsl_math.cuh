@@ -28,7 +28,13 @@ VSL_HD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 VSL_HD float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 VSL_HD float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 VSL_HD float rcp_rn(float a) { return __frcp_rn(a); }
-VSL_HD float fast_rcp(float a) { return __frcp_rn(a); }
+// gradients only (never on the bit-exact forward chain): MUFU.RCP without the IEEE fix-up and its slow-path
+// branch; <= 1 ulp, far inside the gradient tolerance
+VSL_HD float fast_rcp(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
 #else  // host build (tests/emul): compiled with -ffp-contract=off
 VSL_HD float mul_rn(float a, float b) { volatile float r = a * b; return r; }
 VSL_HD float add_rn(float a, float b) { volatile float r = a + b; return r; }
