@@ -177,66 +177,93 @@ __global__ void __launch_bounds__(256) k_u8_to_tensor_x4(const uint8_t* __restri
 }
 
 // level s-1 (HWC uint8, hi x wi) -> level s (HWC uint8, hi/2 x wi/2) + CHW tensor.  One CTA: 32 x 8 outputs.
-// The input rows/columns the tile's taps touch are first copied to shared memory with coalesced byte loads
-// (each input byte is read once per CTA instead of ~5 times by overlapping taps), then the two passes run
-// out of shared memory.
-constexpr int kTX = 32, kTY = 8, kRowsMax = 2 * kTY + kKsize + 1, kColsMax = 2 * kTX + kKsize + 1;
-template <class Out>
+// The input rows/columns the tile's taps touch are first copied to shared memory (32-bit loads when the rows
+// are word-aligned), then both passes run out of shared memory with the coefficient row of the thread's
+// output column / row held in registers and the 13 reserved taps fully unrolled (the table is zero beyond
+// the taps in use).  Optionally the CTA also writes the CHW tensor of ITS part of the input level
+// (out_in: the 64 x 16 input pixels under the tile), which saves the separate conversion launch.
+constexpr int kTX = 32, kTY = 8, kRowsMax = 2 * kTY + kKsize + 1, kRowBytes = (2 * kTX + kKsize + 6) * 3 / 4 * 4 + 4;
+template <class Out, bool kWords>
 __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
-                                                     Out* __restrict__ out_t, AxisTable tx, AxisTable ty, int hi, int wi) {
-  __shared__ uint8_t tin[kRowsMax][kColsMax * 3];  // input window of the tile
-  __shared__ uint8_t hrow[kRowsMax][kTX][3];       // its horizontal pass, rounded to 8 bits
-  __shared__ int32_t kx[kTX][kKsize], ky[kTY][kKsize];  // the tile's coefficient rows (13 words: conflict-free)
-  __shared__ int bx[kTX][2], by[kTY][2];
+                                                     Out* __restrict__ out_t, Out* __restrict__ out_in, AxisTable tx,
+                                                     AxisTable ty, int hi, int wi) {
+  __shared__ __align__(16) uint8_t tin[kRowsMax][kRowBytes];  // input window of the tile
+  __shared__ uint8_t hrow[kRowsMax][kTX][3];                  // its horizontal pass, rounded to 8 bits
+  __shared__ int32_t kx[kTX][kKsize], ky[kTY][kKsize];        // the tile's coefficient rows (13 words: conflict-free)
+  __shared__ int bx[kTX], by[kTY];                            // first tap of every output column / row
   const int ho = hi >> 1, wo = wi >> 1;
   const int b = blockIdx.z, x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
   const int ylast = min(y0 + kTY, ho) - 1, xlast = min(x0 + kTX, wo) - 1;
   const int row_lo = ty.bounds[2 * y0];
   const int row_hi = ty.bounds[2 * ylast] + ty.bounds[2 * ylast + 1];  // exclusive
   const int nrows = row_hi - row_lo;                                    // <= 2 * 7 + 13
-  const int col_lo = tx.bounds[2 * x0];
-  const int ncolb = (tx.bounds[2 * xlast] + tx.bounds[2 * xlast + 1] - col_lo) * 3;  // bytes per row, <= (2 * 31 + 13) * 3
-  const uint8_t* src = in + ((size_t)b * hi + row_lo) * wi * 3 + (size_t)col_lo * 3;
+  // first input column of the window; rounded down to a multiple of 4 pixels (12 bytes) for the word loads
+  const int col_lo = kWords ? (tx.bounds[2 * x0] & ~3) : tx.bounds[2 * x0];
+  const int ncolb = (tx.bounds[2 * xlast] + tx.bounds[2 * xlast + 1] - col_lo) * 3;  // bytes per row, <= (3 + 2 * 31 + 13) * 3
+  const size_t pitch = (size_t)wi * 3;
+  const uint8_t* src = in + ((size_t)b * hi + row_lo) * pitch + (size_t)col_lo * 3;
   for (int item = threadIdx.x; item < kTX * kKsize; item += 256) {
     const int o = item / kKsize, j = item - o * kKsize;
     kx[o][j] = x0 + o < wo ? tx.coefs[(size_t)(x0 + o) * kKsize + j] : 0;
     if (o < kTY) ky[o][j] = y0 + o < ho ? ty.coefs[(size_t)(y0 + o) * kKsize + j] : 0;
   }
-  if (threadIdx.x < kTX * 2) {
-    const int o = threadIdx.x >> 1, w = threadIdx.x & 1;
-    bx[o][w] = x0 + o < wo ? tx.bounds[2 * (x0 + o) + w] : 0;
-    if (o < kTY) by[o][w] = y0 + o < ho ? ty.bounds[2 * (y0 + o) + w] : 0;
+  if (threadIdx.x < kTX) {
+    const int o = threadIdx.x;
+    bx[o] = x0 + o < wo ? tx.bounds[2 * (x0 + o)] - col_lo : 0;
+    if (o < kTY) by[o] = y0 + o < ho ? ty.bounds[2 * (y0 + o)] - row_lo : 0;
   }
-  if ((int)threadIdx.x < ncolb) {  // ncolb <= 225: one thread per byte column, independent loads down the rows
+  if (kWords) {  // rows start on a word boundary (wi % 4 == 0; col_lo is a multiple of 4): <= 59 words per row
+    const int nw = (ncolb + 3) >> 2;  // the last word may reach up to 3 bytes past the taps: still inside the row
+    for (int r = threadIdx.x >> 6; r < nrows; r += 4) {
+      const int w = threadIdx.x & 63;
+      if (w < nw) reinterpret_cast<uint32_t*>(tin[r])[w] = reinterpret_cast<const uint32_t*>(src + r * pitch)[w];
+    }
+  } else if ((int)threadIdx.x < ncolb) {  // one thread per byte column, independent loads down the rows
     const uint8_t* q = src + threadIdx.x;
-    const size_t pitch = (size_t)wi * 3;
 #pragma unroll 5
     for (int r = 0; r < nrows; ++r) tin[r][threadIdx.x] = q[r * pitch];
   }
   __syncthreads();
-  for (int item = threadIdx.x; item < nrows * kTX; item += 256) {
-    const int r = item / kTX, xx = item - r * kTX;
-    const int xo = x0 + xx;
-    if (xo >= wo) continue;
-    const int lo = bx[xx][0] - col_lo, n = bx[xx][1];
-    const int32_t* k = kx[xx];
-    const uint8_t* q = &tin[r][lo * 3];
-    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-    for (int j = 0; j < n; ++j) {
-      const int w = k[j];
-      a0 += q[3 * j] * w; a1 += q[3 * j + 1] * w; a2 += q[3 * j + 2] * w;
+  {
+    const int xx = threadIdx.x & (kTX - 1);
+    if (x0 + xx < wo) {
+      int k[kKsize];
+#pragma unroll
+      for (int j = 0; j < kKsize; ++j) k[j] = kx[xx][j];
+      const int lo3 = bx[xx] * 3;
+      for (int r = threadIdx.x >> 5; r < nrows; r += 8) {
+        const uint8_t* q = &tin[r][lo3];
+        int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+#pragma unroll
+        for (int j = 0; j < kKsize; ++j) {
+          a0 += q[3 * j] * k[j]; a1 += q[3 * j + 1] * k[j]; a2 += q[3 * j + 2] * k[j];
+        }
+        hrow[r][xx][0] = clip8(a0); hrow[r][xx][1] = clip8(a1); hrow[r][xx][2] = clip8(a2);
+      }
     }
-    hrow[r][xx][0] = clip8(a0); hrow[r][xx][1] = clip8(a1); hrow[r][xx][2] = clip8(a2);
+  }
+  if (out_in) {  // CHW tensor of the input pixels under this tile (2 kTY rows x 2 kTX columns)
+    const size_t hwi = (size_t)hi * wi;
+    for (int item = threadIdx.x; item < 2 * kTY * 2 * kTX; item += 256) {
+      const int ry = item / (2 * kTX), rx = item - ry * (2 * kTX);
+      const int y = 2 * y0 + ry, x = 2 * x0 + rx;
+      if (y >= hi || x >= wi) continue;
+      const uint8_t* q = &tin[y - row_lo][(x - col_lo) * 3];
+      Out* dst = out_in + (size_t)b * 3 * hwi + (size_t)y * wi + x;
+      store_tensor<Out>(dst, 0, q[0]);
+      store_tensor<Out>(dst, hwi, q[1]);
+      store_tensor<Out>(dst, 2 * hwi, q[2]);
+    }
   }
   __syncthreads();
   const int xx = threadIdx.x & (kTX - 1), yy = threadIdx.x / kTX;
   const int xo = x0 + xx, yo = y0 + yy;
   if (xo >= wo || yo >= ho) return;
-  const int lo = by[yy][0] - row_lo, n = by[yy][1];
-  const int32_t* k = ky[yy];
+  const int lo = by[yy];
   int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-  for (int j = 0; j < n; ++j) {
-    const int w = k[j];
+#pragma unroll
+  for (int j = 0; j < kKsize; ++j) {
+    const int w = ky[yy][j];
     a0 += hrow[lo + j][xx][0] * w; a1 += hrow[lo + j][xx][1] * w; a2 += hrow[lo + j][xx][2] * w;
   }
   const uint8_t v0 = clip8(a0), v1 = clip8(a1), v2 = clip8(a2);
@@ -255,7 +282,9 @@ template <class Out>
 static int pyramid_forward_impl(const VslPyramidDesc* d, const PyramidPlan& pl, const uint8_t* frames,
                                 void* const levels[VSL_MAX_SCALES], uint8_t* ws, cudaStream_t st) {
   const size_t px0 = (size_t)d->batch * d->height * d->width;
-  if (levels[0]) {
+  // with more than one level the first 2:1 kernel also writes the level-0 tensor (its tiles cover level 0)
+  const bool fuse0 = levels[0] && d->num_levels > 1;
+  if (levels[0] && !fuse0) {
     const int hw = d->height * d->width;
     if (hw % 4 == 0 && ((uintptr_t)frames & 3u) == 0 && ((uintptr_t)levels[0] & 15u) == 0)
       k_u8_to_tensor_x4<Out><<<(unsigned)((px0 / 4 + 255) / 256), 256, 0, st>>>(frames, (Out*)levels[0], hw, px0 / 4);
@@ -269,8 +298,12 @@ static int pyramid_forward_impl(const VslPyramidDesc* d, const PyramidPlan& pl, 
     AxisTable tx = {(const int32_t*)(ws + pl.off_xb[s]), (const int32_t*)(ws + pl.off_xc[s])};
     AxisTable ty = {(const int32_t*)(ws + pl.off_yb[s]), (const int32_t*)(ws + pl.off_yc[s])};
     uint8_t* cur = ws + pl.off_u8[s];
+    Out* out_in = (s == 1 && fuse0) ? (Out*)levels[0] : nullptr;
     dim3 grid(((wi >> 1) + kTX - 1) / kTX, ((hi >> 1) + kTY - 1) / kTY, d->batch);
-    k_lanczos_half<Out><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], tx, ty, hi, wi);
+    if (wi % 4 == 0 && ((uintptr_t)prev & 3u) == 0)
+      k_lanczos_half<Out, true><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi);
+    else
+      k_lanczos_half<Out, false><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi);
     VSL_CUDA_OK_IN(cudaGetLastError());
     prev = cur;
   }
