@@ -469,7 +469,7 @@ def main():
     e2e_u8 = run_e2e("u8")
     e2e_u8.update({
         "host_buffers": "8-bit HWC level-0 frames + fp32 disp pyramid, poses, K/inv_K (pinned)",
-        "gpu_launches_per_step": 3 + (F + 1) + 3,
+        "gpu_launches_per_step": 3 + 3 + F,   # loss step (3) + target pyramid (3 LANCZOS levels; level 0 fused) + F source conversions
         "note": "pyramid (Pillow-exact LANCZOS) + ToTensor on the GPU, on the copy stream behind the H2D of the same "
                 "batch: both overlap the loss kernels of the previous step; loss dict read back every step",
         "numa_node_rank0": numa_node})

@@ -97,3 +97,64 @@ def test_loss_from_u8_frames_equals_loss_from_float_tensors():
     for a, b in zip(ga, gb):
         assert torch.equal(a, b)
     assert torch.equal(oa["identity_selection/0"], ob["identity_selection/0"])
+
+
+def test_host_batch_stager_with_pipeline_equals_direct_upload():
+    """The e2e loop of bench.py in miniature: pinned host batch -> HostBatchStager (copy stream) with the input
+    pipeline as its post hook -> loss step; twice through both slots, against a plain synchronous upload."""
+    from unsupervised_pose_estimation_b200 import layers as L
+    from unsupervised_pose_estimation_b200 import synthetic
+    from unsupervised_pose_estimation_b200.input_pipeline import LossInputPipeline
+    from unsupervised_pose_estimation_b200.staging import HostBatchStager
+    from unsupervised_pose_estimation_b200.trainer import LossPath, make_opt
+    B, H, W, frames = 2, 64, 96, [0, -1, 1]
+    opt = make_opt(height=H, width=W, batch_size=B, frame_ids=frames)
+    path = LossPath(opt, device="cuda", side_outputs="none")
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def host_batch(seed):
+        inputs, outputs, leaves = synthetic.make_batch(B, H, W, frames, seed=seed, family="smooth", device="cpu")
+        hb = {k: v for k, v in inputs.items() if isinstance(k, tuple) and k[0] in ("K", "inv_K") and k[1] == 0}
+        for f in frames:
+            hb[("color_u8", f)] = (inputs[("color", f, 0)].permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous()
+        for s in range(4):
+            hb[("disp", s)] = outputs[("disp", s)].detach()
+        for f in frames[1:]:
+            hb[("cam_T_cam", 0, f)] = L.transformation_from_parameters(
+                leaves[("axisangle", 0, f)][:, 0], leaves[("translation", 0, f)][:, 0], f < 0).detach()
+        return {k: v.pin_memory() for k, v in hb.items()}
+
+    def step(devb, inputs):
+        outputs = {k: v for k, v in devb.items() if k[0] in ("disp", "cam_T_cam")}
+        path.generate_images_pred(inputs, outputs)
+        torch.manual_seed(5)
+        losses = path.compute_losses(inputs, outputs)
+        return torch.stack([losses[k] for k in sorted(losses)]).cpu(), outputs["identity_selection/0"].cpu()
+
+    stager = HostBatchStager(dev, depth=2)
+    pipes, slot_inputs = {}, {}
+
+    def post(devb):
+        key = id(devb)
+        if key not in pipes:
+            pipes[key] = LossInputPipeline(opt, dev)
+            slot_inputs[key] = {k: v for k, v in devb.items() if k[0] in ("K", "inv_K")}
+        pipes[key]({k[1]: v for k, v in devb.items() if k[0] == "color_u8"}, slot_inputs[key])
+
+    batches = [host_batch(s) for s in range(3)]
+    got = []
+    stager.submit(batches[0], post)
+    for i in range(3):
+        if i + 1 < 3:
+            stager.submit(batches[i + 1], post)
+        devb = stager.take()
+        got.append(step(devb, slot_inputs[id(devb)]))
+        stager.release()
+    assert len(pipes) == 2   # two slots, re-used
+    direct_pipe = LossInputPipeline(opt, dev)
+    for i in range(3):
+        devb = {k: v.to(dev) for k, v in batches[i].items()}
+        inputs = {k: v for k, v in devb.items() if k[0] in ("K", "inv_K")}
+        direct_pipe({k[1]: v for k, v in devb.items() if k[0] == "color_u8"}, inputs)
+        want = step(devb, inputs)
+        assert torch.equal(got[i][0], want[0]) and torch.equal(got[i][1], want[1]), i

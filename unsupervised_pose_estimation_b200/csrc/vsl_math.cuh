@@ -31,9 +31,13 @@ VSL_HD float rcp_rn(float a) { return __frcp_rn(a); }
 // gradients only (never on the bit-exact forward chain): MUFU.RCP without the IEEE fix-up and its slow-path
 // branch; <= 1 ulp, far inside the gradient tolerance
 VSL_HD float fast_rcp(float a) {
+#if defined(VSL_EXACT_RCP)  // build knob for accuracy comparisons (tools/stress_parity.py)
+  return __frcp_rn(a);
+#else
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
   return r;
+#endif
 }
 #else  // host build (tests/emul): compiled with -ffp-contract=off
 VSL_HD float mul_rn(float a, float b) { volatile float r = a * b; return r; }
