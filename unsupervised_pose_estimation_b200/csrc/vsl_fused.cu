@@ -9,6 +9,7 @@
 //   k_combine       smoothness chain rule through the per-image mean + upstream weights
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/vsl.h"
 #include "vsl_tile.cuh"
@@ -84,7 +85,7 @@ __device__ __forceinline__ float warp_sum32(float (&v)[32], int lane) {
 // kFastArith: the rounding-order selectors are the compile-time default (arith == 0, PyTorch-CUDA order
 // for batch >= 2), so every variant branch in vsl_math.cuh folds away.
 template <class C, bool kFastArith>
-__global__ void __launch_bounds__(C::NT, 2) k_photometric(const PhotoParams p) {
+__global__ void __launch_bounds__(C::NT, C::NT >= 512 ? 1 : 2) k_photometric(const PhotoParams p) {
   extern __shared__ __align__(16) float sm[];
   GeoConst g = p.g;
   if (kFastArith) g.arith = 0;
@@ -417,10 +418,18 @@ struct Plan {  // sizes derived from the descriptor; identical in workspace_byte
   size_t off_partials, off_gpart[kMaxScales], off_lossb, off_smoothb, off_counter, total;
 };
 
-static Plan make_plan(const VslDesc* d) {
+// Tile height of the kernel variant that will run.  Two source frames: 32x16 tiles, 256 threads, two CTAs per
+// SM.  Three: the 32x16 tile needs 143 KB, so either one 512-thread CTA per SM on 32x16 (the default fp32 /
+// bf16 kernels: 11 % faster than 32x8, whose halo overhead is 1.69x / 1.33x instead of 1.41x / 1.20x) or, for
+// the rarely used --avg_reprojection / --predictive_mask kernels, 32x8 tiles with 256 threads.
+static int tile_height(const VslDesc* d, bool avg, bool pmask) {
+  return (d->num_src >= 3 && (avg || pmask)) ? 8 : 16;
+}
+
+static Plan make_plan(const VslDesc* d, int th) {
   Plan pl;
   pl.tw = 32;
-  pl.th = d->num_src >= 3 ? 8 : 16;  // three source frames: a 32x8 tile keeps two CTAs per SM (127 KB -> 71 KB)
+  pl.th = th;
   pl.tiles_x = (d->width + pl.tw - 1) / pl.tw;
   pl.tiles_y = (d->height + pl.th - 1) / pl.th;
   pl.num_cta = pl.tiles_x * pl.tiles_y * d->batch;
@@ -484,7 +493,13 @@ int vsl_last_cuda_error(void) { return g_last_cuda_error; }
 
 size_t vsl_loss_workspace_bytes(const VslDesc* desc) {
   if (!desc_ok(desc)) return 0;
-  return make_plan(desc).total;
+  // the variant (hence the tile height) depends on buffers the caller passes later: size for either
+  size_t best = 0;
+  for (int th : {8, 16}) {
+    const size_t t = make_plan(desc, th).total;
+    if (t > best) best = t;
+  }
+  return best;
 }
 
 int vsl_loss_forward_backward(const VslDesc* d, const VslLossBuffers* buf, void* workspace, size_t workspace_bytes,
@@ -522,8 +537,10 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   if (d->num_src > 3) return VSL_ERR_UNSUPPORTED;
   const bool automask = (d->flags & VSL_FLAG_AUTOMASK) != 0;
   const int S = d->num_scales, F = d->num_src;
-  Plan pl = make_plan(d);
-  if (workspace_bytes < pl.total) return VSL_ERR_WORKSPACE;
+  bool pmask = false;
+  for (int s = 0; s < d->num_scales; ++s) pmask |= !automask && buf && buf->predictive_mask[s] != nullptr;
+  Plan pl = make_plan(d, tile_height(d, avg, pmask));
+  if (workspace_bytes < vsl_loss_workspace_bytes(d)) return VSL_ERR_WORKSPACE;
   if (((uintptr_t)workspace & 15u) != 0) return VSL_ERR_MISALIGNED;
   if (!buf->inv_K || !buf->losses || !buf->grad_P || !buf->smooth_norm) return VSL_ERR_NULL_POINTER;
   for (int s = 0; s < S; ++s)
@@ -550,8 +567,6 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   pp.pose_per_scale = 0;
   for (int s = 0; s < S; ++s)
     for (int f = 0; f < F; ++f) pp.pose_per_scale |= buf->T_scale[s][f] != nullptr;
-  bool pmask = false;
-  for (int s = 0; s < S; ++s) pmask |= !automask && buf->predictive_mask[s] != nullptr;
   if (pmask && d->image_dtype != VSL_DTYPE_F32) return VSL_ERR_UNSUPPORTED;  // predictive mask + bf16 storage: not instantiated
   pp.no_ssim = (d->flags & VSL_FLAG_NO_SSIM) ? 1 : 0;
   pp.invK = buf->inv_K;
@@ -616,11 +631,11 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   } else if (d->image_dtype == VSL_DTYPE_BF16) {
     if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256, bf16_t>>(pp, pl, d->batch, st);
     else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, bf16_t>>(pp, pl, d->batch, st);
-    else rc = launch_photometric<TileCfg<32, 8, 3, 256, bf16_t>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, 16, 3, 512, bf16_t>>(pp, pl, d->batch, st);
   } else {
     if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256>>(pp, pl, d->batch, st);
     else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256>>(pp, pl, d->batch, st);
-    else rc = launch_photometric<TileCfg<32, 8, 3, 256>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, 16, 3, 512>>(pp, pl, d->batch, st);
   }
   if (rc != VSL_OK) return rc;
   if (event_after) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after, st));
