@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libvsl_b200.so")
 SOURCES = ["vsl_fused.cu", "vsl_layers.cu", "vsl_input.cu"]
 HEADERS = ["vsl_math.cuh", "vsl_tile.cuh", os.path.join("..", "..", "include", "vsl.h")]
 NVCC_FLAGS = [
-    "-std=c++17", "-O3", "-lineinfo",
+    "-std=c++17", "-O3", "-lineinfo", "--threads", "4",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
 ]

@@ -451,11 +451,14 @@ static Plan make_plan(const VslDesc* d, int th) {
 
 template <class C, bool kFastArith>
 static int launch_photometric_impl(const PhotoParams& pp, const Plan& pl, int batch, cudaStream_t st) {
-  static bool attr_done = false;  // idempotent; a race only repeats the call
-  if (!attr_done) {
+  // the attribute is per device: remember which devices have it (idempotent; a race only repeats the call)
+  static bool attr_done[64] = {};
+  int dev = 0;
+  VSL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     VSL_CUDA_OK(cudaFuncSetAttribute(k_photometric<C, kFastArith>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::kBytes));
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   dim3 grid(pl.tiles_x, pl.tiles_y, batch);
   k_photometric<C, kFastArith><<<grid, C::NT, C::kBytes, st>>>(pp);
