@@ -38,6 +38,7 @@ struct SmallParams {  // smoothness + epilogue
   const float* gpart[kMaxScales]; // per-CTA partial up-sample adjoints (null for identity scales)
   float* norm;                    // [S][B][2]: 1/(mean disp + 1e-7), sum(g*d) * inv^2 / n   (for k_combine)
   int tw, th, tiles_x, tiles_y;
+  int log_tw, log_th, level_shift[kMaxScales];
   const float* partials;          // photometric partials [numCTA][S][kPartial]
   float* lossb;                   // [S][B]
   float* smoothb;                 // [S][B][2]
@@ -195,9 +196,16 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
   if (!p.identity_scale[s]) {
     // d(min_loss/s)/d disp_s: add the (<= 4) tile partials of every coarse pixel, tiles in a fixed order
     float* gp = p.gphoto[s] + (size_t)b * n;
-    const int r = p.W / w;
-    for (int i = chunk * kChunk + threadIdx.x; i < min(n, (chunk + 1) * kChunk); i += kSmallNT)
-      gp[i] = gather_adjoint_partials(p.gpart[s], b, i / w, i % w, r, p.tw, p.th, p.tiles_x, p.tiles_y);
+    const int lcw = p.log_tw - p.level_shift[s], lch = p.log_th - p.level_shift[s];
+    // one division per thread instead of two per pixel: the pixels of a thread are kSmallNT apart
+    int i = chunk * kChunk + threadIdx.x;
+    int jy = i / w, jx = i - jy * w;
+    const int dy = kSmallNT / w, dx = kSmallNT - dy * w;
+    for (; i < min(n, (chunk + 1) * kChunk); i += kSmallNT) {
+      gp[i] = gather_adjoint_partials(p.gpart[s], b, jy, jx, lcw, lch, p.tiles_x, p.tiles_y);
+      jy += dy; jx += dx;
+      if (jx >= w) { jx -= w; ++jy; }
+    }
   }
   if (chunk == 0) {
     // per (scale, image): the tiles' partials (loss sum, dL/dP, smoothness sums) in fp64, tile order fixed:
@@ -209,9 +217,21 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
     const int kphoto = p.kpartial - 4;  // 1 + 12 F photometric values, then sum d, sum |dx| e, sum |dy| e, sum g d
     for (int k0 = 0; k0 < p.kpartial; k0 += 32) {  // kpartial <= 41
       double acc = 0.0;
-      if (k0 + k < p.kpartial)
-        for (int tl = grp; tl < p.tiles_per_image; tl += kSmallNT / 32)
-          acc += (double)base[(size_t)tl * p.S * p.kpartial + k0 + k];
+      if (k0 + k < p.kpartial) {
+        // same order of additions as a plain loop over this group's tiles; the loads of eight tiles are issued
+        // together (left to itself the loop waited out one L2 round trip per tile: 30 in a row at config 1)
+        constexpr int kU = 8, kG = kSmallNT / 32;
+        for (int tl = grp; tl < p.tiles_per_image; tl += kG * kU) {
+          float v[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const int ti = tl + kG * u;
+            v[u] = ti < p.tiles_per_image ? __ldcg(base + (size_t)ti * p.S * p.kpartial + k0 + k) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) acc += (double)v[u];
+        }
+      }
       __syncthreads();
       gsum[grp][k] = acc;
       __syncthreads();
@@ -589,7 +609,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     pp.scale_h[s] = sp.scale_h[s] = (float)hs / (float)d->height;
     pp.scale_w[s] = sp.scale_w[s] = (float)wsz / (float)d->width;
     pp.identity_scale[s] = sp.identity_scale[s] = (e == 0);
-    pp.level_shift[s] = e;
+    pp.level_shift[s] = sp.level_shift[s] = e;
     pp.disp[s] = sp.disp[s] = buf->disp[s];
     pp.noise[s] = buf->noise[s];
     pp.mask[s] = automask ? buf->mask[s] : nullptr;
@@ -612,6 +632,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   sp.gradP = buf->grad_P;
   sp.norm = buf->smooth_norm;
   sp.tw = pl.tw; sp.th = pl.th; sp.tiles_x = pl.tiles_x; sp.tiles_y = pl.tiles_y;
+  sp.log_tw = ilog2(pl.tw); sp.log_th = ilog2(pl.th);
   sp.losses = buf->losses;
   sp.counter = (unsigned*)(ws + pl.off_counter);
   sp.chunks0 = pl.chunks0;

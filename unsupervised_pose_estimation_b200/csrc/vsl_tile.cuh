@@ -1037,10 +1037,9 @@ VSL_HD int ilog2(int v) {  // v a power of two
   return l;
 }
 // sum of the tile partials that touch coarse pixel (jy, jx) of image b; tiles in row-major order
-VSL_HD float gather_adjoint_partials(const float* __restrict__ gpart, int b, int jy, int jx, int r, int tw, int th,
+// lcw, lch: log2 of the tile's width / height in pixels of this level (tile and ratio are powers of two)
+VSL_HD float gather_adjoint_partials(const float* __restrict__ gpart, int b, int jy, int jx, int lcw, int lch,
                                      int tiles_x, int tiles_y) {
-  // tw, th and r are powers of two: the tile indices are shifts, not divisions
-  const int lr = ilog2(r), lcw = ilog2(tw) - lr, lch = ilog2(th) - lr;
   const int cw = 1 << lcw, ch = 1 << lch, ncx = cw + 2, ncy = ch + 2;
   int ty_hi = (jy + 1) >> lch, tx_hi = (jx + 1) >> lcw;
   int ty_lo = jy - ch <= 0 ? 0 : (jy - 1) >> lch, tx_lo = jx - cw <= 0 ? 0 : (jx - 1) >> lcw;
