@@ -322,14 +322,15 @@ struct CombineParams {
   const float* K;      // [B,4,4]
   const float* norm;   // [S][B][2]
   int B, S, F, chunks0;
-  int n[kMaxScales], scale_id[kMaxScales];
+  int n[kMaxScales], scale_id[kMaxScales], vec4[kMaxScales];
   float smooth_weight;
 };
+constexpr int kCombineChunk = 4 * kChunk;  // elements per k_combine block
 
 __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
   int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   float tot = p.up[2 * p.S] / (float)p.S;
-  if (chunk * kChunk < p.n[s]) {
+  if (chunk * kCombineChunk < p.n[s]) {
     float a = p.up[s] + p.up[p.S + s] + tot;
     float bb = (p.up[p.S + s] + tot) * p.smooth_weight / (float)(1 << p.scale_id[s]);
     const float* gp = p.gphoto[s] + (size_t)b * p.n[s];
@@ -337,8 +338,16 @@ __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
     float* o = p.out[s] + (size_t)b * p.n[s];
     // d smooth_s/d disp = g * inv - sum(g d) inv^2 / n  (chain through norm_disp = disp / (mean + 1e-7), trainer.py:676-677)
     const float inv = p.norm[(s * p.B + b) * 2], corr = p.norm[(s * p.B + b) * 2 + 1];
-    for (int i = chunk * kChunk + threadIdx.x; i < min(p.n[s], (chunk + 1) * kChunk); i += kSmallNT)
-      o[i] = a * gp[i] + bb * (gs[i] * inv - corr);
+    const int i0 = chunk * kCombineChunk, i1 = min(p.n[s], i0 + kCombineChunk);
+    if (p.vec4[s]) {  // level size and the three buffers 16-byte aligned: four elements per access
+      for (int i = i0 + 4 * threadIdx.x; i < i1; i += 4 * kSmallNT) {
+        const float4 g1 = *reinterpret_cast<const float4*>(gp + i), g2 = *reinterpret_cast<const float4*>(gs + i);
+        *reinterpret_cast<float4*>(o + i) = make_float4(a * g1.x + bb * (g2.x * inv - corr), a * g1.y + bb * (g2.y * inv - corr),
+                                                        a * g1.z + bb * (g2.z * inv - corr), a * g1.w + bb * (g2.w * inv - corr));
+      }
+    } else {
+      for (int i = i0 + threadIdx.x; i < i1; i += kSmallNT) o[i] = a * gp[i] + bb * (gs[i] * inv - corr);
+    }
   }
   if (chunk == 0 && (s == 0 || p.pose_per_scale) && (p.gradP_out || p.gradT_out)) {
     // shared pose: sum the scales' dL/dP with their upstream weights; posecnn: one pose per scale, no sum
@@ -684,7 +693,7 @@ int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLos
   if (!upstream || !buf || !grad_disp) return VSL_ERR_NULL_POINTER;
   CombineParams cp = {};
   cp.up = upstream; cp.B = d->batch; cp.S = d->num_scales; cp.F = d->num_src;
-  cp.chunks0 = (d->height * d->width + kChunk - 1) / kChunk;
+  cp.chunks0 = (d->height * d->width + kCombineChunk - 1) / kCombineChunk;
   cp.smooth_weight = d->smooth_weight;
   cp.gradP = buf->grad_P; cp.gradP_out = grad_P_out; cp.gradT_out = grad_T_out; cp.K = buf->K;
   cp.pose_per_scale = 0;
@@ -700,6 +709,7 @@ int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLos
     cp.n[s] = (d->height >> e) * (d->width >> e);
     cp.scale_id[s] = e + d->smooth_level_bias;
     cp.gphoto[s] = buf->grad_disp_photo[s]; cp.gsmooth[s] = buf->grad_disp_smooth[s]; cp.out[s] = grad_disp[s];
+    cp.vec4[s] = cp.n[s] % 4 == 0 && (((uintptr_t)cp.gphoto[s] | (uintptr_t)cp.gsmooth[s] | (uintptr_t)cp.out[s]) & 15u) == 0;
   }
   if ((grad_P_out || grad_T_out) && !buf->grad_P) return VSL_ERR_NULL_POINTER;
   dim3 grid(cp.chunks0, d->batch, d->num_scales);
