@@ -516,3 +516,24 @@ def test_errors_are_loud():
     lib = _lib.load()
     d = _lib.VslDesc()
     assert lib.vsl_loss_forward_backward(ctypes.byref(d), None, None, 0, None) == -1
+
+
+@pytest.mark.parametrize("shape", [(2, 2, [0]), (4, 8, [0, 1]), (8, 40, [0, 1, 2]), (2, 34, [0]), (16, 16, [0, 1, 2, 3])])
+def test_images_smaller_than_a_tile(shape):
+    """Minimum sizes (a 2x2 image is the smallest the descriptor accepts; 2x2 also has H*W == 4, the inner size
+    of the K@T probe): sampling grid and auto-mask bit-exact, losses 2e-6, gradients 2e-4 rel-L2."""
+    H, W, scales = shape
+    for frames in ([0, -1, 1], [0, -1, 1, "s"]):
+        opt = O.make_opt(height=H, width=W, batch_size=2, frame_ids=list(frames), scales=scales)
+        inputs, outputs, leaves = synthetic.make_batch(2, H, W, frames, synthetic.K_KITTI, scales=tuple(scales),
+                                                       seed=H * W, family="iid", device=DEV)
+        ref_out, ref_losses, ref_g = run_oracle(opt, inputs, outputs, leaves, seed=1)
+        out, losses, g = run_ours(opt, inputs, outputs, leaves, seed=1, side="eager")
+        for k in ref_losses:
+            assert abs(losses[k].item() - ref_losses[k].item()) <= 2e-6 * abs(ref_losses[k].item()), (shape, frames, k)
+        for s in scales:
+            assert torch.equal(out["identity_selection/%d" % s], ref_out["identity_selection/%d" % s])
+            for f in frames[1:]:
+                assert torch.equal(out[("sample", f, s)], ref_out[("sample", f, s)])
+        for k in ref_g:
+            assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm().clamp_min(1e-30)).item() <= 2e-4, (shape, frames, k)

@@ -54,13 +54,12 @@ def calibrate_arith(batch, height, width, device):
     bits = 0
     # (k, columns, probe variants -> plan bits): rays [B,3,3]x[B,3,HW]; projection [B,3,4]x[B,4,HW];
     # P = (K@T)[:, :3, :], a [B,4,4]x[B,4,4] product (probed through its first three rows)
-    probes = ((3, n, {0: 0, _lib.ARITH_DOT3_NOFMA: _lib.ARITH_DOT3_NOFMA, _lib.ARITH_DOT3_REVERSE: _lib.ARITH_DOT3_REVERSE}),
-              (4, n, {0: 0, _lib.ARITH_DOT_NOFMA: _lib.ARITH_DOT_NOFMA, _lib.ARITH_DOT_REVERSE: _lib.ARITH_DOT_REVERSE}),
-              (4, 4, {0: 0, _lib.ARITH_DOT_NOFMA: _lib.ARITH_DOTKT_NOFMA, _lib.ARITH_DOT_REVERSE: _lib.ARITH_DOTKT_REVERSE}))
-    for k, n, variants in probes:
+    probes = ((3, n, False, {0: 0, _lib.ARITH_DOT3_NOFMA: _lib.ARITH_DOT3_NOFMA, _lib.ARITH_DOT3_REVERSE: _lib.ARITH_DOT3_REVERSE}),
+              (4, n, False, {0: 0, _lib.ARITH_DOT_NOFMA: _lib.ARITH_DOT_NOFMA, _lib.ARITH_DOT_REVERSE: _lib.ARITH_DOT_REVERSE}),
+              (4, 4, True, {0: 0, _lib.ARITH_DOT_NOFMA: _lib.ARITH_DOTKT_NOFMA, _lib.ARITH_DOT_REVERSE: _lib.ARITH_DOTKT_REVERSE}))
+    for k, n, full_kt, variants in probes:   # full_kt: the [B,4,4]x[B,4,4] product (a 2x2 image also has n == 4)
         X = torch.randn(batch, k, n, generator=gen).to(device)
         A = M[:, :3, :k]                       # sliced like inv_K[:, :3, :3] / (K@T)[:, :3, :]
-        full_kt = (n == 4)
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
