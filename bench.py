@@ -346,6 +346,36 @@ def main():
     ms_total = float(t.item())
     value = world * n0 * args.steps / (ms_total * 1e-3)
 
+    # ---- contract mode: the same step with every reference-visible side output materialised ---------
+    # (outputs[("depth",0,s)], ("sample",f,s), ("color",f,s): +192 B per target pixel), written by
+    # the fused kernel itself (vsl_side_outputs = "fused")
+    contract = None
+    if not args.no_graph:
+        wl.path.vsl_side_outputs = "fused"
+        cgraphs = [GraphedLossStep(wl.path, st["inputs"], st["leaves"]) for st in wl.sets[:2]]
+        wl.path.vsl_side_outputs = "none"
+        for i in range(4):
+            cgraphs[i % 2].replay()
+        barrier()
+        n_c = min(args.steps, 100)
+        e0.record()
+        for i in range(n_c):
+            cgraphs[i % 2].replay()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c_ms = float(t.item()) / n_c
+        contract = {"side_outputs": "fused (depth, sampling grids, warped colours of every scale and frame written "
+                                    "by k_photometric)", "value": world * n0 / (c_ms * 1e-3), "unit": UNIT,
+                    "ms_per_step": c_ms, "extra_bytes_per_step": n0 * (4 * 4 + 8 * 4 * F + 12 * 4 * F)}
+        # SURVEY.md 8d "contract-mode" bytes: bytes_min + side outputs + the four auto-masks, against the step time
+        c_bytes = algorithmic_bytes_per_pixel(F, 2 if args.bf16_images else 4) * n0 + contract["extra_bytes_per_step"] + 4 * 4 * n0
+        contract["contract_bytes_per_step"] = c_bytes
+        contract["hbm_frac_of_step"] = c_bytes / (c_ms * 1e-3) / 1e9 / peak_hbm_gbs()[0]
+        del cgraphs
+
     # ---- e2e: host buffers in, loss dict out ---------------------------------------------------
     # Per step: H2D of the step's inputs from pinned host memory (copy stream, into the staging slot the
     # step's graph reads), the step, D2H read of the loss dict.  The copies of step i+1 overlap step i.
@@ -508,6 +538,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, cfg),
+            "contract_mode": contract,
             "e2e": e2e_u8,
             "e2e_f32_host_tensors": e2e_f32,
             "gpu_launches": 3 * args.steps,

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VSL_ABI_VERSION 1
+#define VSL_ABI_VERSION 2
 #define VSL_MAX_SCALES 4
 #define VSL_MAX_SRC 4
 
@@ -132,6 +132,11 @@ typedef struct VslLossBuffers {
   float* smooth_norm;                   /* [S][B][2] per-image normalisation terms for the backward          */
   float* grad_P;                        /* d(min_loss/s)/d P_f  [S][F][B][12]                         */
   float* grad_predictive_mask[VSL_MAX_SCALES]; /* d(min_loss/s)/d predictive_mask[s] [B,F,H,W] (with it)    */
+  /* optional side outputs of Trainer.generate_images_pred (trainer.py:506, :532-537), written by the same
+   * kernel that forms them anyway; every pointer may be null.  fp32 whatever the image storage.            */
+  float* side_depth[VSL_MAX_SCALES];                /* outputs[("depth",0,s)]   [B,1,H,W]                    */
+  float* side_sample[VSL_MAX_SCALES][VSL_MAX_SRC];  /* outputs[("sample",f,s)]  [B,H,W,2]                    */
+  float* side_color[VSL_MAX_SCALES][VSL_MAX_SRC];   /* outputs[("color",f,s)]   [B,3,H,W]                    */
 } VslLossBuffers;
 
 size_t vsl_loss_workspace_bytes(const VslDesc* desc);

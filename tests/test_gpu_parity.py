@@ -537,3 +537,24 @@ def test_images_smaller_than_a_tile(shape):
                 assert torch.equal(out[("sample", f, s)], ref_out[("sample", f, s)])
         for k in ref_g:
             assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm().clamp_min(1e-30)).item() <= 2e-4, (shape, frames, k)
+
+
+@pytest.mark.parametrize("frames", [[0, -1, 1], [0, -1, 1, "s"], [0, "s"]])
+def test_fused_side_outputs_equal_eager(frames):
+    """vsl_side_outputs="fused": depth, sampling grid and warped colours written by k_photometric itself are the
+    same bits the separate k_warp_forward launches (mode "eager") produce, and the losses do not change."""
+    B, H, W = 2, 48, 112   # ragged: 112 = 3.5 tiles wide, 48 = 3 tiles high
+    opt = O.make_opt(height=H, width=W, batch_size=B, frame_ids=list(frames))
+    inputs, outputs, leaves = synthetic.make_batch(B, H, W, frames, synthetic.K_KITTI, seed=21, family="smooth", device=DEV)
+    out_e, losses_e, g_e = run_ours(opt, inputs, outputs, leaves, seed=3, side="eager")
+    out_f, losses_f, g_f = run_ours(opt, inputs, outputs, leaves, seed=3, side="fused")
+    for k in losses_e:
+        assert torch.equal(losses_e[k], losses_f[k]), k
+    for k in g_e:
+        assert torch.equal(g_e[k], g_f[k]), k
+    n = 0
+    for k, v in out_e.items():
+        if isinstance(k, tuple) and k[0] in ("depth", "sample", "color", "color_identity"):
+            assert k in out_f and torch.equal(out_f[k], v), k
+            n += 1
+    assert n == 4 * (1 + 3 * (len(frames) - 1))

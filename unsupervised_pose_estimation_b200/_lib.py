@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
 
-VSL_ABI_VERSION = 1
+VSL_ABI_VERSION = 2
 VSL_MAX_SCALES = 4
 VSL_MAX_SRC = 4
 
@@ -68,6 +68,8 @@ class VslLossBuffers(Structure):
         ("losses", c_void_p), ("mask", c_void_p * VSL_MAX_SCALES),
         ("grad_disp_photo", c_void_p * VSL_MAX_SCALES), ("grad_disp_smooth", c_void_p * VSL_MAX_SCALES),
         ("smooth_norm", c_void_p), ("grad_P", c_void_p), ("grad_predictive_mask", c_void_p * VSL_MAX_SCALES),
+        ("side_depth", c_void_p * VSL_MAX_SCALES), ("side_sample", (c_void_p * VSL_MAX_SRC) * VSL_MAX_SCALES),
+        ("side_color", (c_void_p * VSL_MAX_SRC) * VSL_MAX_SCALES),
     ]
 
 

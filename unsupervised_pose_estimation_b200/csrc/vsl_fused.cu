@@ -625,6 +625,13 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     pp.pmask[s] = automask ? nullptr : buf->predictive_mask[s];  // the reference only uses it without automasking
     pp.gpmask[s] = pp.pmask[s] ? buf->grad_predictive_mask[s] : nullptr;
     if (pp.pmask[s] && !pp.gpmask[s]) return VSL_ERR_NULL_POINTER;
+    pp.side_depth[s] = buf->side_depth[s];
+    pp.side_any |= buf->side_depth[s] != nullptr;
+    for (int f = 0; f < F; ++f) {
+      pp.side_sample[s][f] = buf->side_sample[s][f];
+      pp.side_color[s][f] = buf->side_color[s][f];
+      pp.side_any |= buf->side_sample[s][f] != nullptr || buf->side_color[s][f] != nullptr;
+    }
     pp.gD[s] = (e == 0) ? buf->grad_disp_photo[s] : nullptr;
     pp.gpart[s] = (e == 0) ? nullptr : ws + pl.off_gpart[s];
     sp.gpart[s] = pp.gpart[s];

@@ -36,6 +36,11 @@ struct PhotoParams {
   float* gD[kMaxScales];          // identity levels: [B,H,W] d(min_loss/s)/d disp_s, written directly
   float* gpart[kMaxScales];       // other levels: per-CTA partial up-sample adjoints [numCTA][ncy][ncx]
   float* partials;                // [numCTA][S][1 + F*12]
+  // optional side outputs of generate_images_pred for the interior pixels (trainer.py:506, :532-537); fp32
+  float* side_depth[kMaxScales];
+  float* side_sample[kMaxScales][kMaxSrc];
+  float* side_color[kMaxScales][kMaxSrc];
+  int side_any;                   // some side output pointer is set (one uniform test in the warp loop)
   int B, H, W, S, F;
   int hs[kMaxScales], ws[kMaxScales];
   float scale_h[kMaxScales], scale_w[kMaxScales];
@@ -517,6 +522,22 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
           if (interior) {
             G[(f * 6 + c) * C::IN + j] = ddx;
             G[(f * 6 + 3 + c) * C::IN + j] = ddy;
+          }
+        }
+      }
+      if (p.side_any && interior) {  // the reference's outputs[("depth" | "sample" | "color", ...)] for this pixel
+        const size_t o = (size_t)t.b * HW + (size_t)gy * p.W + gx;
+        if (p.side_depth[s]) p.side_depth[s][o] = cam.z;
+#pragma unroll
+        for (int f = 0; f < C::F; ++f) {
+          if (p.side_sample[s][f]) {
+            p.side_sample[s][f][2 * o] = pr[f].gx;
+            p.side_sample[s][f][2 * o + 1] = pr[f].gy;
+          }
+          if (p.side_color[s][f]) {
+            float* q = p.side_color[s][f] + (size_t)t.b * 3 * HW + (size_t)gy * p.W + gx;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) q[(size_t)c * HW] = val[f][c];
           }
         }
       }

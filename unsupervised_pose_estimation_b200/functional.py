@@ -246,11 +246,18 @@ class KernelEvents:
         return out
 
 
+def _side_ptr(t, shape, dev):
+    if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+        raise _lib.VslError("side output buffer must be a contiguous float32 %s tensor on %s (got %s %s %s)"
+                            % (tuple(shape), dev, t.dtype, tuple(t.shape), t.device))
+    return t.data_ptr()
+
+
 class _FusedLoss(torch.autograd.Function):
     """losses vector [2S+1] = (min_loss/s ..., loss/s ..., loss), masks...  <- disps, P matrices."""
 
     @staticmethod
-    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, n_pmask, *leaves):
+    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, n_pmask, side, *leaves):
         S, F = len(plan.scales), plan.num_src
         # the masks are non-differentiable outputs: without this autograd hands backward() a zero-filled
         # [B,H,W] tensor per mask (four 5.9 MB fill kernels per step at config 1)
@@ -321,6 +328,18 @@ class _FusedLoss(torch.autograd.Function):
                 gpm.append(gm)
             ctx.gpm = gpm
         ctx.n_pmask = n_pmask
+        if side is not None:
+            # side outputs of generate_images_pred, written in place by the kernel (no autograd edge: the
+            # reference's own use of them is inside the loss this call computes)
+            for s in range(S):
+                d = side["depth"][s] if side.get("depth") else None
+                if d is not None:
+                    buf.side_depth[s] = _side_ptr(d, (B, 1, H, W), dev)
+                for f in range(F):
+                    for name, field, shape in (("sample", buf.side_sample, (B, H, W, 2)), ("color", buf.side_color, (B, 3, H, W))):
+                        t = side[name][s][f] if side.get(name) else None
+                        if t is not None:
+                            field[s][f] = _side_ptr(t, shape, dev)
         # one flat allocation for everything the backward keeps
         n_levels = [B * (H >> s) * (W >> s) for s in plan.scales]
         sizes = [3 * S + 1, S * F * B * 12, S * B * 2] + n_levels + n_levels
@@ -353,7 +372,7 @@ class _FusedLoss(torch.autograd.Function):
         plan = ctx.plan
         S, F, B = len(plan.scales), plan.num_src, plan.batch
         if gvec is None:  # no loss entry was used (grads are not materialised, see forward)
-            return (None,) * (9 + S + (S if ctx.use_T == "per_scale" else 1) * F + ctx.n_pmask)
+            return (None,) * (10 + S + (S if ctx.use_T == "per_scale" else 1) * F + ctx.n_pmask)
         dev = gvec.device
         up = _dev(gvec, "upstream gradient")
         n_levels = [int(np.prod(sh)) for sh in plan.level_shapes]
@@ -377,18 +396,20 @@ class _FusedLoss(torch.autograd.Function):
             # (the same a_s vsl_loss_combine_grads uses; tiny torch arithmetic on the [2S+1] vector)
             a = up[:S] + up[S:2 * S] + up[2 * S] / S
             gpm = tuple(ctx.gpm[s] * a[s] for s in range(S))
-        return (None, None, None, None, None, None, None, None, None) + tuple(gd) + tuple(gPs) + gpm
+        return (None, None, None, None, None, None, None, None, None, None) + tuple(gd) + tuple(gPs) + gpm
 
 
 def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, K=None, Ts=None,
-               predictive_masks=None):
+               predictive_masks=None, side=None):
     """Run the fused path.  Returns (loss_vector[2S+1], [mask_s ...]).
 
     loss_vector order: min_loss/s for every scale, loss/s for every scale, loss
     (reference trainer.py:672-685).  The camera of each source frame is given either as ``Ps``
     (projection matrices (K@T)[:, :3, :]) or, preferred, as ``K`` + ``Ts`` (the 4x4 poses): the kernel then
     forms K@T itself and the backward returns dL/dT directly, with no torch matmul in between.
-    Gradients flow to ``disps`` and to ``Ps`` / ``Ts``.
+    Gradients flow to ``disps`` and to ``Ps`` / ``Ts``.  ``side``: optional pre-allocated float32 buffers
+    ``{"depth": [S x [B,1,H,W]], "sample": [S][F x [B,H,W,2]], "color": [S][F x [B,3,H,W]]}`` (entries may be
+    None) that receive the reference's ``generate_images_pred`` outputs from the same kernel.
     """
     use_T = Ts is not None
     poses = list(Ts if use_T else Ps)
@@ -398,7 +419,7 @@ def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, 
         poses = [T for per_frame in poses for T in per_frame]
     pm = list(predictive_masks or [])
     res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise or []), bool(want_mask), K, use_T,
-                           len(pm), *(list(disps) + poses + pm))
+                           len(pm), side, *(list(disps) + poses + pm))
     return res[0], list(res[1:])
 
 
