@@ -43,6 +43,8 @@ class GraphedLossStep:
         with torch.cuda.graph(self.graph):
             self.outputs, self.losses, grads = run()
         self.grads = dict(zip(self.keys, grads))
+        # static [2S+1] vector behind the loss dict (min_loss/s..., loss/s..., loss): one D2H copy reads it all
+        self.loss_vector = getattr(path, "vsl_last_loss_vector", None)
 
     def replay(self):
         self.graph.replay()

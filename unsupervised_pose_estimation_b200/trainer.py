@@ -223,6 +223,9 @@ class ViewSynthesisLossMixin:
         vec, masks = VF.fused_loss(plan, targets, sources, disps, inputs[("inv_K", 0)], None, noise,
                                    K=inputs[("K", 0)], Ts=self._vsl_poses(inputs, outputs), predictive_masks=pmasks,
                                    side=side)
+        # the whole loss dict as one contiguous device vector (min_loss/s..., loss/s..., loss): a logger can
+        # read it back with one copy instead of one per entry
+        self.vsl_last_loss_vector = vec.detach() if weighting is None else None
         losses = {}
         for si, scale in enumerate(opt.scales):
             losses["min_loss/{}".format(scale)] = vec[si]
