@@ -49,7 +49,11 @@ enum {
   VSL_FLAG_AUTOMASK = 1 << 0,         /* NOT --disable_automasking (trainer.py:620-633, 654-661) */
   VSL_FLAG_AVG_REPROJECTION = 1 << 1, /* --avg_reprojection (trainer.py:629-630, 649-650)        */
   VSL_FLAG_NO_SSIM = 1 << 2,          /* --no_ssim (trainer.py:549-550)                          */
-  VSL_FLAG_V1_MULTISCALE = 1 << 3     /* --v1_multiscale (trainer.py:497-498, 604-605)           */
+  VSL_FLAG_V1_MULTISCALE = 1 << 3,    /* --v1_multiscale (trainer.py:497-498, 604-605)           */
+  VSL_FLAG_FORWARD_ONLY = 1 << 4      /* losses, masks and side outputs only: Trainer.val() runs the path under
+                                         torch.no_grad() (trainer.py:463-489).  The gradient buffers
+                                         (grad_disp_*, grad_P, smooth_norm, grad_predictive_mask) may be null
+                                         and are not written; vsl_loss_combine_grads must not follow.     */
 };
 
 enum { VSL_DTYPE_F32 = 0, VSL_DTYPE_BF16 = 1 };

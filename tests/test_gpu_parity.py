@@ -558,3 +558,24 @@ def test_fused_side_outputs_equal_eager(frames):
             assert k in out_f and torch.equal(out_f[k], v), k
             n += 1
     assert n == 4 * (1 + 3 * (len(frames) - 1))
+
+
+@pytest.mark.parametrize("frames", [[0, -1, 1], [0, -1, 1, "s"]])
+def test_forward_only_under_no_grad(frames):
+    """Trainer.val() runs the path under torch.no_grad() (trainer.py:463-489): the kernel then skips the adjoint
+    (VSL_FLAG_FORWARD_ONLY); losses, auto-masks and side outputs are the same bits as in a differentiable call."""
+    B, H, W = 2, 64, 96
+    opt = O.make_opt(height=H, width=W, batch_size=B, frame_ids=list(frames))
+    inputs, outputs, leaves = synthetic.make_batch(B, H, W, frames, synthetic.K_KITTI, seed=8, family="smooth", device=DEV)
+    out_g, losses_g, _ = run_ours(opt, inputs, outputs, leaves, seed=4, side="fused")
+    path = LossPath(make_opt(**vars(opt)), device=DEV, side_outputs="fused")
+    with torch.no_grad():
+        out = with_poses(outputs, leaves, opt.frame_ids, L.transformation_from_parameters)
+        path.generate_images_pred(inputs, out)
+        torch.manual_seed(4)
+        losses = path.compute_losses(inputs, out)
+    for k in losses_g:
+        assert not losses[k].requires_grad and torch.equal(losses[k], losses_g[k].detach()), k
+    for k, v in out_g.items():
+        if isinstance(k, tuple) and k[0] in ("depth", "sample", "color") or (isinstance(k, str) and k.startswith("identity_selection")):
+            assert torch.equal(out[k], v), k

@@ -17,6 +17,7 @@ FLAG_AUTOMASK = 1 << 0
 FLAG_AVG_REPROJECTION = 1 << 1
 FLAG_NO_SSIM = 1 << 2
 FLAG_V1_MULTISCALE = 1 << 3
+FLAG_FORWARD_ONLY = 1 << 4
 
 DTYPE_F32 = 0
 DTYPE_BF16 = 1

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(C::NT, C::NT >= 512 ? 1 : 2) k_photometric(con
     else if constexpr (C::F == 2) phase_windows_paired<C>(p, g, t, sm, s, tid, ts);
     else phase_windows<C>(p, g, t, sm, s, tid, ts);
     __syncthreads();
-    phase_backward<C>(p, g, t, sm, s, tid, ts);
+    if (!p.forward_only) phase_backward<C>(p, g, t, sm, s, tid, ts);
     // deterministic block reduction of (loss, dP) -> one partial per CTA and scale
     const int w = tid >> 5, l = tid & 31;
 #pragma unroll
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(C::NT, C::NT >= 512 ? 1 : 2) k_photometric(con
         r += tid < C::kPartial ? red[i * C::kPartial + tid] : sm[C::oRedS + i * 4 + (tid - C::kPartial)];
       p.partials[((size_t)t.cta * p.S + s) * C::kPartialAll + tid] = r;
     }
-    if (!p.identity_scale[s]) {  // block-uniform; the tile's d/d(up-sampled disp) is complete (sync above)
+    if (!p.identity_scale[s] && !p.forward_only) {  // block-uniform; the tile's d/d(up-sampled disp) is complete (sync above)
       phase_adjoint_rows<C>(p, t, sm, s, tid);
       __syncthreads();
       phase_adjoint_cols<C>(p, t, sm, s, tid);
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
   int nchunk = (n + kChunk - 1) / kChunk;
   // identity levels only have the per-image reductions of chunk 0; idle blocks must not touch the counter
   if (chunk >= (p.identity_scale[s] ? 1 : nchunk)) return;
-  if (!p.identity_scale[s]) {
+  if (!p.identity_scale[s] && p.gphoto[s]) {  // gphoto is null with VSL_FLAG_FORWARD_ONLY
     // d(min_loss/s)/d disp_s: add the (<= 4) tile partials of every coarse pixel, tiles in a fixed order
     float* gp = p.gphoto[s] + (size_t)b * n;
     const int lcw = p.log_tw - p.level_shift[s], lch = p.log_th - p.level_shift[s];
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
         if (kk == 0) p.lossb[s * p.B + b] = (float)tot;
         else if (kk < kphoto) {
           int f = (kk - 1) / 12, e = (kk - 1) % 12;
-          p.gradP[((size_t)(s * p.F + f) * p.B + b) * 12 + e] = (float)tot;
+          if (p.gradP) p.gradP[((size_t)(s * p.F + f) * p.B + b) * 12 + e] = (float)tot;
         } else {
           ssum[kk - kphoto] = tot;
         }
@@ -256,8 +256,10 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
       const float mean = (float)(ssum[0] / (double)n);
       const float inv = 1.0f / (mean + 1e-7f);
       const float ainv = fabsf(inv);
-      p.norm[(s * p.B + b) * 2] = ainv;
-      p.norm[(s * p.B + b) * 2 + 1] = (inv < 0.f ? -1.f : 1.f) * (float)ssum[3] * inv * inv / (float)n;
+      if (p.norm) {
+        p.norm[(s * p.B + b) * 2] = ainv;
+        p.norm[(s * p.B + b) * 2 + 1] = (inv < 0.f ? -1.f : 1.f) * (float)ssum[3] * inv * inv / (float)n;
+      }
       p.smoothb[(s * p.B + b) * 2] = (float)(ssum[1] * (double)ainv);
       p.smoothb[(s * p.B + b) * 2 + 1] = (float)(ssum[2] * (double)ainv);
     }
@@ -562,7 +564,9 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
                                     size_t workspace_bytes, void* stream, void* event_before, void* event_after) {
   if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
   if (!buf || !workspace) return VSL_ERR_NULL_POINTER;
-  if (d->flags & ~(VSL_FLAG_AUTOMASK | VSL_FLAG_NO_SSIM | VSL_FLAG_AVG_REPROJECTION)) return VSL_ERR_UNSUPPORTED;
+  if (d->flags & ~(VSL_FLAG_AUTOMASK | VSL_FLAG_NO_SSIM | VSL_FLAG_AVG_REPROJECTION | VSL_FLAG_FORWARD_ONLY))
+    return VSL_ERR_UNSUPPORTED;
+  const bool fwd_only = (d->flags & VSL_FLAG_FORWARD_ONLY) != 0;
   const bool avg = (d->flags & VSL_FLAG_AVG_REPROJECTION) && d->num_src > 1;  // the mean of one frame is the frame
   if (avg && d->image_dtype != VSL_DTYPE_F32) return VSL_ERR_UNSUPPORTED;   // avg + bf16 storage: not instantiated
   if (d->image_dtype != VSL_DTYPE_F32 && d->image_dtype != VSL_DTYPE_BF16) return VSL_ERR_UNSUPPORTED;
@@ -574,11 +578,12 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   Plan pl = make_plan(d, tile_height(d, avg, pmask));
   if (workspace_bytes < vsl_loss_workspace_bytes(d)) return VSL_ERR_WORKSPACE;
   if (((uintptr_t)workspace & 15u) != 0) return VSL_ERR_MISALIGNED;
-  if (!buf->inv_K || !buf->losses || !buf->grad_P || !buf->smooth_norm) return VSL_ERR_NULL_POINTER;
-  for (int s = 0; s < S; ++s)
-    if (!buf->target[s] || !buf->disp[s] || (automask && !buf->noise[s]) || !buf->grad_disp_photo[s] ||
-        !buf->grad_disp_smooth[s])
-      return VSL_ERR_NULL_POINTER;
+  if (!buf->inv_K || !buf->losses) return VSL_ERR_NULL_POINTER;
+  if (!fwd_only && (!buf->grad_P || !buf->smooth_norm)) return VSL_ERR_NULL_POINTER;
+  for (int s = 0; s < S; ++s) {
+    if (!buf->target[s] || !buf->disp[s] || (automask && !buf->noise[s])) return VSL_ERR_NULL_POINTER;
+    if (!fwd_only && (!buf->grad_disp_photo[s] || !buf->grad_disp_smooth[s])) return VSL_ERR_NULL_POINTER;
+  }
   for (int f = 0; f < F; ++f) {
     if (!buf->source[f]) return VSL_ERR_NULL_POINTER;
     for (int s = 0; s < S; ++s) {
@@ -601,6 +606,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     for (int f = 0; f < F; ++f) pp.pose_per_scale |= buf->T_scale[s][f] != nullptr;
   if (pmask && d->image_dtype != VSL_DTYPE_F32) return VSL_ERR_UNSUPPORTED;  // predictive mask + bf16 storage: not instantiated
   pp.no_ssim = (d->flags & VSL_FLAG_NO_SSIM) ? 1 : 0;
+  pp.forward_only = fwd_only ? 1 : 0;
   pp.invK = buf->inv_K;
   pp.B = sp.B = d->batch; pp.H = sp.H = d->height; pp.W = sp.W = d->width; pp.S = sp.S = S; pp.F = sp.F = F;
   pp.g = make_geo(d);
@@ -623,8 +629,8 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     pp.noise[s] = buf->noise[s];
     pp.mask[s] = automask ? buf->mask[s] : nullptr;
     pp.pmask[s] = automask ? nullptr : buf->predictive_mask[s];  // the reference only uses it without automasking
-    pp.gpmask[s] = pp.pmask[s] ? buf->grad_predictive_mask[s] : nullptr;
-    if (pp.pmask[s] && !pp.gpmask[s]) return VSL_ERR_NULL_POINTER;
+    pp.gpmask[s] = (pp.pmask[s] && !fwd_only) ? buf->grad_predictive_mask[s] : nullptr;
+    if (pp.pmask[s] && !pp.gpmask[s] && !fwd_only) return VSL_ERR_NULL_POINTER;
     pp.side_depth[s] = buf->side_depth[s];
     pp.side_any |= buf->side_depth[s] != nullptr;
     for (int f = 0; f < F; ++f) {
@@ -632,21 +638,22 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
       pp.side_color[s][f] = buf->side_color[s][f];
       pp.side_any |= buf->side_sample[s][f] != nullptr || buf->side_color[s][f] != nullptr;
     }
-    pp.gD[s] = (e == 0) ? buf->grad_disp_photo[s] : nullptr;
+    pp.gD[s] = (e == 0 && !fwd_only) ? buf->grad_disp_photo[s] : nullptr;
     pp.gpart[s] = (e == 0) ? nullptr : ws + pl.off_gpart[s];
     sp.gpart[s] = pp.gpart[s];
     sp.img[s] = buf->target[s];
     sp.gsmooth[s] = buf->grad_disp_smooth[s];
     pp.tgts[s] = buf->target[s];
-    pp.gsmooth[s] = buf->grad_disp_smooth[s];
-    sp.gphoto[s] = buf->grad_disp_photo[s];
+    // phase_smooth is switched on by a non-null gsmooth; forward-only runs it for the sums and writes nothing there
+    pp.gsmooth[s] = fwd_only ? (float*)buf->losses : buf->grad_disp_smooth[s];
+    sp.gphoto[s] = fwd_only ? nullptr : buf->grad_disp_photo[s];
     sp.scale_id[s] = e + d->smooth_level_bias;
   }
   sp.partials = pp.partials;
   sp.lossb = ws + pl.off_lossb;
   sp.smoothb = ws + pl.off_smoothb;
-  sp.gradP = buf->grad_P;
-  sp.norm = buf->smooth_norm;
+  sp.gradP = fwd_only ? nullptr : buf->grad_P;
+  sp.norm = fwd_only ? nullptr : buf->smooth_norm;
   sp.tw = pl.tw; sp.th = pl.th; sp.tiles_x = pl.tiles_x; sp.tiles_y = pl.tiles_y;
   sp.log_tw = ilog2(pl.tw); sp.log_th = ilog2(pl.th);
   sp.losses = buf->losses;
@@ -697,6 +704,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
 int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLossBuffers* buf,
                            float* const grad_disp[VSL_MAX_SCALES], float* grad_P_out, float* grad_T_out, void* stream) {
   if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
+  if (d->flags & VSL_FLAG_FORWARD_ONLY) return VSL_ERR_UNSUPPORTED;  // a forward-only pass left no gradients behind
   if (!upstream || !buf || !grad_disp) return VSL_ERR_NULL_POINTER;
   CombineParams cp = {};
   cp.up = upstream; cp.B = d->batch; cp.S = d->num_scales; cp.F = d->num_src;

@@ -41,6 +41,7 @@ struct PhotoParams {
   float* side_sample[kMaxScales][kMaxSrc];
   float* side_color[kMaxScales][kMaxSrc];
   int side_any;                   // some side output pointer is set (one uniform test in the warp loop)
+  int forward_only;               // VSL_FLAG_FORWARD_ONLY: no adjoint state is kept, no gradient is written
   int B, H, W, S, F;
   int hs[kMaxScales], ws[kMaxScales];
   float scale_h[kMaxScales], scale_w[kMaxScales];
@@ -492,7 +493,8 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
       Cam cam = backproject_pixel(D, invK, u, v, g);
       bool interior = ry >= 2 && ry < C::TH + 2 && rx >= 2 && rx < C::TW + 2 && gy < p.H && gx < p.W;
       int j = (ry - 2) * C::TW + (rx - 2);
-      if (interior) sm[C::oZ + j] = cam.z;  // the adjoint re-forms the camera point from it
+      const bool keep = interior && !p.forward_only;  // state the adjoint needs
+      if (keep) sm[C::oZ + j] = cam.z;  // the adjoint re-forms the camera point from it
       // all frames' taps are requested before any is consumed, so their latencies overlap
       Proj pr[C::F];
       Taps tp[C::F];
@@ -519,7 +521,7 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
           // grid_sampler_2d_backward's d out / d(ix, iy); zero where the border clip is active
           float ddx = pr[f].inx ? ((vne - vnw) * tp[f].wy1 + (vse - vsw) * tp[f].wy0) : 0.f;
           float ddy = pr[f].iny ? ((vsw - vnw) * tp[f].wx1 + (vse - vne) * tp[f].wx0) : 0.f;
-          if (interior) {
+          if (keep) {
             G[(f * 6 + c) * C::IN + j] = ddx;
             G[(f * 6 + 3 + c) * C::IN + j] = ddy;
           }
@@ -619,7 +621,7 @@ VSL_HD void phase_smooth(const PhotoParams& p, const TileCtx& t, const float* __
       pixel(-1, 0, cn);
       g -= cy * sgn_of(d[-C::DW] - d0) * smooth_edge_weight(cn, c0);
     }
-    g_out[o] = g;
+    if (!p.forward_only) g_out[o] = g;
     acc[0] += d0;
     acc[3] += g * d0;
   }
@@ -717,12 +719,12 @@ VSL_HD void phase_windows_avg(const PhotoParams& p, const GeoConst& g, const Til
       l[f] = has_pmask<C>(p, s) ? mul_rn(lraw[f], m) : lraw[f];
 #pragma unroll
       for (int k = 0; k < 9; ++k) coef[k] = 0.f;
-      if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc * m, coef);
-      store_rec(Rec + f * C::WN + i, coef, f, m);
+      if (!p.no_ssim && !p.forward_only) window_coefs(so, TS, C::WN, i, kc * m, coef);
+      if (!p.forward_only) store_rec(Rec + f * C::WN + i, coef, f, m);
     }
     const float avg = mean_frames<C::F>(l);
     const bool warped = avg < best;  // identity first: ties keep the identity channel
-    if (!warped) {
+    if (!warped && !p.forward_only) {
 #pragma unroll
       for (int f = 0; f < C::F; ++f) Rec[f * C::WN + i].idx = -1;
     }
@@ -781,7 +783,7 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
       if (l.x < best) { best = l.x; win = 0; }
       if (l.y < best) { best = l.y; win = 1; }
       if (win >= 0) { bidx = C::F + 2 * pr + win; wm = win == 0 ? m0 : m1; }
-      if (win >= 0 && !p.no_ssim) {  // rebuild the winner's SSIM state from its window sums (same ops, same bits)
+      if (win >= 0 && !p.no_ssim && !p.forward_only) {  // rebuild the winner's SSIM state from its window sums (same ops, same bits)
         SsimOut so[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
@@ -802,11 +804,11 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
         wm = m;
 #pragma unroll
         for (int k = 0; k < 9; ++k) coef[k] = 0.f;  // a pair frame may have set them before losing to this one
-        if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc * wm, coef);
+        if (!p.no_ssim && !p.forward_only) window_coefs(so, TS, C::WN, i, kc * wm, coef);
       }
     }
     bool warped = bidx >= C::F;
-    store_rec(Rec + i, coef, warped ? bidx - C::F : -1, wm);
+    if (!p.forward_only) store_rec(Rec + i, coef, warped ? bidx - C::F : -1, wm);
     bool interior = wy >= 1 && wy <= C::TH && wx >= 1 && wx <= C::TW;
     if (interior) {
       ts.loss += best;
@@ -869,7 +871,9 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
     float coef[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) coef[k] = 0.f;
-    if (win == f) {
+    if (p.forward_only) {
+      // no adjoint: nothing to record
+    } else if (win == f) {
       if (!p.no_ssim) window_coefs(so, TS, C::WN, i, kc * m, coef);
       store_rec(Rec + i, coef, f, m);
     } else if (win < 0 && f == 0) {

@@ -257,11 +257,14 @@ class _FusedLoss(torch.autograd.Function):
     """losses vector [2S+1] = (min_loss/s ..., loss/s ..., loss), masks...  <- disps, P matrices."""
 
     @staticmethod
-    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, n_pmask, side, *leaves):
+    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, n_pmask, side, fwd_only, *leaves):
         S, F = len(plan.scales), plan.num_src
         # the masks are non-differentiable outputs: without this autograd hands backward() a zero-filled
         # [B,H,W] tensor per mask (four 5.9 MB fill kernels per step at config 1)
         ctx.set_materialize_grads(False)
+        # fwd_only (decided by the caller: grad mode is always off inside forward()): nothing to differentiate —
+        # Trainer.val() under torch.no_grad(), trainer.py:463-489 — so the kernel keeps no adjoint state and
+        # writes no gradient
         pmasks = leaves[len(leaves) - n_pmask:] if n_pmask else ()   # --predictive_mask, one [B,F,H,W] per scale
         leaves = leaves[:len(leaves) - n_pmask] if n_pmask else leaves
         disps, Ps = leaves[:S], leaves[S:]   # Ps: projection matrices [B,3,4], or poses T [B,4,4] if use_T
@@ -322,10 +325,12 @@ class _FusedLoss(torch.autograd.Function):
                 m = _dev(pmasks[s], "predictive_mask[%d]" % s)
                 if tuple(m.shape) != (B, F, H, W):
                     raise ValueError("predictive_mask[%d] has shape %s, expected %s" % (s, tuple(m.shape), (B, F, H, W)))
-                gm = torch.empty_like(m)
-                buf.predictive_mask[s], buf.grad_predictive_mask[s] = m.data_ptr(), gm.data_ptr()
+                buf.predictive_mask[s] = m.data_ptr()
                 keep.append(m)
-                gpm.append(gm)
+                if not fwd_only:
+                    gm = torch.empty_like(m)
+                    buf.grad_predictive_mask[s] = gm.data_ptr()
+                    gpm.append(gm)
             ctx.gpm = gpm
         ctx.n_pmask = n_pmask
         if side is not None:
@@ -342,23 +347,31 @@ class _FusedLoss(torch.autograd.Function):
                             field[s][f] = _side_ptr(t, shape, dev)
         # one flat allocation for everything the backward keeps
         n_levels = [B * (H >> s) * (W >> s) for s in plan.scales]
-        sizes = [3 * S + 1, S * F * B * 12, S * B * 2] + n_levels + n_levels
+        sizes = [3 * S + 1] if fwd_only else [3 * S + 1, S * F * B * 12, S * B * 2] + n_levels + n_levels
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         parts = torch.split(flat, sizes)
-        losses, gradP, norm = parts[0], parts[1], parts[2]
-        gphoto, gsmooth = parts[3:3 + S], parts[3 + S:3 + 2 * S]
-        buf.losses, buf.grad_P, buf.smooth_norm = losses.data_ptr(), gradP.data_ptr(), norm.data_ptr()
+        losses = parts[0]
+        buf.losses = losses.data_ptr()
+        if not fwd_only:
+            gradP, norm = parts[1], parts[2]
+            gphoto, gsmooth = parts[3:3 + S], parts[3 + S:3 + 2 * S]
+            buf.grad_P, buf.smooth_norm = gradP.data_ptr(), norm.data_ptr()
         masks = []
         for s in range(S):
-            buf.grad_disp_photo[s] = gphoto[s].data_ptr()
-            buf.grad_disp_smooth[s] = gsmooth[s].data_ptr()
+            if not fwd_only:
+                buf.grad_disp_photo[s] = gphoto[s].data_ptr()
+                buf.grad_disp_smooth[s] = gsmooth[s].data_ptr()
             if want_mask and plan.automask:
                 m = torch.empty(B, H, W, dtype=torch.float32, device=dev)
                 buf.mask[s] = m.data_ptr()
                 masks.append(m)
         ws = plan.workspace(dev)
         ev = plan.kernel_events.new_pair() if plan.kernel_events is not None else (None, None)
-        check(plan.lib.vsl_loss_forward_backward_timed(ctypes.byref(plan.desc), ctypes.byref(buf), ws.data_ptr(),
+        desc = plan.desc
+        if fwd_only:
+            desc = type(plan.desc).from_buffer_copy(plan.desc)
+            desc.flags |= _lib.FLAG_FORWARD_ONLY
+        check(plan.lib.vsl_loss_forward_backward_timed(ctypes.byref(desc), ctypes.byref(buf), ws.data_ptr(),
                                                        plan.ws_bytes, _stream(), ev[0], ev[1]),
               "vsl_loss_forward_backward")
         ctx.plan, ctx.buf, ctx.flat, ctx.keep, ctx.use_T = plan, buf, flat, keep, use_T
@@ -372,7 +385,7 @@ class _FusedLoss(torch.autograd.Function):
         plan = ctx.plan
         S, F, B = len(plan.scales), plan.num_src, plan.batch
         if gvec is None:  # no loss entry was used (grads are not materialised, see forward)
-            return (None,) * (10 + S + (S if ctx.use_T == "per_scale" else 1) * F + ctx.n_pmask)
+            return (None,) * (11 + S + (S if ctx.use_T == "per_scale" else 1) * F + ctx.n_pmask)
         dev = gvec.device
         up = _dev(gvec, "upstream gradient")
         n_levels = [int(np.prod(sh)) for sh in plan.level_shapes]
@@ -396,7 +409,7 @@ class _FusedLoss(torch.autograd.Function):
             # (the same a_s vsl_loss_combine_grads uses; tiny torch arithmetic on the [2S+1] vector)
             a = up[:S] + up[S:2 * S] + up[2 * S] / S
             gpm = tuple(ctx.gpm[s] * a[s] for s in range(S))
-        return (None, None, None, None, None, None, None, None, None, None) + tuple(gd) + tuple(gPs) + gpm
+        return (None, None, None, None, None, None, None, None, None, None, None) + tuple(gd) + tuple(gPs) + gpm
 
 
 def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, K=None, Ts=None,
@@ -418,8 +431,10 @@ def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, 
         use_T = "per_scale"
         poses = [T for per_frame in poses for T in per_frame]
     pm = list(predictive_masks or [])
+    leaves = list(disps) + poses + pm
+    fwd_only = not (torch.is_grad_enabled() and any(t.requires_grad for t in leaves))
     res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise or []), bool(want_mask), K, use_T,
-                           len(pm), side, *(list(disps) + poses + pm))
+                           len(pm), side, fwd_only, *leaves)
     return res[0], list(res[1:])
 
 
