@@ -64,3 +64,21 @@ def test_bench_byte_model():
     spec.loader.exec_module(bench)
     assert bench.algorithmic_bytes_per_pixel(2) == pytest.approx(50.5625)
     assert bench.algorithmic_bytes_per_pixel(3, 2) == pytest.approx(36.59375)  # C3, bf16 images
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path, oracle port) runs without a GPU and prints ONE JSON
+    line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C2",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "px/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["config"]["workload"].startswith("C2")
