@@ -151,13 +151,21 @@ class ClockSampler:
         return out
 
 
-def oracle_step_cpu(cfg, family, batch, threads):
-    """One forward+backward of the reference path on the host cores via the oracle port."""
+# the option values both arms run with (monodepth2's) -- passed explicitly to the GPU arm's
+# make_opt AND to the oracle's, so the two can never drift apart through their defaults
+BENCH_OPT = dict(max_depth=100.0, disparity_smoothness=1e-3, min_depth=0.1)
+
+
+def oracle_step_cpu(cfg, family, batch, threads, device="cpu"):
+    """One forward+backward of the reference path via the oracle port: on the host cores (cpu_baseline,
+    --impl reference) or, with device="cuda", as the eager PyTorch-CUDA op stream (the `eager_cuda` record)."""
     from oracle import vsl_oracle as O
-    torch.set_num_threads(threads)
-    opt = O.make_opt(height=cfg["height"], width=cfg["width"], batch_size=batch, frame_ids=list(cfg["frame_ids"]))
+    if device == "cpu":
+        torch.set_num_threads(threads)
+    opt = O.make_opt(height=cfg["height"], width=cfg["width"], batch_size=batch, frame_ids=list(cfg["frame_ids"]),
+                     **BENCH_OPT)
     inputs, outputs, leaves = synthetic.make_batch(batch, cfg["height"], cfg["width"], cfg["frame_ids"], cfg["K"],
-                                                   seed=0, family=family, device="cpu")
+                                                   seed=0, family=family, device=device)
 
     def run():
         out = dict(outputs)
@@ -165,9 +173,13 @@ def oracle_step_cpu(cfg, family, batch, threads):
             if f != "s":
                 out[("cam_T_cam", 0, f)] = O.transformation_from_parameters(
                     leaves[("axisangle", 0, f)][:, 0], leaves[("translation", 0, f)][:, 0], f < 0)
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         losses = O.loss_step(opt, inputs, out)
         torch.autograd.grad(losses["loss"], list(leaves.values()))
+        if device != "cpu":
+            torch.cuda.synchronize()
         return time.perf_counter() - t0
     return run
 
@@ -209,6 +221,92 @@ def workload_config(args, cfg):
             "side_outputs": "none (fused path; reference side outputs are materialised on logging steps only)"}
 
 
+def shard_parity(cfg, family, device, rank, world, dist):
+    """N > 1, before anything is timed: the path's claim that it shards by image with no exchange, checked on
+    the hardware path.  Every rank runs its shard (rows [rank*B, (rank+1)*B) of a global batch of B*world images,
+    same tie-break noise rows), rank 0 also runs the global batch on one GPU; required: the auto-masks of the shard
+    rows are the same bits as the global run's, the all-reduced losses (parallel.all_reduce_losses) equal the
+    global losses to 1e-6, and shard gradients / world equal the global gradient rows to 1e-5 rel-L2
+    (reference semantics: batch means, trainer.py:672-685)."""
+    from unsupervised_pose_estimation_b200 import functional as VF
+    from unsupervised_pose_estimation_b200 import layers as L
+    from unsupervised_pose_estimation_b200 import parallel
+    B, H, W, frames = cfg["batch"], cfg["height"], cfg["width"], cfg["frame_ids"]
+    Bg, F, S = B * world, len(cfg["frame_ids"]) - 1, 4
+    inputs, _, leaves = synthetic.make_batch(Bg, H, W, frames, cfg["K"], seed=4242, family=family, device="cpu",
+                                             requires_grad=False)
+    gen = torch.Generator().manual_seed(99)
+    noise_g = [torch.randn(Bg, F, H, W, generator=gen) for _ in range(S)]
+
+    def run(lo, hi):
+        b = hi - lo
+        dv = lambda t: t[lo:hi].to(device)
+        plan = VF.FusedLossPlan(b, H, W, list(range(S)), F, BENCH_OPT["min_depth"], BENCH_OPT["max_depth"],
+                                BENCH_OPT["disparity_smoothness"], arith=VF.calibrate_arith(b, H, W, device))
+        disps = [dv(leaves[("disp", s)]).requires_grad_(True) for s in range(S)]
+        Ts = []
+        for f in frames[1:]:
+            if f == "s":
+                Ts.append(dv(inputs["stereo_T"]))
+            else:
+                T = L.transformation_from_parameters(dv(leaves[("axisangle", 0, f)])[:, 0],
+                                                     dv(leaves[("translation", 0, f)])[:, 0], f < 0)
+                Ts.append(T.detach().requires_grad_(True))
+        vec, masks = VF.fused_loss(plan, [dv(inputs[("color", 0, s)]) for s in range(S)],
+                                   [dv(inputs[("color", f, 0)]) for f in frames[1:]], disps, dv(inputs[("inv_K", 0)]),
+                                   None, [dv(z) for z in noise_g], K=dv(inputs[("K", 0)]), Ts=Ts)
+        wrt = disps + [T for T in Ts if T.requires_grad]
+        grads = torch.autograd.grad(vec[2 * S], wrt)
+        return vec.detach(), torch.stack(masks), [g.flatten(1) for g in grads]
+
+    lo, hi = rank * B, (rank + 1) * B
+    vec_l, masks_l, grads_l = run(lo, hi)
+    names = ["min_loss/%d" % s for s in range(S)] + ["loss/%d" % s for s in range(S)] + ["loss"]
+    reduced = parallel.all_reduce_losses({k: vec_l[i] for i, k in enumerate(names)}, B)
+    gshape = [(Bg, g.shape[1]) for g in grads_l]
+    if rank == 0:
+        vec_g, masks_g, grads_g = run(0, Bg)
+    else:
+        vec_g = torch.empty(2 * S + 1, device=device)
+        masks_g = torch.empty(S, Bg, H, W, device=device)
+        grads_g = [torch.empty(sh, device=device) for sh in gshape]
+    for t in [vec_g, masks_g] + grads_g:
+        dist.broadcast(t, 0)
+    mask_ok = torch.equal(masks_l, masks_g[:, lo:hi])
+    loss_err = max(abs(float(reduced[k]) - float(vec_g[i])) / abs(float(vec_g[i])) for i, k in enumerate(names))
+    grad_err = max(float((gl / world - gg[lo:hi]).norm() / gg[lo:hi].norm().clamp_min(1e-30)) for gl, gg in zip(grads_l, grads_g))
+    ok = torch.tensor([1.0 if (mask_ok and loss_err <= 1e-6 and grad_err <= 1e-5) else 0.0, loss_err, grad_err],
+                      device=device, dtype=torch.float64)
+    worst = ok.clone()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    if float(ok[0]) != 1.0:
+        raise SystemExit("shard parity FAILED on some rank: masks_equal=%s loss_err=%.3g grad_err=%.3g (rank %d)"
+                         % (mask_ok, loss_err, grad_err, rank))
+    del masks_g, grads_g
+    torch.cuda.empty_cache()
+    return {"status": "ok", "global_batch": Bg, "ranks": world, "automask_rows_bit_equal": True,
+            "max_rel_loss_err_allreduced_vs_global": float(worst[1]), "max_rel_l2_grad_err_shard_vs_global_rows": float(worst[2]),
+            "checked": "every rank's shard of a B*N-image batch against rank 0's single-GPU run of the whole batch"}
+
+
+def timed_loop(fn, n, barrier, device, dist):
+    """ms per call of fn(i) over n calls: CUDA events on the current stream, barrier + synchronize on both sides,
+    max over ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / n
+
+
+
 class Workload:
     """A ring of device-resident input sets + the public-API step."""
 
@@ -217,7 +315,7 @@ class Workload:
         from unsupervised_pose_estimation_b200.trainer import LossPath, make_opt
         self.cfg, self.device, self.L = cfg, device, L
         self.opt = make_opt(height=cfg["height"], width=cfg["width"], batch_size=cfg["batch"],
-                            frame_ids=list(cfg["frame_ids"]), max_depth=100.0, disparity_smoothness=1e-3)
+                            frame_ids=list(cfg["frame_ids"]), **BENCH_OPT)
         self.path = LossPath(self.opt, device=device, side_outputs="none")
         self.sets = []
         self.host = []
@@ -270,6 +368,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--e2e-skip", default="", help="diagnostic: comma list of pipeline,h2d,readback to leave out of the "
                     "e2e loop (the line is then marked invalid)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling C5 sub-record")
     ap.add_argument("--bf16-images", action="store_true",
                     help="store the colour images as bf16 (BASELINE config 3); arithmetic stays fp32")
     args = ap.parse_args()
@@ -301,6 +400,7 @@ def main():
     B, H, W = cfg["batch"], cfg["height"], cfg["width"]
     F = len(cfg["frame_ids"]) - 1
     n0 = B * H * W
+    parity = shard_parity(cfg, args.family, device, rank, world, dist) if dist is not None else None
     ring = 4  # 4 x ~79 MB of inputs (+ 47 MB of fresh tie-break noise per step) > 126 MB L2
     wl = Workload(cfg, args.family, device, ring, bf16_images=args.bf16_images)
 
@@ -553,26 +653,68 @@ def main():
     e2e_f32 = run_e2e("f32")
     e2e_f32["host_buffers"] = "fp32 (\"color\", f, s) tensors as the reference's DataLoader yields them + disp, poses, K/inv_K"
 
-    # ---- informational (N > 1): the one exchange of data-parallel training with this loss, outside the path:
-    # an all-reduce of the depth/pose-net gradients (28,641,888 fp32 parameters)
-    grad_allreduce = None
-    if dist is not None:
+    # ---- N > 1: the one exchange of data-parallel training with this loss -- the all-reduce of the depth/pose-net
+    # gradients (28,641,888 fp32 parameters) -- alone, and issued CONCURRENTLY with the loss step
+    # (comm stream; buckets as parallel.GradBuckets cuts them), so the line shows what the two contend for
+    grad_allreduce = train_step = None
+    if dist is not None and not args.no_graph:
         payload = torch.zeros(28641888, device=device)
-        for _ in range(3):
-            dist.all_reduce(payload)
-        barrier()
-        e0.record()
-        for _ in range(10):
-            dist.all_reduce(payload)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1) / 10], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ar_ms = float(t.item())
+        bucket = (32 << 20) // 4
+        buckets = [payload[i:i + bucket] for i in range(0, payload.numel(), bucket)]
+        comm = torch.cuda.Stream(device=device)
+
+        def allreduce_all():
+            return [dist.all_reduce(b, async_op=True) for b in buckets]
+
+        def alone(i):
+            for w in allreduce_all():
+                w.wait()
+        for i in range(3):
+            alone(i)
+        ar_ms = timed_loop(alone, 20, barrier, device, dist)
         nbytes = payload.numel() * 4
-        grad_allreduce = {"bytes": nbytes, "ms": ar_ms,
+        grad_allreduce = {"bytes": nbytes, "buckets": len(buckets), "ms": ar_ms,
                           "bus_gbs": 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
-                          "note": "NCCL all-reduce of the net gradients; not part of the timed loss path"}
+                          "note": "NCCL all-reduce of the net gradients in 32 MB buckets, nothing else running"}
+
+        def overlapped(i):
+            # the exchange of the previous step's network gradients rides next to this step's loss kernels
+            ev = torch.cuda.Event()
+            ev.record()
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                works = allreduce_all()
+            run_step(i)
+            for w in works:
+                w.wait()   # the compute stream waits for the collectives before the next step (optimizer.step would)
+        for i in range(5):
+            overlapped(i)
+        n_t = min(args.steps, 100)
+        ov_ms = timed_loop(overlapped, n_t, barrier, device, dist)
+        loss_ms = ms_total / args.steps
+        train_step = {"ms_per_step_loss_plus_allreduce_overlapped": ov_ms, "ms_per_step_loss_alone": loss_ms,
+                      "ms_allreduce_alone": ar_ms, "ms_if_serial": loss_ms + ar_ms,
+                      "hidden_fraction_of_allreduce": max(0.0, min(1.0, (loss_ms + ar_ms - ov_ms) / ar_ms)),
+                      "value": world * n0 / (ov_ms * 1e-3), "unit": UNIT,
+                      "note": "graph-replayed loss step on the compute stream, 4 bucket all-reduces (114.6 MB) on a side "
+                              "stream issued at the same time; NCCL's channels take SMs from k_photometric while they run"}
+        del payload, buckets
+
+    # ---- strong scaling, BASELINE config 5: a GLOBAL batch of 96 images at 640x192 sharded 96/N per GPU ----------
+    strong = None
+    if args.config == "C1" and not args.no_graph and 96 % world == 0 and not args.no_strong:
+        cfg5 = dict(synthetic.CONFIGS["C5"])
+        cfg5["batch"] = 96 // world
+        wl5 = Workload(cfg5, args.family, device, 2, bf16_images=args.bf16_images)
+        g5 = [GraphedLossStep(wl5.path, st["inputs"], st["leaves"]) for st in wl5.sets]
+        for i in range(4):
+            g5[i % 2].replay()
+        n5 = min(args.steps, 40)
+        ms5 = timed_loop(lambda i: g5[i % 2].replay(), n5, barrier, device, dist)
+        strong = {"workload": "C5: global batch 96 at %dx%d, %d images per GPU" % (cfg5["width"], cfg5["height"], cfg5["batch"]),
+                  "scaling": "strong", "global_batch": 96, "per_gpu_batch": cfg5["batch"], "ms_per_step": ms5,
+                  "value": 96 * cfg5["height"] * cfg5["width"] / (ms5 * 1e-3), "unit": UNIT, "steps": n5}
+        del g5, wl5
 
     if rank == 0:
         peak, peak_src = peak_hbm_gbs()
@@ -622,10 +764,15 @@ def main():
                 "reference_unfused_bytes_per_step": unfused,
                 "unfused_equivalent_gbs": unfused / (ms_total / args.steps * 1e-3) / 1e9,
                 "unfused_equivalent_over_hbm_peak": unfused / (ms_total / args.steps * 1e-3) / 1e9 / peak,
-                "eager_pytorch_cuda_ms_per_step_same_b200": 45.0,
-                "eager_source": "profiles/r1_eager_cuda.md"}
+                }
         if grad_allreduce is not None:
             line["grad_allreduce"] = grad_allreduce
+            line["train_step"] = train_step
+        if parity is not None:
+            line["shard_parity"] = parity["status"]
+            line["shard_parity_detail"] = parity
+        if strong is not None:
+            line["strong_scaling_c5"] = strong
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             run = oracle_step_cpu(cfg, args.family, B, threads)
@@ -634,6 +781,16 @@ def main():
             line["cpu_baseline"] = {"value": n0 / min(ts), "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "3 full %s steps (batch %d) after 1 warm-up, best of 3, oracle port "
                                               "of the reference on the host cores" % (args.config, B)}
+            # the same op stream as eager PyTorch-CUDA on this GPU, measured in this run: what the
+            # reference does when it is NOT given --no_cuda.  Checker code used as a reported baseline, like cpu_baseline.
+            run = oracle_step_cpu(cfg, args.family, B, threads, device=device)
+            run()
+            tg = [run() for _ in range(3)]
+            line["eager_cuda"] = {"ms_per_step": 1e3 * min(tg), "value": n0 / min(tg), "unit": UNIT,
+                                  "speedup_of_fused_step": 1e3 * min(tg) / (ms_total / args.steps),
+                                  "sample": "3 full %s steps after 1 warm-up, best of 3: the reference's op stream "
+                                            "(oracle port) as eager PyTorch on the same B200, wall clock around "
+                                            "synchronize()" % args.config}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -7,7 +7,8 @@ Shows how the pieces of this repository sit in the reference's ``Trainer.process
     depth net (stand-in)  -> outputs[("disp", s)]            s = 0..3
     pose net  (stand-in)  -> axis-angle / translation -> transformation_from_parameters -> ("cam_T_cam", 0, f)
     ViewSynthesisLossMixin.generate_images_pred + compute_losses   (one fused CUDA kernel, forward + backward)
-    losses["loss"].backward() -> Adam step                   (+ parallel.all_reduce_grads under torchrun)
+    losses["loss"].backward() -> Adam step                   (+ parallel.GradBuckets under torchrun: bucketed
+                                                              all-reduce overlapped with the backward)
 
     python examples/minimal_training.py [--steps 20]
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 examples/minimal_training.py
@@ -71,6 +72,8 @@ class MiniTrainer(ViewSynthesisLossMixin):
         self.pose = TinyPoseNet().to(device)
         self.params = list(self.depth.parameters()) + list(self.pose.parameters())
         self.optim = torch.optim.Adam(self.params, 1e-3)
+        # .grad of every parameter becomes a view into one flat buffer; hooks all-reduce bucket by bucket during backward
+        self.buckets = parallel.GradBuckets(self.params, local_batch=opt.batch_size, bucket_bytes=1 << 16)
         self.inputs_from_frames = LossInputPipeline(opt, device)
 
     def process_batch(self, inputs):
@@ -86,9 +89,9 @@ class MiniTrainer(ViewSynthesisLossMixin):
         inputs = dict(intrinsics)
         self.inputs_from_frames({f: v.to(self.device, non_blocking=True) for f, v in frames_u8.items()}, inputs)
         outputs, losses = self.process_batch(inputs)
-        self.optim.zero_grad(set_to_none=True)
-        losses["loss"].backward()                              # trainer.py:312
-        parallel.all_reduce_grads(self.params)                 # no-op unless torch.distributed is initialised
+        self.buckets.begin_step()                              # trainer.py:311 zero_grad, keeping the flat views
+        losses["loss"].backward()                              # trainer.py:312; bucket all-reduces start from the hooks
+        self.buckets.finish()                                  # no exchange unless torch.distributed is initialised
         self.optim.step()
         return outputs, losses
 

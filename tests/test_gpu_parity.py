@@ -348,6 +348,50 @@ def test_full_size_properties_c1():
         assert ((g1[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
 
 
+@pytest.mark.parametrize("batch", [24, 48, 96])
+def test_c5_per_gpu_batches(batch):
+    """BASELINE config 5 (global batch 96 at 640x192 over 4 / 2 / 1 GPUs): the per-GPU shapes at full size
+    against the oracle run on the whole batch -- auto-mask bit-exact, losses 1e-6, gradients 5e-5 rel-L2."""
+    cfg = synthetic.CONFIGS["C5"]
+    opt = O.make_opt(height=cfg["height"], width=cfg["width"], batch_size=batch, frame_ids=list(cfg["frame_ids"]))
+    inputs, outputs, leaves = synthetic.make_batch(batch, cfg["height"], cfg["width"], cfg["frame_ids"], cfg["K"],
+                                                   seed=40 + batch, family="smooth", device=DEV)
+    out, losses, g = run_ours(opt, inputs, outputs, leaves, side="none")
+    ref_out, ref_l, ref_g = run_oracle(opt, inputs, outputs, leaves)
+    for k in ref_l:
+        assert abs(losses[k].item() - ref_l[k].item()) <= 1e-6 * abs(ref_l[k].item()), k
+    for s in opt.scales:
+        assert torch.equal(out["identity_selection/%d" % s], ref_out["identity_selection/%d" % s]), s
+    for k in ref_g:
+        assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
+    del ref_out, ref_l, ref_g
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("config", ["C1", "C2", "C3", "C4"])
+def test_full_size_side_outputs(config):
+    """Every BASELINE single-GPU config at its FULL batch (12): the reference-visible side outputs written by the
+    fused kernel itself (depth, sampling grid, warped colours of every scale and frame) and the auto-masks are
+    the oracle's bits; losses 1e-6, gradients 5e-5."""
+    cfg = synthetic.CONFIGS[config]
+    opt = O.make_opt(height=cfg["height"], width=cfg["width"], batch_size=cfg["batch"], frame_ids=list(cfg["frame_ids"]))
+    inputs, outputs, leaves = synthetic.make_config(config, seed=13, family="smooth", device=DEV)
+    out, losses, g = run_ours(opt, inputs, outputs, leaves, side="fused")
+    ref_out, ref_l, ref_g = run_oracle(opt, inputs, outputs, leaves)
+    for s in opt.scales:
+        assert torch.equal(out[("depth", 0, s)], ref_out[("depth", 0, s)]), ("depth", s)
+        for f in opt.frame_ids[1:]:
+            assert torch.equal(out[("sample", f, s)], ref_out[("sample", f, s)]), ("sample", f, s)
+            assert torch.equal(out[("color", f, s)], ref_out[("color", f, s)]), ("color", f, s)
+        assert torch.equal(out["identity_selection/%d" % s], ref_out["identity_selection/%d" % s]), s
+    for k in ref_l:
+        assert abs(losses[k].item() - ref_l[k].item()) <= 1e-6 * abs(ref_l[k].item()), k
+    for k in ref_g:
+        assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
+    del ref_out, ref_l, ref_g
+    torch.cuda.empty_cache()
+
+
 def test_backward_is_linear_in_the_upstream_gradient():
     """Every entry of the loss dict is differentiable (trainer.py:672-685), not just losses['loss']."""
     opt, inputs, outputs, leaves = build_case("mono_iid_64x96")

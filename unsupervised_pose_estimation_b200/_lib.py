@@ -89,7 +89,9 @@ _LIB = None
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvsl_b200.so")
+    """The in-tree library; VSL_LIB_PATH points the loader at another build of the same ABI (developer knob
+    for measuring kernel variants side by side — never a different compute path)."""
+    return os.environ.get("VSL_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvsl_b200.so")
 
 
 def load():
@@ -99,13 +101,15 @@ def load():
         return _LIB
     path = lib_path()
     from . import build as _build
-    if _build.is_stale() and _build.find_nvcc() is not None:
-        _build.build()
-    if not os.path.exists(path):
-        raise VslError(
-            "libvsl_b200.so is missing and nvcc is not available to build it; run "
-            "`python -m unsupervised_pose_estimation_b200.build`. There is no CPU/PyTorch fallback.")
-    lib = ctypes.CDLL(path)
+    # one rank builds, the others wait on the lock and then find a complete, renamed-into-place file
+    with _build.build_lock():
+        if not os.environ.get("VSL_LIB_PATH") and _build.is_stale() and _build.find_nvcc() is not None:
+            _build.build()
+        if not os.path.exists(path):
+            raise VslError(
+                "libvsl_b200.so is missing and nvcc is not available to build it; run "
+                "`python -m unsupervised_pose_estimation_b200.build`. There is no CPU/PyTorch fallback.")
+        lib = ctypes.CDLL(path)
     if lib.vsl_abi_version() != VSL_ABI_VERSION:
         raise VslError("libvsl_b200.so ABI version mismatch; rebuild it")
 

@@ -6,10 +6,13 @@ The library has no torch dependency: plain CUDA runtime, `extern "C"` entry poin
 """
 from __future__ import annotations
 
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
 import sys
+import tempfile
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
@@ -38,23 +41,50 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile the library if it is missing or older than its sources. Returns the .so path."""
-    if not force and not is_stale():
+@contextlib.contextmanager
+def build_lock():
+    """Exclusive inter-process lock around "is it stale? -> build -> load": under torchrun every rank imports
+    the package at once, and only one may run nvcc while the others wait for the finished file."""
+    fd = os.open(os.path.join(PKG_DIR, ".build.lock"), os.O_CREAT | os.O_RDWR, 0o644)
+    try:
+        fcntl.flock(fd, fcntl.LOCK_EX)
+        yield
+    finally:
+        fcntl.flock(fd, fcntl.LOCK_UN)
+        os.close(fd)
+
+
+def build(force=False, verbose=False, out_path=None, extra_flags=()):
+    """Compile the library if it is missing or older than its sources. Returns the .so path.
+
+    nvcc writes to a temporary file in the same directory which is then renamed onto the target, so a
+    concurrent ``ctypes.CDLL`` never sees a half-written ELF.  ``out_path`` / ``extra_flags``: developer
+    knobs for building kernel variants next to the product library (tools/)."""
+    target = out_path or LIB_PATH
+    if out_path is None and not force and not is_stale():
         return LIB_PATH
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libvsl_b200.so (there is no CPU fallback)")
-    extra = os.environ.get("VSL_NVCC_EXTRA", "").split()  # developer knob, e.g. -DVSL_CTAS_PER_SM=2
+    extra = os.environ.get("VSL_NVCC_EXTRA", "").split() + list(extra_flags)  # e.g. -DVSL_EXACT_RCP
+    fd, tmp = tempfile.mkstemp(prefix=".libvsl_b200.", suffix=".so.tmp", dir=os.path.dirname(target))
+    os.close(fd)
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH] + [os.path.join(CSRC, f) for f in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+        ["-o", tmp] + [os.path.join(CSRC, f) for f in SOURCES]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+        os.chmod(tmp, 0o755)
+        os.replace(tmp, target)
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    with build_lock():
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -374,7 +374,11 @@ class _FusedLoss(torch.autograd.Function):
         check(plan.lib.vsl_loss_forward_backward_timed(ctypes.byref(desc), ctypes.byref(buf), ws.data_ptr(),
                                                        plan.ws_bytes, _stream(), ev[0], ev[1]),
               "vsl_loss_forward_backward")
-        ctx.plan, ctx.buf, ctx.flat, ctx.keep, ctx.use_T = plan, buf, flat, keep, use_T
+        ctx.plan, ctx.buf, ctx.keep, ctx.use_T = plan, buf, keep, use_T
+        # what backward() reads through the raw pointers in `buf`: the unit gradients (flat) and K (dL/dT = K^T dL/dP).
+        # Saved through autograd so an in-place overwrite between forward and backward (a stager slot or a graph
+        # input re-filled too early) raises instead of silently producing a wrong dL/dT.
+        ctx.save_for_backward(flat, Kc if use_T else None)
         ctx.mark_non_differentiable(*masks)
         out = losses[:2 * S + 1]
         ctx.smooth_terms = losses[2 * S + 1:]
@@ -386,6 +390,7 @@ class _FusedLoss(torch.autograd.Function):
         S, F, B = len(plan.scales), plan.num_src, plan.batch
         if gvec is None:  # no loss entry was used (grads are not materialised, see forward)
             return (None,) * (11 + S + (S if ctx.use_T == "per_scale" else 1) * F + ctx.n_pmask)
+        ctx.saved_tensors  # version-counter check of the buffers `ctx.buf` points at
         dev = gvec.device
         up = _dev(gvec, "upstream gradient")
         n_levels = [int(np.prod(sh)) for sh in plan.level_shapes]

@@ -20,8 +20,10 @@ class GraphedLossStep:
         self.path, self.inputs, self.leaves = path, inputs, leaves
         self.keys = list(leaves.keys())
         dev = next(iter(leaves.values())).device
-        if path._vsl_plan().kernel_events is not None:
-            raise RuntimeError("kernel timing events cannot be recorded inside a captured graph")
+        # one plan, or one per level with --v1_multiscale; built for the dtype the images are stored in
+        for plan, _, _ in path._vsl_level_plans(inputs[("color", 0, 0)].dtype):
+            if plan.kernel_events is not None:
+                raise RuntimeError("kernel timing events cannot be recorded inside a captured graph")
 
         def run():
             if pre is not None:

@@ -42,6 +42,9 @@ class HostBatchStager:
         self.next_slot = (k + 1) % self.depth
         if self.slots[k] is None:
             self.slots[k] = self._alloc_like(host_batch)
+            # the caching allocator hands out blocks in compute-stream order: the block may have just been freed
+            # by a tensor whose kernels are still queued there, so the first copy into it waits for that stream
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         dst = self.slots[k]
         with torch.no_grad(), torch.cuda.stream(self.copy_stream):
             if self.free[k] is not None:
@@ -62,7 +65,9 @@ class HostBatchStager:
         return self.slots[k]
 
     def release(self):
-        """Mark the batch returned by the last take() as consumed (call after enqueuing its kernels)."""
+        """Mark the batch returned by the last take() as consumed.  Call it only after EVERY kernel that reads
+        the slot has been enqueued — including the backward of the loss step, which reads K and the gradient
+        buffers through raw pointers (functional._FusedLoss) — or the next submit() may overwrite them."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self.free[self._last] = ev
