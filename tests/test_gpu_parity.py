@@ -254,6 +254,38 @@ def test_bf16_image_storage(frames):
         run_ours(opt, mixed, outputs, leaves)
 
 
+@pytest.mark.parametrize("frames", [[0, -1, 1], [0, -1, 1, "s"]])
+@pytest.mark.parametrize("mode", ["avg_reprojection", "predictive_mask", "avg+predictive_mask"])
+def test_bf16_image_storage_with_avg_and_predictive_mask(frames, mode):
+    """bf16 image storage is instantiated for the --avg_reprojection and --predictive_mask kernels too
+    (round 1 returned VSL_ERR_UNSUPPORTED there)."""
+    B, H, W = 2, 64, 96
+    F = len(frames) - 1
+    o = {"avg_reprojection": "avg" in mode}
+    if "predictive_mask" in mode:
+        o.update(predictive_mask=True, disable_automasking=True)
+    opt = O.make_opt(height=H, width=W, batch_size=B, frame_ids=list(frames), **o)
+    inputs, outputs, leaves = synthetic.make_batch(B, H, W, frames, seed=33, family="smooth", device=DEV)
+    if "predictive_mask" in mode:
+        gen = torch.Generator().manual_seed(6)
+        for s in opt.scales:
+            leaves[("pmask", s)] = torch.sigmoid(2 * torch.randn(B, F, H >> s, W >> s, generator=gen)).to(DEV).requires_grad_(True)
+        outputs = dict(outputs)
+        outputs["predictive_mask"] = {("disp", s): leaves[("pmask", s)] for s in opt.scales}
+    in16 = {k: (v.bfloat16() if k[0] == "color" else v) for k, v in inputs.items()}
+    in32 = {k: (v.float() if k[0] == "color" else v) for k, v in in16.items()}
+    ref_out, ref_losses, ref_g = run_oracle(opt, in32, outputs, leaves)
+    out, losses, g = run_ours(opt, in16, outputs, leaves, side="none")
+    for k in ref_losses:
+        assert abs(losses[k].item() - ref_losses[k].item()) <= 1e-6 * abs(ref_losses[k].item()), k
+    if not opt.disable_automasking:
+        for s in opt.scales:
+            assert torch.equal(out["identity_selection/%d" % s], ref_out["identity_selection/%d" % s])
+    assert set(g) == set(ref_g)
+    for k in ref_g:
+        assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
+
+
 def test_pose_given_as_T_equals_pose_given_as_P():
     """K@T formed inside the kernel (calibrated to cuBLAS's order) == torch.matmul(K, T)[:, :3, :] fed as P;
     the returned dL/dT equals autograd's K[:3,:]^T dL/dP."""

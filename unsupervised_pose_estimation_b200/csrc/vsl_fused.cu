@@ -103,8 +103,6 @@ __global__ void __launch_bounds__(C::NT, C::NT >= 512 ? 1 : 2) k_photometric(con
     t.cta = (int)((bz * gridDim.y + by) * gridDim.x + bx);
   }
   const int tid = threadIdx.x;
-  const size_t img_off = (size_t)t.b * 3 * p.H * p.W;
-
   // Global reads whose addresses do not depend on computed values are issued as asynchronous copies well
   // before their phase: disp_s window (one scale ahead), tie-break noise (a phase ahead), image tiles.
   phase_stage_disp<C>(p, t, sm, 0, tid);
@@ -115,14 +113,10 @@ __global__ void __launch_bounds__(C::NT, C::NT >= 512 ? 1 : 2) k_photometric(con
     phase_target_stats<C>(p, t, sm, tid);
     if (p.automask) phase_identity<C>(p, g, t, sm, tid);
   } else {
-    phase_load_region<C>(p, t, (const typename C::Img*)p.tgt + img_off, sm + C::oT, tid);
+    phase_load_tiles<C>(p, t, sm, tid, p.automask != 0);
     __syncthreads();
     phase_target_stats<C>(p, t, sm, tid);
-    if (p.automask) {
-      phase_load_sources<C>(p, t, sm, tid);
-      __syncthreads();
-      phase_identity<C>(p, g, t, sm, tid);
-    }
+    if (p.automask) phase_identity<C>(p, g, t, sm, tid);
   }
 
   float* red = sm + C::oRed;
@@ -151,9 +145,16 @@ __global__ void __launch_bounds__(C::NT, C::NT >= 512 ? 1 : 2) k_photometric(con
     stage_wait<0>();
     __syncthreads();
     if (s + 1 < p.S) phase_stage_disp<C>(p, t, sm, s + 1, tid);  // the adjoint reads the saved depth, not disp
+    float pre[3];
+    if constexpr (!C::kStageImg) {
+      if (s + 1 < p.S) phase_prefetch_level<C>(p, t, s + 1, tid, pre);  // lands during the window phase
+    }
     if constexpr (C::AVG) phase_windows_avg<C>(p, g, t, sm, s, tid, ts);
     else if constexpr (C::F == 2) phase_windows_paired<C>(p, g, t, sm, s, tid, ts);
     else phase_windows<C>(p, g, t, sm, s, tid, ts);
+    if constexpr (!C::kStageImg) {
+      if (s + 1 < p.S) phase_store_level<C>(sm, tid, pre);  // phase_smooth of this scale is done with the buffer (barrier above)
+    }
     __syncthreads();
     if (!p.forward_only) phase_backward<C>(p, g, t, sm, s, tid, ts);
     // deterministic block reduction of (loss, dP) -> one partial per CTA and scale
@@ -568,7 +569,6 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     return VSL_ERR_UNSUPPORTED;
   const bool fwd_only = (d->flags & VSL_FLAG_FORWARD_ONLY) != 0;
   const bool avg = (d->flags & VSL_FLAG_AVG_REPROJECTION) && d->num_src > 1;  // the mean of one frame is the frame
-  if (avg && d->image_dtype != VSL_DTYPE_F32) return VSL_ERR_UNSUPPORTED;   // avg + bf16 storage: not instantiated
   if (d->image_dtype != VSL_DTYPE_F32 && d->image_dtype != VSL_DTYPE_BF16) return VSL_ERR_UNSUPPORTED;
   if (d->num_src > 3) return VSL_ERR_UNSUPPORTED;
   const bool automask = (d->flags & VSL_FLAG_AUTOMASK) != 0;
@@ -604,7 +604,6 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   pp.pose_per_scale = 0;
   for (int s = 0; s < S; ++s)
     for (int f = 0; f < F; ++f) pp.pose_per_scale |= buf->T_scale[s][f] != nullptr;
-  if (pmask && d->image_dtype != VSL_DTYPE_F32) return VSL_ERR_UNSUPPORTED;  // predictive mask + bf16 storage: not instantiated
   pp.no_ssim = (d->flags & VSL_FLAG_NO_SSIM) ? 1 : 0;
   pp.forward_only = fwd_only ? 1 : 0;
   pp.invK = buf->inv_K;
@@ -666,14 +665,21 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   VSL_CUDA_OK(cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), st));
   if (event_before) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_before, st));
   int rc;
+  const bool bf16 = d->image_dtype == VSL_DTYPE_BF16;
   if (pmask) {  // --predictive_mask kernels: run-time rounding selectors only (one instantiation each)
-    if (avg && F == 2) rc = launch_photometric_impl<TileCfg<32, 16, 2, 256, float, true, true>, false>(pp, pl, d->batch, st);
-    else if (avg) rc = launch_photometric_impl<TileCfg<32, 8, 3, 256, float, true, true>, false>(pp, pl, d->batch, st);
-    else if (F == 1) rc = launch_photometric_impl<TileCfg<32, 16, 1, 256, float, false, true>, false>(pp, pl, d->batch, st);
-    else if (F == 2) rc = launch_photometric_impl<TileCfg<32, 16, 2, 256, float, false, true>, false>(pp, pl, d->batch, st);
-    else rc = launch_photometric_impl<TileCfg<32, 8, 3, 256, float, false, true>, false>(pp, pl, d->batch, st);
+#define VSL_PMASK_LAUNCH(IMG)                                                                                                  \
+    if (avg && F == 2) rc = launch_photometric_impl<TileCfg<32, 16, 2, 256, IMG, true, true>, false>(pp, pl, d->batch, st);    \
+    else if (avg) rc = launch_photometric_impl<TileCfg<32, 8, 3, 256, IMG, true, true>, false>(pp, pl, d->batch, st);          \
+    else if (F == 1) rc = launch_photometric_impl<TileCfg<32, 16, 1, 256, IMG, false, true>, false>(pp, pl, d->batch, st);     \
+    else if (F == 2) rc = launch_photometric_impl<TileCfg<32, 16, 2, 256, IMG, false, true>, false>(pp, pl, d->batch, st);     \
+    else rc = launch_photometric_impl<TileCfg<32, 8, 3, 256, IMG, false, true>, false>(pp, pl, d->batch, st);
+    if (bf16) { VSL_PMASK_LAUNCH(bf16_t) } else { VSL_PMASK_LAUNCH(float) }
+#undef VSL_PMASK_LAUNCH
   } else if (avg) {
-    if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, float, true>>(pp, pl, d->batch, st);
+    if (bf16) {  // rarely used together: run-time rounding selectors only
+      if (F == 2) rc = launch_photometric_impl<TileCfg<32, 16, 2, 256, bf16_t, true>, false>(pp, pl, d->batch, st);
+      else rc = launch_photometric_impl<TileCfg<32, 8, 3, 256, bf16_t, true>, false>(pp, pl, d->batch, st);
+    } else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, float, true>>(pp, pl, d->batch, st);
     else rc = launch_photometric<TileCfg<32, 8, 3, 256, float, true>>(pp, pl, d->batch, st);
   } else if (d->image_dtype == VSL_DTYPE_BF16) {
     if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256, bf16_t>>(pp, pl, d->batch, st);

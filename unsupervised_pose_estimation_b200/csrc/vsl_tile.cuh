@@ -88,9 +88,11 @@ struct TileCfg {
   static constexpr int oRedS = oZ + IN;         // per-warp smoothness sums [NT/32][4]
   // target pyramid pixels under the tile's own pixels of a level s >= 1, +1 halo (smoothness edge weights)
   static constexpr int SW = TW / 2 + 2, SH = TH / 2 + 2, SN = SW * SH;
-  static constexpr bool kStageImg = sizeof(Img_) == 4;  // fp32 images only (bf16 needs a conversion: read directly)
+  // fp32 images are staged with asynchronous copies; bf16 images need a conversion, so their tiles are loaded into
+  // registers in one batch (phase_load_tiles) and their level pixels are prefetched into registers a phase ahead
+  static constexpr bool kStageImg = sizeof(Img_) == 4;
   static constexpr int oImgS = oRedS + (NT / 32) * 4;   // [3][SN]
-  static constexpr int kFloats = oImgS + (kStageImg ? 3 * SN : 0);
+  static constexpr int kFloats = oImgS + 3 * SN;
   static constexpr int kBytes = kFloats * 4;
   static constexpr int kPartial = 1 + F * 12;   // photometric partials per (CTA, scale): loss, dL/dP
   static constexpr int kPartialAll = kPartial + 4;  // + smoothness: sum d, sum |dx| e, sum |dy| e, sum g d
@@ -194,6 +196,78 @@ VSL_HD void phase_stage_noise(const PhotoParams& p, const TileCtx& t, float* __r
     }
   }
   stage_commit();
+}
+
+template <class C>
+struct XLayout;  // defined below
+
+// ---- bf16 images: the level-s target pixels phase_smooth reads (same window as phase_stage_disp stages for
+// fp32), loaded into registers a phase ahead and parked in shared memory once the phase in between is done
+template <class C>
+VSL_HD void phase_prefetch_level(const PhotoParams& p, const TileCtx& t, int s, int tid, float (&pre)[3]) {
+  pre[0] = pre[1] = pre[2] = 0.f;
+  if (!(p.gsmooth[s] && !p.identity_scale[s])) return;
+  const int e = p.level_shift[s], hs = p.hs[s], ws = p.ws[s];
+  const int oy = (t.y0 >> e) - 1, ox = (t.x0 >> e) - 1, nrow = (C::TH >> e) + 2, ncol = (C::TW >> e) + 2;
+  const int ry = tid / C::SW, rx = tid - ry * C::SW;
+  if (ry >= nrow || rx >= ncol) return;
+  int yy = oy + ry, xx = ox + rx;
+  yy = yy < 0 ? 0 : (yy > hs - 1 ? hs - 1 : yy);
+  xx = xx < 0 ? 0 : (xx > ws - 1 ? ws - 1 : xx);
+  const typename C::Img* img = (const typename C::Img*)p.tgts[s] + (size_t)t.b * 3 * hs * ws + yy * ws + xx;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pre[c] = ldimg(img, (size_t)c * hs * ws);
+}
+template <class C>
+VSL_HD void phase_store_level(float* __restrict__ sm, int tid, const float (&pre)[3]) {
+  static_assert(C::NT >= C::SN, "one level pixel per thread");
+  if (tid < C::SN) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sm[C::oImgS + c * C::SN + tid] = pre[c];
+  }
+}
+
+// ---- bf16 images: target and source tiles (+2 halo, reflect-mapped) in ONE batch of loads -------------
+// Same placement as phase_load_region + phase_load_sources; every load of the thread is issued before the
+// first converted value is stored, so the tile costs one global-memory round trip instead of one per image.
+template <class C>
+VSL_HD void phase_load_tiles(const PhotoParams& p, const TileCtx& t, float* __restrict__ sm, int tid, bool sources) {
+  using XL = XLayout<C>;
+  typedef typename C::Img Img;
+  constexpr int IT = (C::RN + C::NT - 1) / C::NT;
+  float* T = sm + C::oT;
+  float* X = sm + C::oX;
+  const int HW = p.H * p.W;
+  const size_t img_off = (size_t)t.b * 3 * HW;
+  float v[IT][(1 + C::F) * 3];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid + it * C::NT;
+    const int ry = i / C::RW, rx = i - ry * C::RW;
+    const int gy = t.y0 - 2 + ry, gx = t.x0 - 2 + rx;
+    const bool valid = i < C::RN && gy >= -1 && gy <= p.H && gx >= -1 && gx <= p.W;
+    const int o = reflect1(gy, p.H) * p.W + reflect1(gx, p.W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[it][c] = valid ? ldimg((const Img*)p.tgt, img_off + c * HW + o) : 0.f;
+#pragma unroll
+      for (int f = 0; f < C::F; ++f)
+        v[it][(1 + f) * 3 + c] = (valid && sources) ? ldimg((const Img*)p.src[f], img_off + c * HW + o) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid + it * C::NT;
+    if (i >= C::RN) continue;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T[c * C::RN + i] = v[it][c];
+      if (sources) {
+#pragma unroll
+        for (int f = 0; f < C::F; ++f) X[XL::at(f, c, i)] = v[it][(1 + f) * 3 + c];
+      }
+    }
+  }
 }
 
 // ---- phase: load an image tile + 2 halo into a region buffer, reflect-mapped --------------------
@@ -579,7 +653,6 @@ VSL_HD void phase_smooth(const PhotoParams& p, const TileCtx& t, const float* __
   const int hs = p.hs[s], ws = p.ws[s], n = hs * ws;
   int cy0, cx0, rows, cols;
   disp_window<C>(p, t, s, cy0, cx0, rows, cols);
-  const typename C::Img* img = (const typename C::Img*)p.tgts[s] + (size_t)t.b * 3 * n;
   float* g_out = p.gsmooth[s] + (size_t)t.b * n;
   const float cx = 1.0f / ((float)p.B * hs * (ws - 1)), cy = 1.0f / ((float)p.B * (hs - 1) * ws);
   const bool from_tile = p.identity_scale[s] != 0;  // level 0: the target tile is in shared memory
@@ -594,8 +667,7 @@ VSL_HD void phase_smooth(const PhotoParams& p, const TileCtx& t, const float* __
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         v[c] = from_tile ? T[c * C::RN + (iy + 2 + dy) * C::RW + (ix + 2 + dx)]
-               : C::kStageImg ? sm[C::oImgS + c * C::SN + (iy + 1 + dy) * C::SW + (ix + 1 + dx)]
-                              : ldimg(img, (size_t)c * n + o + dy * ws + dx);
+               : sm[C::oImgS + c * C::SN + (iy + 1 + dy) * C::SW + (ix + 1 + dx)];
     };
     float c0[3], cn[3];
     pixel(0, 0, c0);
@@ -889,6 +961,7 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
     }
   }
 }
+
 #endif
 
 // ---- phase: adjoint for the interior pixels of scale s -------------------------------------------
