@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VSL_ABI_VERSION 2
+#define VSL_ABI_VERSION 3
 #define VSL_MAX_SCALES 4
 #define VSL_MAX_SRC 4
 
@@ -141,6 +141,11 @@ typedef struct VslLossBuffers {
   float* side_depth[VSL_MAX_SCALES];                /* outputs[("depth",0,s)]   [B,1,H,W]                    */
   float* side_sample[VSL_MAX_SCALES][VSL_MAX_SRC];  /* outputs[("sample",f,s)]  [B,H,W,2]                    */
   float* side_color[VSL_MAX_SCALES][VSL_MAX_SRC];   /* outputs[("color",f,s)]   [B,3,H,W]                    */
+  /* optional: the arg-min CHANNEL of trainer.py:663-666 per pixel and scale [B,H,W] (the mask above only says
+   * whether a warped frame won).  0..F-1: identity candidate of source frame f; F..2F-1: warped frame f-F; with
+   * VSL_FLAG_AVG_REPROJECTION 0 = identity mean, 1 = warped mean.  Needed for the source-image gradient
+   * (vsl_source_grad_upstream); may be null.                                                                */
+  uint8_t* winner[VSL_MAX_SCALES];
 } VslLossBuffers;
 
 size_t vsl_loss_workspace_bytes(const VslDesc* desc);
@@ -230,6 +235,29 @@ int vsl_smooth_loss_forward(int batch, int height, int width, const float* disp,
 /* grad_loss: device scalar */
 int vsl_smooth_loss_backward(int batch, int height, int width, const float* disp, const float* img,
                              const float* grad_loss, float* grad_disp, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Gradient with respect to the SOURCE IMAGES (optional; the reference's autograd produces it whenever
+ * inputs[("color", f, 0)] requires grad: through F.grid_sample's backward for the warped candidates,
+ * trainer.py:534-537, and through the identity reprojection losses, trainer.py:620-633).  Composed by the
+ * host layer from: the `winner` maps of the fused call, vsl_source_grad_upstream (what each candidate's
+ * reprojection loss receives from the loss dict), vsl_reprojection_loss_backward (d loss / d pred), and
+ * vsl_grid_sample_backward_source (the bilinear scatter into the source image).
+ * ------------------------------------------------------------------------------------ */
+/* upstream [2S+1] (device; same vector as vsl_loss_combine_grads).  Writes, per pixel,
+ *   up_warped[s][f][B,H,W] = a_s / (B H W) where warped frame f won at scale s, else 0
+ *   up_identity[f][B,H,W]  = sum_s a_s / (B H W) where identity candidate f won at scale s   (null without automask)
+ * with a_s = upstream[s] + upstream[S+s] + upstream[2S]/S; with VSL_FLAG_AVG_REPROJECTION every frame receives
+ * 1/F of its candidate's weight. */
+int vsl_source_grad_upstream(const VslDesc* desc, const float* upstream, const uint8_t* const winner[VSL_MAX_SCALES],
+                             float* up_identity, float* const up_warped[VSL_MAX_SCALES], void* stream);
+/* Adjoint of F.grid_sample(source, grid, padding_mode="border", align_corners=True) with respect to `source`:
+ * grad_source [B,3,H,W] += scatter of grad_pred [B,3,H,W] through the four bilinear taps of grid [B,H,W,2]
+ * (ATen grid_sampler_2d_backward's safe_add_2d).  A CTA accumulates the taps that land near its tile in shared
+ * memory and flushes them with one red.global.add.f32 per touched source pixel; far taps go to global memory
+ * directly.  Float atomics: the summation order is not fixed (neither is PyTorch's). */
+int vsl_grid_sample_backward_source(int batch, int height, int width, const float* grid, const float* grad_pred,
+                                    float* grad_source, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Input pipeline: 8-bit frames -> the ("color", f, s) pyramid.

@@ -424,6 +424,47 @@ def test_full_size_side_outputs(config):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("case", [
+    (2, 64, 96, [0, -1, 1], "iid", {}),
+    (2, 64, 96, [0, -1, 1], "smooth", {}),
+    (2, 192, 640, [0, -1, 1], "smooth", {}),                      # C1 shape
+    (2, 64, 96, [0, -1, 1, "s"], "smooth", {}),
+    (2, 40, 72, [0, 1], "iid", {"scales": [0, 2]}),                # ragged tiles, one source frame
+    (2, 64, 96, [0, -1, 1], "iid", {"disable_automasking": True}),
+    (2, 64, 96, [0, -1, 1], "smooth", {"avg_reprojection": True}),
+    (2, 64, 96, [0, -1, 1], "iid", {"no_ssim": True}),
+    (2, 64, 96, [0, -1, 1], "smooth", {"v1_multiscale": True}),
+])
+def test_source_image_gradients(case):
+    """Gradient with respect to the source images (north_star: "scatters warp gradients into the source image"):
+    when inputs[("color", f, 0)] requires grad the reference's autograd returns it through grid_sample's backward
+    (trainer.py:534-537) and the identity losses (trainer.py:620-633).  1e-5 rel-L2 against the oracle's autograd
+    (both sides accumulate with float atomics, so the comparison has a tolerance); the other gradients and the
+    losses are unchanged by asking for it."""
+    B, H, W, frames, family, o = case
+    opt = O.make_opt(height=H, width=W, batch_size=B, frame_ids=list(frames), **o)
+    inputs, outputs, leaves = synthetic.make_batch(B, H, W, frames, synthetic.K_KITTI, seed=77, family=family, device=DEV)
+    base_out, base_l, base_g = run_ours(opt, inputs, outputs, leaves, side="none")
+    src_keys = [("color", f, s) for f in frames[1:] for s in (opt.scales if opt.v1_multiscale else [0])]
+    inputs = dict(inputs)
+    for k in src_keys:
+        inputs[k] = inputs[k].clone().requires_grad_(True)
+    all_leaves = dict(leaves)
+    all_leaves.update({k: inputs[k] for k in src_keys})
+    ref_out, ref_l, ref_g = run_oracle(opt, inputs, outputs, all_leaves)
+    out, losses, g = run_ours(opt, inputs, outputs, all_leaves, side="none")
+    for k in ref_l:
+        assert torch.equal(losses[k], base_l[k]), k
+    assert set(g) == set(ref_g)
+    for k in ref_g:
+        err = ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item()
+        assert err <= (1e-5 if k in src_keys else 5e-5), (k, err)
+        if k in base_g:
+            assert torch.equal(g[k], base_g[k]), k
+    for k in src_keys:
+        assert g[k].abs().max().item() > 0
+
+
 def test_backward_is_linear_in_the_upstream_gradient():
     """Every entry of the loss dict is differentiable (trainer.py:672-685), not just losses['loss']."""
     opt, inputs, outputs, leaves = build_case("mono_iid_64x96")

@@ -9,7 +9,7 @@ import ctypes
 import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
 
-VSL_ABI_VERSION = 2
+VSL_ABI_VERSION = 3
 VSL_MAX_SCALES = 4
 VSL_MAX_SRC = 4
 
@@ -47,6 +47,7 @@ EXPORTED_SYMBOLS = [
     "vsl_reprojection_loss_forward", "vsl_reprojection_loss_backward",
     "vsl_smooth_workspace_bytes", "vsl_smooth_loss_forward", "vsl_smooth_loss_backward",
     "vsl_pyramid_workspace_bytes", "vsl_pyramid_plan", "vsl_pyramid_forward", "vsl_pyramid_coefficients",
+    "vsl_source_grad_upstream", "vsl_grid_sample_backward_source",
 ]
 
 
@@ -71,6 +72,7 @@ class VslLossBuffers(Structure):
         ("smooth_norm", c_void_p), ("grad_P", c_void_p), ("grad_predictive_mask", c_void_p * VSL_MAX_SCALES),
         ("side_depth", c_void_p * VSL_MAX_SCALES), ("side_sample", (c_void_p * VSL_MAX_SRC) * VSL_MAX_SCALES),
         ("side_color", (c_void_p * VSL_MAX_SRC) * VSL_MAX_SCALES),
+        ("winner", c_void_p * VSL_MAX_SCALES),
     ]
 
 
@@ -153,6 +155,9 @@ def load():
     lib.vsl_pyramid_forward.argtypes = [POINTER(VslPyramidDesc), vp, POINTER(c_void_p * VSL_MAX_SCALES),
                                         POINTER(c_void_p * VSL_MAX_SCALES), vp, c_size_t, vp]
     lib.vsl_pyramid_coefficients.argtypes = [c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_int]
+    lib.vsl_source_grad_upstream.argtypes = [POINTER(VslDesc), vp, POINTER(c_void_p * VSL_MAX_SCALES), vp,
+                                             POINTER(c_void_p * VSL_MAX_SCALES), vp]
+    lib.vsl_grid_sample_backward_source.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
     _LIB = lib
     return lib
 

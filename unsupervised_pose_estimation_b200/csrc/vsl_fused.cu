@@ -627,6 +627,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
     pp.disp[s] = sp.disp[s] = buf->disp[s];
     pp.noise[s] = buf->noise[s];
     pp.mask[s] = automask ? buf->mask[s] : nullptr;
+    pp.winner[s] = buf->winner[s];
     pp.pmask[s] = automask ? nullptr : buf->predictive_mask[s];  // the reference only uses it without automasking
     pp.gpmask[s] = (pp.pmask[s] && !fwd_only) ? buf->grad_predictive_mask[s] : nullptr;
     if (pp.pmask[s] && !pp.gpmask[s] && !fwd_only) return VSL_ERR_NULL_POINTER;

@@ -31,6 +31,7 @@ struct PhotoParams {
                                   // whose translation is rescaled by each level's mean inverse depth (trainer.py:516-525)
   const float* noise[kMaxScales]; // [B,F,H,W]
   float* mask[kMaxScales];        // [B,H,W] or null
+  unsigned char* winner[kMaxScales];  // [B,H,W] or null: arg-min channel (identity f: f, warped f: F + f; AVG: 0 / 1)
   const float* pmask[kMaxScales]; // [B,F,H,W] --predictive_mask, already at the warp resolution; or null
   float* gpmask[kMaxScales];      // [B,F,H,W] d(min_loss/s)/d pmask
   float* gD[kMaxScales];          // identity levels: [B,H,W] d(min_loss/s)/d disp_s, written directly
@@ -804,6 +805,7 @@ VSL_HD void phase_windows_avg(const PhotoParams& p, const GeoConst& g, const Til
     if (interior) {
       ts.loss += warped ? avg : best;
       if (p.mask[s]) p.mask[s][(size_t)t.b * HW + gy * p.W + gx] = warped ? 1.f : 0.f;
+      if (p.winner[s]) p.winner[s][(size_t)t.b * HW + gy * p.W + gx] = warped ? 1 : 0;
 #pragma unroll
       for (int f = 0; f < C::F; ++f)
         store_gpmask<C>(p, t, s, f, gy, gx, warped ? p.wpix * (1.0f / (float)C::F) * lraw[f] : 0.f);
@@ -885,6 +887,7 @@ VSL_HD void phase_windows(const PhotoParams& p, const GeoConst& g, const TileCtx
     if (interior) {
       ts.loss += best;
       if (p.mask[s]) p.mask[s][(size_t)t.b * HW + gy * p.W + gx] = warped ? 1.f : 0.f;
+      if (p.winner[s]) p.winner[s][(size_t)t.b * HW + gy * p.W + gx] = (unsigned char)bidx;
 #pragma unroll
       for (int f = 0; f < C::F; ++f)
         store_gpmask<C>(p, t, s, f, gy, gx, (warped && bidx - C::F == f) ? p.wpix * lraw[f] : 0.f);
@@ -917,12 +920,14 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
     int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
     const bool inside = live && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
     float best = INFINITY, l = INFINITY, lraw = 0.f, m = 1.0f;
+    bool id1 = false;  // the second identity candidate is the better one
     SsimOut so[3];
     if (inside) {
       if (p.automask) {
         float c0 = add_rn(Id[i], mul_rn(sm[C::oNz + i], 1e-5f));
         float c1 = add_rn(Id[C::WN + i], mul_rn(sm[C::oNz + C::WN + i], 1e-5f));
-        best = c1 < c0 ? c1 : c0;
+        id1 = c1 < c0;
+        best = id1 ? c1 : c0;
       }
       l = lraw = reproj_window<C, 2>(X + XL::pair_base(0, 0) + f, 2 * C::RN, T, TS, wy, wx, i, g.arith, so, p.no_ssim != 0);
       if (has_pmask<C>(p, s)) {
@@ -957,6 +962,7 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
       if (f == 0) {
         ts.loss += mn;
         if (p.mask[s]) p.mask[s][(size_t)t.b * HW + gy * p.W + gx] = win >= 0 ? 1.f : 0.f;
+        if (p.winner[s]) p.winner[s][(size_t)t.b * HW + gy * p.W + gx] = (unsigned char)(win >= 0 ? 2 + win : (id1 ? 1 : 0));
       }
     }
   }

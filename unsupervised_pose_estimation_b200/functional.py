@@ -257,8 +257,13 @@ class _FusedLoss(torch.autograd.Function):
     """losses vector [2S+1] = (min_loss/s ..., loss/s ..., loss), masks...  <- disps, P matrices."""
 
     @staticmethod
-    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, n_pmask, side, fwd_only, *leaves):
+    def forward(ctx, plan, targets, sources, inv_K, noise, want_mask, K, use_T, n_pmask, side, fwd_only, n_srcgrad,
+                *leaves):
         S, F = len(plan.scales), plan.num_src
+        # n_srcgrad == F: the last F leaves are the source images themselves (they require grad: the optional
+        # source-image gradient, see backward); they are read through `sources` like always
+        if n_srcgrad:
+            leaves = leaves[:len(leaves) - n_srcgrad]
         # the masks are non-differentiable outputs: without this autograd hands backward() a zero-filled
         # [B,H,W] tensor per mask (four 5.9 MB fill kernels per step at config 1)
         ctx.set_materialize_grads(False)
@@ -272,7 +277,7 @@ class _FusedLoss(torch.autograd.Function):
         dev = disps[0].device
         B, H, W = plan.batch, plan.height, plan.width
         buf = VslLossBuffers()
-        keep = []
+        keep, src_c, tgt0_c = [], [], None
         for s in range(S):
             t = _dev(targets[s], "target[%d]" % s, plan.image_dtype)
             d = _dev(disps[s], "disp[%d]" % s)
@@ -282,6 +287,8 @@ class _FusedLoss(torch.autograd.Function):
                 raise ValueError("target[%d] has shape %s" % (s, tuple(t.shape)))
             buf.target[s], buf.disp[s] = t.data_ptr(), d.data_ptr()
             keep += [t, d]
+            if s == 0:
+                tgt0_c = t
             if plan.automask:
                 z = _dev(noise[s], "noise[%d]" % s)
                 if tuple(z.shape) != (B, plan.noise_channels, H, W):
@@ -294,6 +301,7 @@ class _FusedLoss(torch.autograd.Function):
                 raise ValueError("source[%d] has shape %s" % (f, tuple(src.shape)))
             buf.source[f] = src.data_ptr()
             keep.append(src)
+            src_c.append(src)
             for s in range(S if per_scale else 1):
                 P = _dev(Ps[s * F + f], "T[%d]" % f if use_T else "P[%d]" % f)
                 if tuple(P.shape) != ((B, 4, 4) if use_T else (B, 3, 4)):
@@ -333,6 +341,23 @@ class _FusedLoss(torch.autograd.Function):
                     gpm.append(gm)
             ctx.gpm = gpm
         ctx.n_pmask = n_pmask
+        ctx.n_srcgrad = n_srcgrad
+        if n_srcgrad and not fwd_only:
+            # the backward needs every warped image and sampling grid plus the arg-min channel per pixel
+            if n_pmask:
+                raise NotImplementedError("source-image gradients are not implemented together with --predictive_mask")
+            if plan.image_dtype != torch.float32:
+                raise NotImplementedError("source-image gradients need fp32 image storage")
+            side = dict(side or {})
+            for name, shape in (("sample", (B, H, W, 2)), ("color", (B, 3, H, W))):
+                cur = side.get(name) or [[None] * F for _ in range(S)]
+                side[name] = [[cur[s][f] if cur[s][f] is not None else torch.empty(shape, dtype=torch.float32, device=dev)
+                               for f in range(F)] for s in range(S)]
+            ctx.winner = [torch.empty(B, H, W, dtype=torch.uint8, device=dev) for _ in range(S)]
+            for s in range(S):
+                buf.winner[s] = ctx.winner[s].data_ptr()
+            ctx.src_side = side
+            ctx.src_images = (tgt0_c, src_c)
         if side is not None:
             # side outputs of generate_images_pred, written in place by the kernel (no autograd edge: the
             # reference's own use of them is inside the loss this call computes)
@@ -389,7 +414,7 @@ class _FusedLoss(torch.autograd.Function):
         plan = ctx.plan
         S, F, B = len(plan.scales), plan.num_src, plan.batch
         if gvec is None:  # no loss entry was used (grads are not materialised, see forward)
-            return (None,) * (11 + S + (S if ctx.use_T == "per_scale" else 1) * F + ctx.n_pmask)
+            return (None,) * (12 + S + (S if ctx.use_T == "per_scale" else 1) * F + ctx.n_pmask + ctx.n_srcgrad)
         ctx.saved_tensors  # version-counter check of the buffers `ctx.buf` points at
         dev = gvec.device
         up = _dev(gvec, "upstream gradient")
@@ -414,7 +439,56 @@ class _FusedLoss(torch.autograd.Function):
             # (the same a_s vsl_loss_combine_grads uses; tiny torch arithmetic on the [2S+1] vector)
             a = up[:S] + up[S:2 * S] + up[2 * S] / S
             gpm = tuple(ctx.gpm[s] * a[s] for s in range(S))
-        return (None, None, None, None, None, None, None, None, None, None, None) + tuple(gd) + tuple(gPs) + gpm
+        gsrc = ()
+        if ctx.n_srcgrad:
+            gsrc = _source_image_grads(ctx, plan, up)
+        return (None,) * 12 + tuple(gd) + tuple(gPs) + gpm + gsrc
+
+
+def _source_image_grads(ctx, plan, up):
+    """d L / d inputs[("color", f, 0)] per source frame (what the reference's autograd returns when the source
+    images require grad): identity candidates directly (trainer.py:620-633), warped candidates through the
+    bilinear scatter (grid_sample's backward, trainer.py:534-537).  Per frame and scale: what the candidate's
+    reprojection loss receives from the loss dict (vsl_source_grad_upstream, from the arg-min channel the fused
+    kernel recorded) -> d/d pred (vsl_reprojection_loss_backward) -> scatter (vsl_grid_sample_backward_source)."""
+    lib = plan.lib
+    S, F, B, H, W = len(plan.scales), plan.num_src, plan.batch, plan.height, plan.width
+    dev = up.device
+    target, sources = ctx.src_images
+    automask = plan.automask
+    no_ssim = 1 if (plan.desc.flags & _lib.FLAG_NO_SSIM) else 0
+    up_id = torch.empty(F, B, H, W, dtype=torch.float32, device=dev) if automask else None
+    up_w = [torch.empty(F, B, H, W, dtype=torch.float32, device=dev) for _ in range(S)]
+    wptr = (ctypes.c_void_p * VSL_MAX_SCALES)()
+    uptr = (ctypes.c_void_p * VSL_MAX_SCALES)()
+    for s in range(S):
+        wptr[s], uptr[s] = ctx.winner[s].data_ptr(), up_w[s].data_ptr()
+    check(lib.vsl_source_grad_upstream(ctypes.byref(plan.desc), up.data_ptr(), ctypes.byref(wptr), ptr(up_id),
+                                       ctypes.byref(uptr), _stream()), "vsl_source_grad_upstream")
+    nbytes = 0 if no_ssim else lib.vsl_ssim_workspace_bytes(B, 3, H, W)
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+    tmp = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
+    out = []
+    for f in range(F):
+        if not ctx.needs_input_grad[len(ctx.needs_input_grad) - F + f]:
+            out.append(None)
+            continue
+        if automask:
+            g = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
+            check(lib.vsl_reprojection_loss_backward(B, H, W, no_ssim, sources[f].data_ptr(), target.data_ptr(),
+                                                     up_id[f].data_ptr(), g.data_ptr(), None, ws.data_ptr(), nbytes,
+                                                     _stream()), "vsl_reprojection_loss_backward")
+        else:
+            g = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev)
+        for s in range(S):
+            color, grid = ctx.src_side["color"][s][f], ctx.src_side["sample"][s][f]
+            check(lib.vsl_reprojection_loss_backward(B, H, W, no_ssim, color.data_ptr(), target.data_ptr(),
+                                                     up_w[s][f].data_ptr(), tmp.data_ptr(), None, ws.data_ptr(), nbytes,
+                                                     _stream()), "vsl_reprojection_loss_backward")
+            check(lib.vsl_grid_sample_backward_source(B, H, W, grid.data_ptr(), tmp.data_ptr(), g.data_ptr(), _stream()),
+                  "vsl_grid_sample_backward_source")
+        out.append(g)
+    return tuple(out)
 
 
 def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, K=None, Ts=None,
@@ -437,9 +511,14 @@ def fused_loss(plan, targets, sources, disps, inv_K, Ps, noise, want_mask=True, 
         poses = [T for per_frame in poses for T in per_frame]
     pm = list(predictive_masks or [])
     leaves = list(disps) + poses + pm
+    # optional: gradients with respect to the source images (the reference's autograd gives them whenever
+    # inputs[("color", f, 0)] requires grad); the images then travel as autograd leaves as well
+    n_srcgrad = len(sources) if torch.is_grad_enabled() and any(t.requires_grad for t in sources) else 0
+    if n_srcgrad:
+        leaves = leaves + list(sources)
     fwd_only = not (torch.is_grad_enabled() and any(t.requires_grad for t in leaves))
-    res = _FusedLoss.apply(plan, list(targets), list(sources), inv_K, list(noise or []), bool(want_mask), K, use_T,
-                           len(pm), side, fwd_only, *leaves)
+    res = _FusedLoss.apply(plan, list(targets), [t.detach() for t in sources], inv_K, list(noise or []), bool(want_mask),
+                           K, use_T, len(pm), side, fwd_only, n_srcgrad, *leaves)
     return res[0], list(res[1:])
 
 
