@@ -260,6 +260,32 @@ int vsl_grid_sample_backward_source(int batch, int height, int width, const floa
                                     float* grad_source, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Depth metrics and the GAN prior's loss: the losses / metrics next to the path.
+ * One caller-owned workspace of vsl_metrics_workspace_bytes() bytes (8-byte aligned) serves every call below;
+ * results stay on the device.  Reductions run in a fixed order (reproducible); medians are exact.
+ * ------------------------------------------------------------------------------------ */
+size_t vsl_metrics_workspace_bytes(void);
+/* compute_depth_errors (layers.py:335-353): gt, pred [n], all positive ->
+ * out7 = abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3 */
+int vsl_depth_errors(size_t n, const float* gt, const float* pred, float* out7, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* Trainer.compute_depth_losses (trainer.py:688-716): depth_pred = outputs[("depth",0,0)] [B,1,h,w] is up-sampled
+ * (bilinear, align_corners=False) to depth_gt's size [B,1,gt_h,gt_w] and clamped to [clamp_min, clamp_max]; pixels
+ * with depth_gt > 0 inside crop = {y0, y1, x0, x1} (half-open; the reference's Garg/Eigen crop is
+ * {153, 371, 44, 1197} at 375 x 1242) are kept, the prediction is scaled by median(gt) / median(pred) (torch.median:
+ * the lower median), clamped again, and the seven metrics of compute_depth_errors are written to out7. */
+int vsl_depth_losses(int batch, int height, int width, int gt_height, int gt_width, const int crop[4],
+                     float clamp_min, float clamp_max, const float* depth_pred, const float* depth_gt, float* out7,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* SLlog.forward (layers.py:32-56; used as self.si_loss(fake_disp_scaled, disp), trainer.py:579): fake, real [n]
+ * -> loss (device scalar); stats3 = (N, mean of the log differences, loss) is kept for the backward. */
+int vsl_sllog_forward(size_t n, const float* fake, const float* real, float* loss, float* stats3, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* its backward: grad_loss (device scalar) -> grad_fake, grad_real [n] (either may be null) */
+int vsl_sllog_backward(size_t n, const float* fake, const float* real, const float* stats3, const float* grad_loss,
+                       float* grad_fake, float* grad_real, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Input pipeline: 8-bit frames -> the ("color", f, s) pyramid.
  * Replaces MonoDataset.preprocess (datasets/mono_dataset2.py:103-124): level s =
  * transforms.Resize((H // 2^s, W // 2^s), Image.ANTIALIAS)(level s-1) on 8-bit PIL images

@@ -213,9 +213,9 @@ def generate_images_pred(opt, inputs, outputs):
                 outputs[("color_identity", frame_id, scale)] = inputs[("color", frame_id, src_scale)]
 
 
-def compute_losses(opt, inputs, outputs, noise=None):
-    """trainer.py:557-686 (photometric + smoothness part; the GAN-prior term at :565-583
-    is off unless --pre_trained_generator and is outside the path).
+def compute_losses(opt, inputs, outputs, noise=None, generator=None, gen_transform=None):
+    """trainer.py:557-686.  The GAN-prior term (:565-583, :684) is evaluated only with --pre_trained_generator;
+    ``generator`` / ``gen_transform`` then stand for self.models["pre_trained_generator"] / self.gen_transform.
 
     ``noise``: optional list (one [B,F,H,W] tensor per scale) replacing the reference's
     ``torch.randn`` draw at trainer.py:656-657; ``None`` draws from the global RNG exactly
@@ -223,7 +223,17 @@ def compute_losses(opt, inputs, outputs, noise=None):
     """
     losses = {}
     total = 0
+    gan_total = 0
     n_src = len(opt.frame_ids) - 1
+    if opt.pre_trained_generator:  # trainer.py:565-583
+        from oracle.metrics_oracle import depth_to_disp, sllog
+        fake_B1 = generator(gen_transform(inputs[("color", 0, 0)]))
+        _, fake_disp_scaled = depth_to_disp(fake_B1)
+        for scale in opt.scales:
+            disp = F.interpolate(outputs[("disp", scale)], [opt.height, opt.width], mode="bilinear", align_corners=False)
+            gan_loss = sllog(fake_disp_scaled, disp)
+            losses["gan_loss/{}".format(scale)] = gan_loss
+            gan_total = gan_total + gan_loss
     for si, scale in enumerate(opt.scales):
         loss = 0
         src_scale = scale if opt.v1_multiscale else 0
@@ -277,7 +287,7 @@ def compute_losses(opt, inputs, outputs, noise=None):
         total += loss
         losses["loss/{}".format(scale)] = loss
     total /= len(opt.scales)
-    losses["loss"] = total
+    losses["loss"] = total + gan_total / len(opt.scales) * 0.002   # trainer.py:684
     assert n_src >= 1
     return losses
 

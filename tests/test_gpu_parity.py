@@ -627,9 +627,8 @@ def test_errors_are_loud():
     cpu_inputs[("color", 0, 0)] = inputs[("color", 0, 0)].cpu()
     with pytest.raises(_lib.VslError):
         path.compute_losses(cpu_inputs, out)
-    for flag in ("pre_trained_generator",):
-        with pytest.raises(NotImplementedError):
-            LossPath(make_opt(**{flag: True}), device=DEV).generate_images_pred(inputs, out)
+    with pytest.raises(NotImplementedError):   # the reference itself fails for posecnn + a stereo frame
+        LossPath(make_opt(pose_model_type="posecnn", frame_ids=[0, -1, 1, "s"]), device=DEV).generate_images_pred(inputs, out)
     lib = _lib.load()
     d = _lib.VslDesc()
     assert lib.vsl_loss_forward_backward(ctypes.byref(d), None, None, 0, None) == -1

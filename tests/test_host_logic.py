@@ -48,12 +48,12 @@ def test_layers_reexports_reference_names():
     assert L.ConvBlock(3, 4)(x).shape == (1, 4, 8, 8) and L.upsample(x).shape == (1, 3, 16, 16)
 
 
-@pytest.mark.parametrize("flag", ["pre_trained_generator"])
-def test_unsupported_flags_fail_loudly(flag):
+def test_unsupported_flags_fail_loudly():
+    """posecnn with a stereo frame is the one combination the path refuses (the reference itself fails there)."""
     class P(ViewSynthesisLossMixin):
         pass
     p = P()
-    p.opt = make_opt(**{flag: True})
+    p.opt = make_opt(pose_model_type="posecnn", frame_ids=[0, -1, 1, "s"])
     with pytest.raises(NotImplementedError):
         p._vsl_plan()
 

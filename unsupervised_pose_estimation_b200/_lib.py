@@ -48,6 +48,7 @@ EXPORTED_SYMBOLS = [
     "vsl_smooth_workspace_bytes", "vsl_smooth_loss_forward", "vsl_smooth_loss_backward",
     "vsl_pyramid_workspace_bytes", "vsl_pyramid_plan", "vsl_pyramid_forward", "vsl_pyramid_coefficients",
     "vsl_source_grad_upstream", "vsl_grid_sample_backward_source",
+    "vsl_metrics_workspace_bytes", "vsl_depth_errors", "vsl_depth_losses", "vsl_sllog_forward", "vsl_sllog_backward",
 ]
 
 
@@ -158,6 +159,13 @@ def load():
     lib.vsl_source_grad_upstream.argtypes = [POINTER(VslDesc), vp, POINTER(c_void_p * VSL_MAX_SCALES), vp,
                                              POINTER(c_void_p * VSL_MAX_SCALES), vp]
     lib.vsl_grid_sample_backward_source.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
+    lib.vsl_metrics_workspace_bytes.restype = c_size_t
+    lib.vsl_metrics_workspace_bytes.argtypes = []
+    lib.vsl_depth_errors.argtypes = [c_size_t, vp, vp, vp, vp, c_size_t, vp]
+    lib.vsl_depth_losses.argtypes = [c_int, c_int, c_int, c_int, c_int, POINTER(c_int * 4), c_float, c_float, vp, vp, vp,
+                                     vp, c_size_t, vp]
+    lib.vsl_sllog_forward.argtypes = [c_size_t, vp, vp, vp, vp, vp, c_size_t, vp]
+    lib.vsl_sllog_backward.argtypes = [c_size_t, vp, vp, vp, vp, vp, vp, vp]
     _LIB = lib
     return lib
 

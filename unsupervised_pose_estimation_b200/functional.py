@@ -711,3 +711,71 @@ class _SmoothLoss(torch.autograd.Function):
 
 def smooth_loss(disp, img):
     return _SmoothLoss.apply(disp, img)
+
+
+# --------------------------------------------------------------------------------------------------
+# depth metrics and the GAN prior's loss
+# --------------------------------------------------------------------------------------------------
+def _metrics_ws(dev):
+    lib = _lib.load()
+    nbytes = lib.vsl_metrics_workspace_bytes()
+    return torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev), nbytes
+
+
+def depth_errors(gt, pred):
+    """compute_depth_errors (layers.py:335-353) in one kernel: returns the seven metrics as a [7] device tensor
+    (abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3)."""
+    gt, pred = _dev(gt.detach().reshape(-1), "gt"), _dev(pred.detach().reshape(-1), "pred")
+    if gt.numel() != pred.numel() or gt.numel() == 0:
+        raise ValueError("gt and pred must have the same, non-zero number of elements")
+    out = torch.empty(7, dtype=torch.float32, device=gt.device)
+    ws, nbytes = _metrics_ws(gt.device)
+    check(_lib.load().vsl_depth_errors(gt.numel(), gt.data_ptr(), pred.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes,
+                                       _stream()), "vsl_depth_errors")
+    return out
+
+
+def depth_losses(depth_pred, depth_gt, crop=(153, 371, 44, 1197), clamp=(1e-3, 80.0)):
+    """Trainer.compute_depth_losses (trainer.py:688-716) on the device: [7] tensor of the metrics."""
+    depth_pred, depth_gt = _dev(depth_pred.detach(), "depth_pred"), _dev(depth_gt.detach(), "depth_gt")
+    B, _, h, w = depth_pred.shape
+    Bg, _, gh, gw = depth_gt.shape
+    if B != Bg:
+        raise ValueError("depth_pred and depth_gt have different batch sizes")
+    out = torch.empty(7, dtype=torch.float32, device=depth_pred.device)
+    ws, nbytes = _metrics_ws(depth_pred.device)
+    c = (ctypes.c_int * 4)(*[int(v) for v in crop])
+    check(_lib.load().vsl_depth_losses(B, h, w, gh, gw, ctypes.byref(c), float(np.float32(clamp[0])), float(np.float32(clamp[1])),
+                                       depth_pred.data_ptr(), depth_gt.data_ptr(), out.data_ptr(), ws.data_ptr(), nbytes,
+                                       _stream()), "vsl_depth_losses")
+    return out
+
+
+class _SLlog(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fake, real):
+        fake, real = _dev(fake, "fake"), _dev(real, "real")
+        if fake.shape != real.shape:
+            raise ValueError("SLlog needs equal shapes (the reference's resize branch reads an unassigned name)")
+        dev = fake.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        stats = torch.empty(3, dtype=torch.float32, device=dev)
+        ws, nbytes = _metrics_ws(dev)
+        check(_lib.load().vsl_sllog_forward(fake.numel(), fake.data_ptr(), real.data_ptr(), loss.data_ptr(), stats.data_ptr(),
+                                            ws.data_ptr(), nbytes, _stream()), "vsl_sllog_forward")
+        ctx.save_for_backward(fake, real, stats)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        fake, real, stats = ctx.saved_tensors
+        g = _dev(g, "grad")
+        gf = torch.empty_like(fake) if ctx.needs_input_grad[0] else None
+        gr = torch.empty_like(real) if ctx.needs_input_grad[1] else None
+        check(_lib.load().vsl_sllog_backward(fake.numel(), fake.data_ptr(), real.data_ptr(), stats.data_ptr(), g.data_ptr(),
+                                             ptr(gf), ptr(gr), _stream()), "vsl_sllog_backward")
+        return gf, gr
+
+
+def sllog(fake, real):
+    return _SLlog.apply(fake, real)

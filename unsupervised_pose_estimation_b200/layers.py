@@ -7,9 +7,11 @@ CUDA-backed (the hot path; reference layers.py lines in brackets):
 Pose helpers: transformation_from_parameters [97-114] is one CUDA kernel
 for CUDA inputs (bit-identical to the torch ops, with an analytic backward) and the original torch ops
 otherwise; get_translation_matrix [117-130] and rot_from_axisangle [133-172] stay plain torch.
+Adjacent losses / metrics: SLlog [32-56] and compute_depth_errors [335-353] run as
+CUDA kernels for CUDA inputs (fixed-order fp64 reductions), the reference's torch ops otherwise.
 Names re-exported only so ``from layers import *`` users keep working (networks/depth_decoder.py:14,
-evaluate_depth.py:10): SLlog, RMSE_log, depth_to_disp, ConvBlock, Conv3x3, batchNorm, upsample,
-deconv, compute_depth_errors.  They are network blocks / eval metrics, not part of the path.
+evaluate_depth.py:10): RMSE_log, depth_to_disp, ConvBlock, Conv3x3, batchNorm, upsample, deconv.  They are
+network blocks, not part of the path.
 """
 from __future__ import absolute_import, division, print_function
 
@@ -167,6 +169,8 @@ class SLlog(nn.Module):
     """Scale-invariant log loss of the GAN-prior branch (reference layers.py:32-56)."""
 
     def forward(self, fake1, real1):
+        if fake1.is_cuda and fake1.dtype == torch.float32:
+            return VF.sllog(fake1, real1)   # one reduction kernel forward, one element-wise kernel backward
         n = (real1 > 0).float().sum()
         d = _valid_log_pair(fake1, real1)
         return torch.sqrt((torch.sum(d ** 2) / n) - ((torch.sum(d) / n) ** 2))
@@ -232,7 +236,10 @@ class deconv(nn.Module):
 
 
 def compute_depth_errors(gt, pred):
-    """KITTI depth metrics (reference layers.py:335-353)."""
+    """KITTI depth metrics (reference layers.py:335-353).  CUDA fp32 inputs: one kernel (VF.depth_errors); the
+    seven results are 0-dim views of one device vector, like the reference's seven 0-dim tensors."""
+    if gt.is_cuda and gt.dtype == torch.float32 and pred.dtype == torch.float32:
+        return tuple(VF.depth_errors(gt, pred).unbind(0))
     ratio = torch.max(gt / pred, pred / gt)
     a1, a2, a3 = ((ratio < 1.25 ** k).float().mean() for k in (1, 2, 3))
     rmse = torch.sqrt(((gt - pred) ** 2).mean())

@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import types
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -34,8 +35,6 @@ def _unsupported(opt):
     bad = []
     if getattr(opt, "pose_model_type", "separate_resnet") == "posecnn" and "s" in opt.frame_ids:
         bad.append("--pose_model_type posecnn with a stereo frame (the reference itself fails there)")
-    if getattr(opt, "pre_trained_generator", False):
-        bad.append("--pre_trained_generator")
     return bad
 
 
@@ -233,7 +232,47 @@ class ViewSynthesisLossMixin:
             if plan.automask:  # the reference writes the mask only with automasking on (trainer.py:668-670)
                 outputs["identity_selection/{}".format(scale)] = masks[si]
         losses["loss"] = vec[2 * S] if weighting is None else vec[2 * S] + sum(weighting) / S
+        self._vsl_gan_prior(inputs, outputs, losses)
         return losses
+
+    def _vsl_gan_prior(self, inputs, outputs, losses):
+        """--pre_trained_generator (trainer.py:565-583, :684): the scale-invariant log loss between the generator's
+        disparity and every up-sampled ("disp", s), 0.002 / num_scales of their sum added to the total.  The
+        generator and its input transform are the caller's (``self.models["pre_trained_generator"]``,
+        ``self.gen_transform``, trainer.py:118-131); the loss itself is the SLlog CUDA kernel."""
+        opt = self.opt
+        if not getattr(opt, "pre_trained_generator", False):
+            return
+        models = getattr(self, "models", None)
+        if not models or "pre_trained_generator" not in models or not hasattr(self, "gen_transform"):
+            raise RuntimeError('--pre_trained_generator needs self.models["pre_trained_generator"] and self.gen_transform '
+                               "(trainer.py:118-131)")
+        from .layers import SLlog, depth_to_disp
+        fake_B1 = models["pre_trained_generator"](self.gen_transform(inputs[("color", 0, 0)]))
+        _, fake_disp_scaled = depth_to_disp(fake_B1)
+        si_loss = getattr(self, "si_loss", None) or SLlog()
+        gan_total = 0
+        for scale in opt.scales:
+            disp = torch.nn.functional.interpolate(outputs[("disp", scale)], [opt.height, opt.width], mode="bilinear",
+                                                   align_corners=False)
+            gan_loss = si_loss(fake_disp_scaled.contiguous(), disp)
+            losses["gan_loss/{}".format(scale)] = gan_loss
+            gan_total = gan_total + gan_loss
+        losses["loss"] = losses["loss"] + gan_total / len(opt.scales) * 0.002
+        self.vsl_last_loss_vector = None   # the dict no longer is one contiguous vector
+
+    depth_metric_names = ["de/abs_rel", "de/sq_rel", "de/rms", "de/log_rms", "da/a1", "da/a2", "da/a3"]  # trainer.py:255-256
+
+    def compute_depth_losses(self, inputs, outputs, losses):
+        """Reference trainer.py:688-716 (validation-time depth metrics against inputs["depth_gt"]): up-sample,
+        Garg/Eigen crop, median scaling, clamp and the seven metrics in CUDA kernels; one device-to-host read."""
+        depth = outputs.get(("depth", 0, 0))
+        if depth is None:   # side outputs were skipped ("none" mode): only the depth of scale 0 is needed here
+            from .layers import disp_to_depth
+            _, depth = disp_to_depth(outputs[("disp", 0)].detach(), self.opt.min_depth, self.opt.max_depth)
+        vals = VF.depth_losses(depth, inputs["depth_gt"]).cpu().numpy()
+        for i, metric in enumerate(self.depth_metric_names):
+            losses[metric] = np.array(vals[i])
 
 
     def _compute_losses_v1(self, inputs, outputs, plans):
@@ -258,6 +297,7 @@ class ViewSynthesisLossMixin:
                 outputs["identity_selection/{}".format(scale)] = masks[0]
             total = total + level_loss
         losses["loss"] = total / self.num_scales if hasattr(self, "num_scales") else total / len(opt.scales)
+        self._vsl_gan_prior(inputs, outputs, losses)
         return losses
 
 
