@@ -313,6 +313,16 @@ int vsl_pyramid_plan(const VslPyramidDesc* desc, void* workspace, size_t workspa
 int vsl_pyramid_forward(const VslPyramidDesc* desc, const uint8_t* frames_hwc, void* const levels[VSL_MAX_SCALES],
                         uint8_t* const levels_u8[VSL_MAX_SCALES], void* workspace, size_t workspace_bytes,
                         void* stream);
+/* The same with the horizontal flip of MonoDataset.get_color (`color.transpose(Image.FLIP_LEFT_RIGHT)` when the
+ * item's do_flip is set, datasets/mono_dataset2.py:151-156 via kitti_dataset.py) applied to the raw frame while it is
+ * read: flip [B] bytes on the device, non-zero = mirror that image; null = no flips.  Flipping first and resampling
+ * afterwards is what the reference does (its fixed-point LANCZOS tables are not exactly mirror-symmetric). */
+int vsl_pyramid_forward_flip(const VslPyramidDesc* desc, const uint8_t* frames_hwc, const uint8_t* flip,
+                             void* const levels[VSL_MAX_SCALES], uint8_t* const levels_u8[VSL_MAX_SCALES],
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* inputs["stereo_T"] of MonoDataset.__getitem__ (datasets/mono_dataset2.py:197-203) for a batch: identity with
+ * T[0,3] = side_sign * baseline_sign * baseline; side_left [B] / flip [B] bytes on the device (null = all zero). */
+int vsl_stereo_transform(int batch, const uint8_t* flip, const uint8_t* side_left, float baseline, float* T, void* stream);
 /* host-only helper (no device work): the coefficient table of one axis, bounds [out_size][2] = (first
  * input index, tap count), coefs [out_size][13]; ksize_capacity must be 13.  Lets tests compare the
  * tables with Pillow's without a GPU. */

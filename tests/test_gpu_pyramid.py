@@ -158,3 +158,82 @@ def test_host_batch_stager_with_pipeline_equals_direct_upload():
         direct_pipe({k[1]: v for k, v in devb.items() if k[0] == "color_u8"}, inputs)
         want = step(devb, inputs)
         assert torch.equal(got[i][0], want[0]) and torch.equal(got[i][1], want[1]), i
+
+
+AUGMENT = os.path.join(os.path.dirname(__file__), "golden", "pyramid", "augment_pil.npz")
+
+
+@pytest.mark.parametrize("name", ["iid_64x96", "smooth_96x160", "edges_32x64"])
+def test_flip_equals_pillow_goldens(name):
+    """MonoDataset's do_flip (`color.transpose(Image.FLIP_LEFT_RIGHT)` before the pyramid) applied per image while the
+    raw frame is read: flagged images equal the goldens made with PIL's transpose + torchvision's Resize/ToTensor,
+    unflagged images in the same batch are untouched."""
+    from unsupervised_pose_estimation_b200.input_pipeline import FramePyramid
+    g, a = np.load(GOLDEN), np.load(AUGMENT)
+    img = g[name + "/u8_0"]
+    batch = torch.from_numpy(np.stack([img, img, img[::-1].copy()])).cuda()
+    flip = torch.tensor([1, 0, 1], dtype=torch.uint8, device="cuda")
+    H, W = img.shape[:2]
+    for levels in (None, [0]):   # all levels (target frame: fused level-0 write) and level 0 only (source frames)
+        pyr = FramePyramid(3, H, W, 4, "cuda", levels=levels)
+        out, u8 = pyr(batch, want_u8=True, flip=flip)
+        torch.cuda.synchronize()
+        assert np.array_equal(out[0][0].cpu().numpy(), O.to_tensor(a["flip/%s/u8_0" % name]))
+        assert np.array_equal(out[0][1].cpu().numpy(), O.to_tensor(img))
+        if levels is None:
+            for s in range(1, 4):
+                assert np.array_equal(u8[s][0].cpu().numpy(), a["flip/%s/u8_%d" % (name, s)]), (name, s)
+                assert np.array_equal(u8[s][1].cpu().numpy(), g["%s/u8_%d" % (name, s)]), (name, s)
+            assert np.array_equal(out[3][0].cpu().numpy(), a["flip/%s/f32_3" % name])
+            # image 2 is the vertically mirrored frame, flipped horizontally: the oracle on the mirrored input
+            lv, tn = O.pyramid(img[::-1, ::-1].copy()[None], 4)
+            for s in range(1, 4):
+                assert np.array_equal(u8[s][2].cpu().numpy(), lv[s][0]), s
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 40), (3, 10, 18), (2, 192, 640)])
+def test_flip_ragged_and_full_shapes(shape):
+    """Widths that are not multiples of 4 take the scalar conversion and the byte-column staging."""
+    from unsupervised_pose_estimation_b200.input_pipeline import FramePyramid
+    B, H, W = shape
+    rng = np.random.RandomState(H * W)
+    batch = rng.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
+    n = 2 if (H % 8 or W % 8) else 4
+    flip = np.arange(B) % 2 == 0
+    pyr = FramePyramid(B, H, W, n, "cuda")
+    out, u8 = pyr(torch.from_numpy(batch).cuda(), want_u8=True, flip=torch.from_numpy(flip.astype(np.uint8)).cuda())
+    want = np.where(flip[:, None, None, None], batch[:, :, ::-1], batch)
+    levels, tensors = O.pyramid(np.ascontiguousarray(want), n)
+    for s in range(n):
+        if s:
+            assert np.array_equal(u8[s].cpu().numpy(), levels[s]), s
+        assert np.array_equal(out[s].cpu().numpy(), tensors[s]), s
+
+
+def test_stereo_T_and_cached_intrinsics():
+    """inputs["stereo_T"] from the per-item flags (datasets/mono_dataset2.py:197-203) and the per-scale K / inv_K as
+    plan constants (:168-177), equal to what the reference's dataset code produces."""
+    from unsupervised_pose_estimation_b200 import synthetic
+    from unsupervised_pose_estimation_b200.input_pipeline import LossInputPipeline
+    from unsupervised_pose_estimation_b200.trainer import make_opt
+    opt = make_opt(height=32, width=64, batch_size=4, frame_ids=[0, -1, 1, "s"])
+    pipe = LossInputPipeline(opt, "cuda")
+    flip = torch.tensor([0, 1, 0, 1], dtype=torch.uint8, device="cuda")
+    left = torch.tensor([0, 0, 1, 1], dtype=torch.uint8, device="cuda")
+    T = pipe.stereo_T(flip, left).cpu().numpy()
+    for b, (do_flip, side) in enumerate([(False, "r"), (True, "r"), (False, "l"), (True, "l")]):
+        ref = np.eye(4, dtype=np.float32)   # the reference's own lines
+        baseline_sign = -1 if do_flip else 1
+        side_sign = -1 if side == "l" else 1
+        ref[0, 3] = side_sign * baseline_sign * 0.1
+        assert np.array_equal(T[b], ref), b
+    intr = pipe.intrinsics(synthetic.K_KITTI)
+    ref = synthetic.scaled_intrinsics(synthetic.K_KITTI, 32, 64, 4, 4)   # restates mono_dataset2.py:168-177
+    for k, v in ref.items():
+        assert torch.equal(intr[k].cpu(), v), k
+    assert pipe.intrinsics(synthetic.K_KITTI)[("K", 0)] is intr[("K", 0)]   # cached: no per-step work or copy
+    rng = np.random.RandomState(0)
+    frames = {f: torch.from_numpy(rng.randint(0, 256, (4, 32, 64, 3)).astype(np.uint8)).cuda() for f in opt.frame_ids}
+    inputs = pipe(frames, flip=flip, side_left=left)
+    assert torch.equal(inputs["stereo_T"].cpu(), torch.from_numpy(T))
+    assert torch.equal(inputs[("color", "s", 0)][1].cpu(), torch.from_numpy(O.to_tensor(frames["s"][1].cpu().numpy()[:, ::-1])))

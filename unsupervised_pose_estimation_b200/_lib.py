@@ -48,6 +48,7 @@ EXPORTED_SYMBOLS = [
     "vsl_smooth_workspace_bytes", "vsl_smooth_loss_forward", "vsl_smooth_loss_backward",
     "vsl_pyramid_workspace_bytes", "vsl_pyramid_plan", "vsl_pyramid_forward", "vsl_pyramid_coefficients",
     "vsl_source_grad_upstream", "vsl_grid_sample_backward_source",
+    "vsl_pyramid_forward_flip", "vsl_stereo_transform",
     "vsl_metrics_workspace_bytes", "vsl_depth_errors", "vsl_depth_losses", "vsl_sllog_forward", "vsl_sllog_backward",
 ]
 
@@ -156,6 +157,9 @@ def load():
     lib.vsl_pyramid_forward.argtypes = [POINTER(VslPyramidDesc), vp, POINTER(c_void_p * VSL_MAX_SCALES),
                                         POINTER(c_void_p * VSL_MAX_SCALES), vp, c_size_t, vp]
     lib.vsl_pyramid_coefficients.argtypes = [c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_int]
+    lib.vsl_pyramid_forward_flip.argtypes = [POINTER(VslPyramidDesc), vp, vp, POINTER(c_void_p * VSL_MAX_SCALES),
+                                             POINTER(c_void_p * VSL_MAX_SCALES), vp, c_size_t, vp]
+    lib.vsl_stereo_transform.argtypes = [c_int, vp, vp, c_float, vp, vp]
     lib.vsl_source_grad_upstream.argtypes = [POINTER(VslDesc), vp, POINTER(c_void_p * VSL_MAX_SCALES), vp,
                                              POINTER(c_void_p * VSL_MAX_SCALES), vp]
     lib.vsl_grid_sample_backward_source.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]

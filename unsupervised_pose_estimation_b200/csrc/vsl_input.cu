@@ -135,13 +135,20 @@ template <> __device__ __forceinline__ void store_tensor<bf16_t>(bf16_t* p, size
 }
 
 // level 0: HWC uint8 -> CHW tensor
+// `flip` (optional, [B] bytes): images whose flag is set are mirrored left-right while they are read, like
+// `color.transpose(Image.FLIP_LEFT_RIGHT)` in MonoDataset.get_color (datasets/mono_dataset2.py via kitti_dataset.py)
 template <class Out>
 __global__ void __launch_bounds__(256) k_u8_to_tensor(const uint8_t* __restrict__ in, Out* __restrict__ out, int hw,
-                                                     size_t total_px) {
+                                                     size_t total_px, int W, const uint8_t* __restrict__ flip) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // pixel index over [B, H*W]
   if (i >= total_px) return;
   const size_t b = i / hw, o = i - b * hw;
-  const uint8_t* q = in + i * 3;
+  size_t src = i;
+  if (flip && flip[b]) {
+    const int y = (int)(o / W), x = (int)(o - (size_t)y * W);
+    src = b * hw + (size_t)y * W + (W - 1 - x);
+  }
+  const uint8_t* q = in + src * 3;
   Out* dst = out + b * 3 * hw + o;
   store_tensor<Out>(dst, 0, q[0]);
   store_tensor<Out>(dst, (size_t)hw, q[1]);
@@ -160,16 +167,31 @@ __device__ __forceinline__ void store4(bf16_t* p, const uint8_t v[4]) {
 }
 template <class Out>
 __global__ void __launch_bounds__(256) k_u8_to_tensor_x4(const uint8_t* __restrict__ in, Out* __restrict__ out, int hw,
-                                                        size_t total_quads) {
+                                                        size_t total_quads, int W, const uint8_t* __restrict__ flip) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // group of 4 pixels
   if (i >= total_quads) return;
   const size_t px = i * 4;
   const size_t b = px / hw, o = px - b * hw;
-  const uint32_t* q = reinterpret_cast<const uint32_t*>(in + px * 3);
+  const bool fl = flip && flip[b];  // only with W % 4 == 0 (the launcher checks): a quad never straddles two rows
+  size_t spx = px;
+  if (fl) {
+    const int y = (int)(o / W), x = (int)(o - (size_t)y * W);
+    spx = b * hw + (size_t)y * W + (W - 4 - x);  // the four source pixels, read in reverse below
+  }
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(in + spx * 3);
   const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];  // bytes r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
-  const uint8_t r[4] = {(uint8_t)w0, (uint8_t)(w0 >> 24), (uint8_t)(w1 >> 16), (uint8_t)(w2 >> 8)};
-  const uint8_t g[4] = {(uint8_t)(w0 >> 8), (uint8_t)w1, (uint8_t)(w1 >> 24), (uint8_t)(w2 >> 16)};
-  const uint8_t bl[4] = {(uint8_t)(w0 >> 16), (uint8_t)(w1 >> 8), (uint8_t)w2, (uint8_t)(w2 >> 24)};
+  uint8_t r[4] = {(uint8_t)w0, (uint8_t)(w0 >> 24), (uint8_t)(w1 >> 16), (uint8_t)(w2 >> 8)};
+  uint8_t g[4] = {(uint8_t)(w0 >> 8), (uint8_t)w1, (uint8_t)(w1 >> 24), (uint8_t)(w2 >> 16)};
+  uint8_t bl[4] = {(uint8_t)(w0 >> 16), (uint8_t)(w1 >> 8), (uint8_t)w2, (uint8_t)(w2 >> 24)};
+  if (fl) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      uint8_t t;
+      t = r[k]; r[k] = r[3 - k]; r[3 - k] = t;
+      t = g[k]; g[k] = g[3 - k]; g[3 - k] = t;
+      t = bl[k]; bl[k] = bl[3 - k]; bl[3 - k] = t;
+    }
+  }
   Out* dst = out + b * 3 * hw + o;
   store4(dst, r);
   store4(dst + hw, g);
@@ -186,7 +208,7 @@ constexpr int kTX = 32, kTY = 8, kRowsMax = 2 * kTY + kKsize + 1, kRowBytes = (2
 template <class Out, bool kWords>
 __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
                                                      Out* __restrict__ out_t, Out* __restrict__ out_in, AxisTable tx,
-                                                     AxisTable ty, int hi, int wi) {
+                                                     AxisTable ty, int hi, int wi, const uint8_t* __restrict__ flip) {
   __shared__ __align__(16) uint8_t tin[kRowsMax][kRowBytes];  // input window of the tile
   __shared__ uint8_t hrow[kRowsMax][kTX][3];                  // its horizontal pass, rounded to 8 bits
   __shared__ int32_t kx[kTX][kKsize], ky[kTY][kKsize];        // the tile's coefficient rows (13 words: conflict-free)
@@ -212,7 +234,18 @@ __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict_
     bx[o] = x0 + o < wo ? tx.bounds[2 * (x0 + o)] - col_lo : 0;
     if (o < kTY) by[o] = y0 + o < ho ? ty.bounds[2 * (y0 + o)] - row_lo : 0;
   }
-  if (kWords) {  // rows start on a word boundary (wi % 4 == 0; col_lo is a multiple of 4): <= 59 words per row
+  if (flip && flip[b]) {
+    // mirrored read of the raw frame (level 1 only): window column c holds source column wi - 1 - (col_lo + c);
+    // byte loads, each pixel's three channels kept in order.  Everything after the staging sees a flipped image.
+    const int ncol = ncolb / 3;
+    const uint8_t* row0 = in + ((size_t)b * hi + row_lo) * pitch;
+    for (int idx = threadIdx.x; idx < nrows * ncolb; idx += 256) {
+      const int r = idx / ncolb, j = idx - r * ncolb;
+      const int c = j / 3, ch = j - 3 * c;
+      (void)ncol;
+      tin[r][j] = row0[r * pitch + (size_t)(wi - 1 - (col_lo + c)) * 3 + ch];
+    }
+  } else if (kWords) {  // rows start on a word boundary (wi % 4 == 0; col_lo is a multiple of 4): <= 59 words per row
     const int nw = (ncolb + 3) >> 2;  // the last word may reach up to 3 bytes past the taps: still inside the row
     for (int r = threadIdx.x >> 6; r < nrows; r += 4) {
       const int w = threadIdx.x & 63;
@@ -280,16 +313,17 @@ __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict_
 
 template <class Out>
 static int pyramid_forward_impl(const VslPyramidDesc* d, const PyramidPlan& pl, const uint8_t* frames,
-                                void* const levels[VSL_MAX_SCALES], uint8_t* ws, cudaStream_t st) {
+                                const uint8_t* flip, void* const levels[VSL_MAX_SCALES], uint8_t* ws, cudaStream_t st) {
   const size_t px0 = (size_t)d->batch * d->height * d->width;
   // with more than one level the first 2:1 kernel also writes the level-0 tensor (its tiles cover level 0)
   const bool fuse0 = levels[0] && d->num_levels > 1;
   if (levels[0] && !fuse0) {
     const int hw = d->height * d->width;
-    if (hw % 4 == 0 && ((uintptr_t)frames & 3u) == 0 && ((uintptr_t)levels[0] & 15u) == 0)
-      k_u8_to_tensor_x4<Out><<<(unsigned)((px0 / 4 + 255) / 256), 256, 0, st>>>(frames, (Out*)levels[0], hw, px0 / 4);
+    if (hw % 4 == 0 && (!flip || d->width % 4 == 0) && ((uintptr_t)frames & 3u) == 0 && ((uintptr_t)levels[0] & 15u) == 0)
+      k_u8_to_tensor_x4<Out><<<(unsigned)((px0 / 4 + 255) / 256), 256, 0, st>>>(frames, (Out*)levels[0], hw, px0 / 4,
+                                                                                 d->width, flip);
     else
-      k_u8_to_tensor<Out><<<(unsigned)((px0 + 255) / 256), 256, 0, st>>>(frames, (Out*)levels[0], hw, px0);
+      k_u8_to_tensor<Out><<<(unsigned)((px0 + 255) / 256), 256, 0, st>>>(frames, (Out*)levels[0], hw, px0, d->width, flip);
     VSL_CUDA_OK_IN(cudaGetLastError());
   }
   const uint8_t* prev = frames;
@@ -300,10 +334,11 @@ static int pyramid_forward_impl(const VslPyramidDesc* d, const PyramidPlan& pl, 
     uint8_t* cur = ws + pl.off_u8[s];
     Out* out_in = (s == 1 && fuse0) ? (Out*)levels[0] : nullptr;
     dim3 grid(((wi >> 1) + kTX - 1) / kTX, ((hi >> 1) + kTY - 1) / kTY, d->batch);
+    const uint8_t* fl = s == 1 ? flip : nullptr;  // later levels read the already mirrored 8-bit level
     if (wi % 4 == 0 && ((uintptr_t)prev & 3u) == 0)
-      k_lanczos_half<Out, true><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi);
+      k_lanczos_half<Out, true><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi, fl);
     else
-      k_lanczos_half<Out, false><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi);
+      k_lanczos_half<Out, false><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi, fl);
     VSL_CUDA_OK_IN(cudaGetLastError());
     prev = cur;
   }
@@ -356,6 +391,35 @@ int vsl_pyramid_coefficients(int in_size, int out_size, int32_t* bounds, int32_t
 
 int vsl_pyramid_forward(const VslPyramidDesc* d, const uint8_t* frames_hwc, void* const levels[VSL_MAX_SCALES],
                         uint8_t* const levels_u8[VSL_MAX_SCALES], void* workspace, size_t workspace_bytes, void* stream) {
+  return vsl_pyramid_forward_flip(d, frames_hwc, nullptr, levels, levels_u8, workspace, workspace_bytes, stream);
+}
+
+// stereo_T of MonoDataset.__getitem__ (datasets/mono_dataset2.py:197-203): identity with
+// T[0,3] = side_sign * baseline_sign * baseline, side_sign = -1 for the left camera, baseline_sign = -1 when flipped
+__global__ void k_stereo_T(int B, const uint8_t* __restrict__ flip, const uint8_t* __restrict__ side_left, float baseline,
+                           float* __restrict__ T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 16) return;
+  const int b = i >> 4, e = i & 15;
+  float v = (e == 0 || e == 5 || e == 10 || e == 15) ? 1.0f : 0.0f;
+  if (e == 3) {
+    const bool neg = ((flip && flip[b]) ? 1 : 0) != ((side_left && side_left[b]) ? 1 : 0);
+    v = neg ? -baseline : baseline;
+  }
+  T[i] = v;
+}
+
+int vsl_stereo_transform(int batch, const uint8_t* flip, const uint8_t* side_left, float baseline, float* T, void* stream) {
+  if (batch < 1) return VSL_ERR_BAD_DESC;
+  if (!T) return VSL_ERR_NULL_POINTER;
+  k_stereo_T<<<(batch * 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(batch, flip, side_left, baseline, T);
+  VSL_CUDA_OK_IN(cudaGetLastError());
+  return VSL_OK;
+}
+
+int vsl_pyramid_forward_flip(const VslPyramidDesc* d, const uint8_t* frames_hwc, const uint8_t* flip,
+                             void* const levels[VSL_MAX_SCALES], uint8_t* const levels_u8[VSL_MAX_SCALES], void* workspace,
+                             size_t workspace_bytes, void* stream) {
   if (!pyr_desc_ok(d)) return VSL_ERR_BAD_DESC;
   if (!frames_hwc || !levels || !workspace) return VSL_ERR_NULL_POINTER;
   if (((uintptr_t)workspace & 255u) != 0) return VSL_ERR_MISALIGNED;
@@ -363,8 +427,8 @@ int vsl_pyramid_forward(const VslPyramidDesc* d, const uint8_t* frames_hwc, void
   if (workspace_bytes < pl.total) return VSL_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = d->out_dtype == VSL_DTYPE_BF16
-               ? pyramid_forward_impl<bf16_t>(d, pl, frames_hwc, levels, (uint8_t*)workspace, st)
-               : pyramid_forward_impl<float>(d, pl, frames_hwc, levels, (uint8_t*)workspace, st);
+               ? pyramid_forward_impl<bf16_t>(d, pl, frames_hwc, flip, levels, (uint8_t*)workspace, st)
+               : pyramid_forward_impl<float>(d, pl, frames_hwc, flip, levels, (uint8_t*)workspace, st);
   if (rc != VSL_OK) return rc;
   if (levels_u8) {  // optional copies of the 8-bit levels (what PIL would hold), for checking / logging
     for (int s = 1; s < d->num_levels; ++s)

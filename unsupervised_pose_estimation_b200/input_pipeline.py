@@ -64,8 +64,13 @@ class FramePyramid:
                                             _stream()), "vsl_pyramid_plan")
             torch.cuda.current_stream().synchronize()  # the tables come from temporary host memory
 
-    def __call__(self, frame_u8, want_u8=False):
-        """frame_u8: [B,H,W,3] uint8 CUDA tensor.  Returns {level: tensor}; with want_u8 also the 8-bit levels."""
+    def __call__(self, frame_u8, want_u8=False, flip=None):
+        """frame_u8: [B,H,W,3] uint8 CUDA tensor.  Returns {level: tensor}; with want_u8 also the 8-bit levels.
+        ``flip``: optional [B] uint8 CUDA tensor, non-zero = mirror that image left-right first (the dataset's
+        ``do_flip``, datasets/mono_dataset2.py:151-156)."""
+        if flip is not None and (flip.device != self.device or flip.dtype != torch.uint8 or flip.numel() != self.batch
+                                 or not flip.is_contiguous()):
+            raise _lib.VslError("flip must be a contiguous uint8 tensor of %d flags on %s" % (self.batch, self.device))
         if frame_u8.device != self.device or frame_u8.dtype != torch.uint8 or not frame_u8.is_contiguous():
             raise _lib.VslError("frames must be contiguous uint8 tensors on %s (got %s %s)"
                                 % (self.device, frame_u8.dtype, frame_u8.device))
@@ -83,10 +88,11 @@ class FramePyramid:
             u8p = (ctypes.c_void_p * VSL_MAX_SCALES)()
             for s, t in u8.items():
                 u8p[s] = t.data_ptr()
-        check(self.lib.vsl_pyramid_forward(ctypes.byref(self.desc), ctypes.c_void_p(frame_u8.data_ptr()),
-                                           ctypes.byref(lv), ctypes.byref(u8p) if u8p is not None else None,
-                                           ctypes.c_void_p(self.ws_ptr), self.ws_bytes, _stream()),
-              "vsl_pyramid_forward")
+        check(self.lib.vsl_pyramid_forward_flip(ctypes.byref(self.desc), ctypes.c_void_p(frame_u8.data_ptr()),
+                                                ctypes.c_void_p(flip.data_ptr()) if flip is not None else None,
+                                                ctypes.byref(lv), ctypes.byref(u8p) if u8p is not None else None,
+                                                ctypes.c_void_p(self.ws_ptr), self.ws_bytes, _stream()),
+              "vsl_pyramid_forward_flip")
         return (self.out, u8) if want_u8 else self.out
 
 
@@ -100,19 +106,64 @@ class LossInputPipeline:
 
     def __init__(self, opt, device="cuda", dtype=torch.float32, all_levels=False):
         self.frame_ids = list(opt.frame_ids)
+        self.opt = opt
+        self.device = torch.device(device)
+        self._intrinsics = {}
         n = len(opt.scales)
         self.pyramids = {
             f: FramePyramid(opt.batch_size, opt.height, opt.width, n, device, dtype,
                             levels=None if (all_levels or i == 0) else [0])
             for i, f in enumerate(self.frame_ids)}
 
-    def __call__(self, frames_u8, inputs=None):
-        """frames_u8: {frame_id: [B,H,W,3] uint8 CUDA tensor}.  Fills / returns ``inputs[("color", f, s)]``."""
+    def __call__(self, frames_u8, inputs=None, flip=None, side_left=None):
+        """frames_u8: {frame_id: [B,H,W,3] uint8 CUDA tensor}.  Fills / returns ``inputs[("color", f, s)]``.
+
+        ``flip`` ([B] uint8 on the device): the items' ``do_flip`` draws — every frame of a flagged item is mirrored
+        before the pyramid is formed, and with a stereo frame ``inputs["stereo_T"]`` gets the matching baseline sign
+        (datasets/mono_dataset2.py:155-156, :197-203; ``side_left``: [B] uint8, 1 where the item is a left image)."""
         inputs = {} if inputs is None else inputs
         for f in self.frame_ids:
-            for s, t in self.pyramids[f](frames_u8[f]).items():
+            for s, t in self.pyramids[f](frames_u8[f], flip=flip).items():
                 inputs[("color", f, s)] = t
+        if "s" in self.frame_ids and (flip is not None or side_left is not None):
+            inputs["stereo_T"] = self.stereo_T(flip, side_left)
         return inputs
+
+    def stereo_T(self, flip=None, side_left=None, baseline=0.1):
+        """inputs["stereo_T"] [B,4,4] (datasets/mono_dataset2.py:197-203) from the per-item flags, on the device."""
+        B = self.opt.batch_size
+        dev = next(iter(self.pyramids.values())).device
+        T = torch.empty(B, 4, 4, dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        check(lib.vsl_stereo_transform(B, ctypes.c_void_p(flip.data_ptr()) if flip is not None else None,
+                               ctypes.c_void_p(side_left.data_ptr()) if side_left is not None else None,
+                               float(baseline), ctypes.c_void_p(T.data_ptr()), _stream()), "vsl_stereo_transform")
+        return T
+
+    def intrinsics(self, K_norm, inputs=None):
+        """inputs[("K", s)] / [("inv_K", s)] [B,4,4] for every scale (datasets/mono_dataset2.py:168-177), as PLAN
+        CONSTANTS: the reference re-derives them for every item in its DataLoader workers and copies 8 matrices per
+        image to the device every step, although ``self.K`` is one constant per dataset.  Here they are computed once
+        per normalised K with the reference's own numpy operations (row scaling by ``width // 2**s`` /
+        ``height // 2**s``, ``np.linalg.pinv``: the bit pattern of inv_K feeds the bit-exact ray computation, so it has
+        to be numpy's) and stay resident; later calls return the cached device tensors."""
+        import numpy as np
+        K_norm = np.asarray(K_norm, dtype=np.float32)
+        key = K_norm.tobytes()
+        if key not in self._intrinsics:
+            opt, dev = self.opt, next(iter(self.pyramids.values())).device
+            out = {}
+            for s in range(len(opt.scales)):
+                K = K_norm.copy()
+                K[0, :] *= opt.width // (2 ** s)
+                K[1, :] *= opt.height // (2 ** s)
+                inv_K = np.linalg.pinv(K)
+                out[("K", s)] = torch.from_numpy(K).unsqueeze(0).repeat(opt.batch_size, 1, 1).to(dev)
+                out[("inv_K", s)] = torch.from_numpy(inv_K).unsqueeze(0).repeat(opt.batch_size, 1, 1).to(dev)
+            self._intrinsics[key] = out
+        if inputs is not None:
+            inputs.update(self._intrinsics[key])
+        return self._intrinsics[key]
 
 
 def pyramid_coefficients(in_size, out_size):
