@@ -149,6 +149,9 @@ typedef struct VslLossBuffers {
 } VslLossBuffers;
 
 size_t vsl_loss_workspace_bytes(const VslDesc* desc);
+/* Once per workspace, before its first use (and after any aborted call): zeroes it.  The per-call completion
+ * counter inside is reset by the call itself, so the hot path carries no memset. */
+int vsl_loss_workspace_init(const VslDesc* desc, void* workspace, size_t workspace_bytes, void* stream);
 int vsl_loss_forward_backward(const VslDesc* desc, const VslLossBuffers* buf,
                               void* workspace, size_t workspace_bytes, void* stream);
 

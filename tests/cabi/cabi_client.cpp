@@ -149,6 +149,7 @@ static int run_loss(const std::vector<unsigned char>& in, FILE* out) {
   CHECK_CUDA(cudaMalloc(&ws, ws_bytes));
   cudaStream_t st;
   CHECK_CUDA(cudaStreamCreate(&st));
+  CHECK_VSL(vsl_loss_workspace_init(&d, ws, ws_bytes, st));
   CHECK_VSL(vsl_loss_forward_backward(&d, &buf, ws, ws_bytes, st));
   CHECK_VSL(vsl_loss_combine_grads(&d, upstream, &buf, grad_disp, nullptr, gradT, st));
   CHECK_CUDA(cudaStreamSynchronize(st));

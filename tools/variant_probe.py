@@ -68,6 +68,8 @@ def main():
     dev = torch.device("cuda", 0)
     ring = 4
     wl = bench.Workload(cfg, args.family, dev, ring, bf16_images=args.bf16)
+    wl.path.vsl_parallel_noise = not os.environ.get("VSL_SERIAL_NOISE")
+    res["parallel_noise"] = wl.path.vsl_parallel_noise
     for i in range(5):
         wl.step(wl.sets[i % ring])
     torch.cuda.synchronize()

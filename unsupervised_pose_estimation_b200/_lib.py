@@ -38,7 +38,7 @@ ARITH_NORM_SEQ = 1 << 11
 # every symbol include/vsl.h declares (tests check the shared object exports all of them)
 EXPORTED_SYMBOLS = [
     "vsl_abi_version", "vsl_status_string", "vsl_last_cuda_error",
-    "vsl_loss_workspace_bytes", "vsl_loss_forward_backward", "vsl_loss_forward_backward_timed",
+    "vsl_loss_workspace_bytes", "vsl_loss_workspace_init", "vsl_loss_forward_backward", "vsl_loss_forward_backward_timed",
     "vsl_event_create", "vsl_event_destroy", "vsl_event_elapsed_ms", "vsl_loss_combine_grads",
     "vsl_warp_forward", "vsl_probe_bmm", "vsl_pose_forward", "vsl_pose_backward",
     "vsl_backproject_forward", "vsl_backproject_backward",
@@ -122,6 +122,7 @@ def load():
     lib.vsl_status_string.argtypes = [c_int]
     lib.vsl_loss_workspace_bytes.restype = c_size_t
     lib.vsl_loss_workspace_bytes.argtypes = [POINTER(VslDesc)]
+    lib.vsl_loss_workspace_init.argtypes = [POINTER(VslDesc), vp, c_size_t, vp]
     lib.vsl_loss_forward_backward.argtypes = [POINTER(VslDesc), POINTER(VslLossBuffers), vp, c_size_t, vp]
     lib.vsl_loss_forward_backward_timed.argtypes = [POINTER(VslDesc), POINTER(VslLossBuffers), vp, c_size_t, vp, vp, vp]
     lib.vsl_event_create.argtypes = [POINTER(c_void_p)]

@@ -53,6 +53,35 @@ struct SmallParams {  // smoothness + epilogue
   float smooth_weight;
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream is still draining; it must call pdl_wait() before it touches anything the
+// predecessor wrote.  The predecessor calls pdl_launch_dependents() once its CTAs no longer need to be alone.
+#ifndef VSL_PDL
+#define VSL_PDL 1
+#endif
+__device__ __forceinline__ void pdl_wait() {
+#if VSL_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if VSL_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <class... Args>
+static cudaError_t launch_after(bool programmatic, void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem,
+                                cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (programmatic && VSL_PDL) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -189,6 +218,8 @@ __global__ void __launch_bounds__(C::NT, C::NT >= 512 ? 1 : 2) k_photometric(con
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
   __shared__ bool is_last;
+  pdl_wait();  // everything k_photometric wrote is visible from here on
+  pdl_launch_dependents();
   int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   int h = p.hs[s], w = p.ws[s], n = h * w;
   int nchunk = (n + kChunk - 1) / kChunk;
@@ -328,9 +359,10 @@ struct CombineParams {
   int n[kMaxScales], scale_id[kMaxScales], vec4[kMaxScales];
   float smooth_weight;
 };
-constexpr int kCombineChunk = 4 * kChunk;  // elements per k_combine block
+constexpr int kCombineChunk = kChunk;  // elements per k_combine block: one float4 per thread, every load in flight at once
 
 __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
+  pdl_wait();  // launched programmatically behind k_epilogue when the two are adjacent in the stream (graph replay)
   int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   float tot = p.up[2 * p.S] / (float)p.S;
   if (chunk * kCombineChunk < p.n[s]) {
@@ -537,6 +569,14 @@ size_t vsl_loss_workspace_bytes(const VslDesc* desc) {
   return best;
 }
 
+int vsl_loss_workspace_init(const VslDesc* d, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!desc_ok(d)) return VSL_ERR_BAD_DESC;
+  if (!workspace) return VSL_ERR_NULL_POINTER;
+  if (workspace_bytes < vsl_loss_workspace_bytes(d)) return VSL_ERR_WORKSPACE;
+  VSL_CUDA_OK(cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream));
+  return VSL_OK;
+}
+
 int vsl_loss_forward_backward(const VslDesc* d, const VslLossBuffers* buf, void* workspace, size_t workspace_bytes,
                               void* stream) {
   return vsl_loss_forward_backward_timed(d, buf, workspace, workspace_bytes, stream, nullptr, nullptr);
@@ -663,7 +703,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   sp.kpartial = pl.kpartial;
   sp.smooth_weight = d->smooth_weight;
 
-  VSL_CUDA_OK(cudaMemsetAsync(sp.counter, 0, sizeof(unsigned), st));
+  // sp.counter: zero on entry (vsl_loss_workspace_init, once per workspace), reset by the last epilogue block
   if (event_before) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_before, st));
   int rc;
   const bool bf16 = d->image_dtype == VSL_DTYPE_BF16;
@@ -702,7 +742,8 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
       if (active > gx) gx = active;
       sp.epilogue_blocks += (unsigned)active * d->batch;
     }
-    k_epilogue<<<dim3(gx, d->batch, S), kSmallNT, 0, st>>>(sp);
+    // programmatic launch right behind k_photometric (not when an event has to sit between the two)
+    VSL_CUDA_OK(launch_after(event_after == nullptr, k_epilogue, dim3(gx, d->batch, S), dim3(kSmallNT), 0, st, sp));
   }
   VSL_CUDA_OK(cudaGetLastError());
   return VSL_OK;
@@ -735,7 +776,7 @@ int vsl_loss_combine_grads(const VslDesc* d, const float* upstream, const VslLos
   }
   if ((grad_P_out || grad_T_out) && !buf->grad_P) return VSL_ERR_NULL_POINTER;
   dim3 grid(cp.chunks0, d->batch, d->num_scales);
-  k_combine<<<grid, kSmallNT, 0, (cudaStream_t)stream>>>(cp);
+  VSL_CUDA_OK(launch_after(true, k_combine, grid, dim3(kSmallNT), 0, (cudaStream_t)stream, cp));
   VSL_CUDA_OK(cudaGetLastError());
   return VSL_OK;
 }

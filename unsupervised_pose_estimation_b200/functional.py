@@ -215,6 +215,8 @@ class FusedLossPlan:
         ws = self._ws.get(device)
         if ws is None:
             ws = torch.empty(self.ws_bytes // 4, dtype=torch.float32, device=device)
+            check(self.lib.vsl_loss_workspace_init(ctypes.byref(self.desc), ws.data_ptr(), self.ws_bytes, _stream()),
+                  "vsl_loss_workspace_init")
             self._ws[device] = ws
         return ws
 

@@ -212,10 +212,7 @@ class ViewSynthesisLossMixin:
         disps = [outputs[("disp", s)] for s in opt.scales]
         dev = disps[0].device
         # one draw per scale, same shape/order/device as trainer.py:656-657
-        noise = None
-        if plan.automask:
-            noise = [torch.randn((opt.batch_size, plan.noise_channels, opt.height, opt.width), device=dev)
-                     for _ in opt.scales]
+        noise = self._vsl_draw_noise(plan, dev, len(opt.scales)) if plan.automask else None
         pmasks, weighting = self._vsl_predictive_masks(outputs)
         side = getattr(self, "_vsl_side_pending", None)
         self._vsl_side_pending = None
@@ -234,6 +231,37 @@ class ViewSynthesisLossMixin:
         losses["loss"] = vec[2 * S] if weighting is None else vec[2 * S] + sum(weighting) / S
         self._vsl_gan_prior(inputs, outputs, losses)
         return losses
+
+    vsl_parallel_noise = True   # the S draws run as parallel branches (side streams); False: back to back on one stream
+
+    def _vsl_draw_noise(self, plan, dev, S):
+        """The tie-break noise of trainer.py:656-657: one ``randn`` per scale, in the reference's order, so the
+        global Philox stream is consumed exactly like the reference does (the offsets are assigned on the host, call
+        by call).  The S generator kernels are independent; enqueued on side streams they run as parallel branches
+        (also inside a captured CUDA graph) instead of four launch-latency-bound kernels in a row."""
+        shape = (plan.batch, plan.noise_channels, plan.height, plan.width)
+        if not self.vsl_parallel_noise or S == 1:
+            return [torch.randn(shape, device=dev) for _ in range(S)]
+        cur = torch.cuda.current_stream(dev)
+        side = getattr(self, "_vsl_noise_streams", None)
+        if side is None or len(side) < S - 1 or side[0].device != dev:
+            side = self._vsl_noise_streams = [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
+        noise = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(S)]   # allocated on `cur`
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        noise[0].normal_()                         # randn == empty + normal_(0, 1): same generator calls, same order
+        joins = []
+        for s in range(1, S):
+            st = side[s - 1]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                noise[s].normal_()
+                ev = torch.cuda.Event()
+                ev.record(st)
+                joins.append(ev)
+        for ev in joins:
+            cur.wait_event(ev)
+        return noise
 
     def _vsl_gan_prior(self, inputs, outputs, losses):
         """--pre_trained_generator (trainer.py:565-583, :684): the scale-invariant log loss between the generator's
@@ -283,7 +311,7 @@ class ViewSynthesisLossMixin:
         for plan, scale in zip(plans, opt.scales):
             disp = outputs[("disp", scale)]
             noise = None
-            if plan.automask:
+            if plan.automask:   # one level per call: a single draw
                 noise = [torch.randn((opt.batch_size, plan.noise_channels, plan.height, plan.width), device=disp.device)]
             pmasks, weighting = self._vsl_predictive_masks(outputs, [scale])
             vec, masks = VF.fused_loss(plan, [inputs[("color", 0, scale)]],
