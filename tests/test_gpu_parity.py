@@ -3,8 +3,9 @@
 The oracle (oracle/vsl_oracle.py) is run on the same GPU, where it IS the eager PyTorch-CUDA
 reference; integer / index-like results (sampling grid, bilinear tap indices, auto-mask) must be
 bit-exact, floating-point results within the tolerances written next to each assert
-(north_star: 1e-5 relative for losses and warped images; gradients are compared in rel-L2 and, because
-fp32 autograd itself is only that accurate, three-way against the fp64 oracle).
+(north_star: 1e-5 relative for losses, warped images and input gradients; the gradient gate is 1e-5 rel-L2 per
+leaf, 3e-5 for d/d disp at the warp resolution on i.i.d. images -- see grad_tol -- and three-way against the fp64
+oracle).
 Nothing here reads /root/reference: the committed goldens under tests/golden/ came from it.
 """
 import ctypes
@@ -59,6 +60,15 @@ def run_ours(opt, inputs, outputs, leaves, seed=123, side="eager"):
     losses = path.compute_losses(inputs, out)
     grads = torch.autograd.grad(losses["loss"], list(leaves.values()), allow_unused=True)
     return out, losses, {k: v for k, v in zip(leaves.keys(), grads) if v is not None}
+
+
+def grad_tol(key, family, opt=None):
+    """rel-L2 gate per leaf.  north_star's 1e-5 holds for every leaf on every case except d/d disp at the warp
+    resolution on i.i.d. images: there each value is a cancelling sum of SSIM terms over nine windows and the order
+    of those additions (tile gather here, autograd's avg_pool backward there) shows as 1e-5 .. 2.3e-5 — 200x below
+    the fp32 reference's own distance from fp64 (profiles/r2_grad_error_by_leaf.md, profiles/r2_case_grad_errors.md)."""
+    full_res = key[0] == "disp" and (key[1] == 0 or (opt is not None and opt.v1_multiscale))
+    return 3e-5 if (family == "iid" and full_res) else 1e-5
 
 
 def tap_indices(grid, H, W):
@@ -138,7 +148,7 @@ def test_fused_path_matches_oracle(name):
     assert set(g) == set(ref_g)
     for k in ref_g:  # rel-L2 of every input gradient
         err = ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item()
-        assert err <= 5e-5, (k, err)
+        assert err <= grad_tol(k, CASES[name][5], opt), (k, err)
 
 
 def test_randomised_shapes_and_options():
@@ -247,7 +257,7 @@ def test_bf16_image_storage(frames):
     for k in ref_losses:
         assert abs(losses[k].item() - ref_losses[k].item()) <= 1e-6 * abs(ref_losses[k].item()), k
     for k in ref_g:  # north_star allows 1e-2 in bf16 mode; with identical inputs the fp32 bound holds
-        assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
+        assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 1e-5, k
     with pytest.raises(TypeError):  # mixed storage types are rejected
         mixed = dict(in16)
         mixed[("color", -1, 0)] = inputs[("color", -1, 0)]
@@ -377,7 +387,7 @@ def test_full_size_properties_c1():
     for s in opt.scales:
         assert torch.equal(out1["identity_selection/%d" % s], ref_out["identity_selection/%d" % s])
     for k in ref_g:
-        assert ((g1[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
+        assert ((g1[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 1e-5, k
 
 
 @pytest.mark.parametrize("batch", [24, 48, 96])
@@ -395,7 +405,7 @@ def test_c5_per_gpu_batches(batch):
     for s in opt.scales:
         assert torch.equal(out["identity_selection/%d" % s], ref_out["identity_selection/%d" % s]), s
     for k in ref_g:
-        assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 5e-5, k
+        assert ((g[k] - ref_g[k]).norm() / ref_g[k].norm()).item() <= 1e-5, k
     del ref_out, ref_l, ref_g
     torch.cuda.empty_cache()
 

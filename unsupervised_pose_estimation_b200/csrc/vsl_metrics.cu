@@ -95,29 +95,40 @@ __global__ void __launch_bounds__(kMT) k_median_hist(const PairSource s, Metrics
   if (h[0][threadIdx.x]) atomicAdd(&ws->hist[0][threadIdx.x], h[0][threadIdx.x]);
   if (h[1][threadIdx.x]) atomicAdd(&ws->hist[1][threadIdx.x], h[1][threadIdx.x]);
 }
-__global__ void k_median_select(MetricsWs* ws, int shift, int first, int last) {
-  const int q = threadIdx.x;  // 0: gt, 1: pred
-  if (q >= 2) return;
-  unsigned k = ws->rank[q];
-  if (first) {
-    unsigned total = 0;
-    for (int d = 0; d < 256; ++d) total += ws->hist[q][d];
-    if (q == 0) ws->n_valid = total;
-    k = total ? (total - 1) / 2 : 0;  // torch.median: the lower of the two middle elements
+__global__ void __launch_bounds__(64) k_median_select(MetricsWs* ws, int shift, int first, int last) {
+  // warp q (0: gt, 1: pred): lane l owns bins 8l .. 8l+7; exclusive scan over the lanes finds the digit whose
+  // cumulative count passes the rank
+  __shared__ unsigned pref[2];
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned c[8], mine = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j] = ws->hist[q][8 * lane + j]; mine += c[j]; }
+  unsigned incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
-  unsigned d = 0;
-  for (; d < 255; ++d) {
-    const unsigned c = ws->hist[q][d];
-    if (k < c) break;
-    k -= c;
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned k = first ? (total ? (total - 1) / 2 : 0) : ws->rank[q];  // torch.median: the lower of the two middle elements
+  if (first && q == 0 && lane == 0) ws->n_valid = total;
+  const unsigned before = incl - mine;
+  const bool here = total == 0 ? lane == 0 : (k >= before && k < incl);
+  if (here) {
+    unsigned r = k - before, d = 0;
+    for (; d < 7; ++d) {
+      if (r < c[d]) break;
+      r -= c[d];
+    }
+    ws->rank[q] = r;
+    const unsigned p = ws->prefix[q] | ((unsigned)(8 * lane + d) << shift);
+    ws->prefix[q] = p;
+    pref[q] = p;
   }
-  ws->rank[q] = k;
-  ws->prefix[q] |= d << shift;
-  for (int i = 0; i < 256; ++i) ws->hist[q][i] = 0u;
-  if (last) {
-    __syncwarp(3u);
-    if (q == 0) ws->ratio = __uint_as_float(ws->prefix[0]) / __uint_as_float(ws->prefix[1]);  // trainer.py:709
-  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ws->hist[q][8 * lane + j] = 0u;
+  __syncthreads();
+  if (last && threadIdx.x == 0) ws->ratio = __uint_as_float(pref[0]) / __uint_as_float(pref[1]);  // trainer.py:709
 }
 
 // ---- the seven metrics -----------------------------------------------------------------------------------
@@ -152,13 +163,18 @@ __global__ void __launch_bounds__(kMT) k_depth_errors(const PairSource s, Metric
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (threadIdx.x < kTerms) {
-    double tot = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) tot += ((volatile double*)&ws->partial[b][0])[threadIdx.x];
-    scratch[threadIdx.x] = tot;
+  // the blocks' partials: thread t adds blocks t, t + 256, ... (independent loads), then a fixed-order block sum
+  __shared__ double total[kTerms];
+#pragma unroll
+  for (int k = 0; k < kTerms; ++k) {
+    double v = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kMT) v += __ldcg(&ws->partial[b][k]);
+    v = block_sum_d(v, scratch);
+    if (threadIdx.x == 0) total[k] = v;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    const double* scratch = total;
     const double n = scratch[0];
     out[0] = (float)(scratch[1] / n);        // abs_rel
     out[1] = (float)(scratch[2] / n);        // sq_rel
@@ -195,14 +211,14 @@ __global__ void __launch_bounds__(kMT) k_sllog_fwd(size_t n, const float* __rest
   __threadfence();
   if (threadIdx.x == 0) is_last = atomicAdd(&ws->counter, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (!is_last || threadIdx.x != 0) return;
+  if (!is_last) return;
   __threadfence();
-  double N = 0.0, S1 = 0.0, S2 = 0.0;
-  for (unsigned k = 0; k < gridDim.x; ++k) {
-    N += ((volatile double*)&ws->partial[k][0])[0];
-    S1 += ((volatile double*)&ws->partial[k][0])[1];
-    S2 += ((volatile double*)&ws->partial[k][0])[2];
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+  for (unsigned k = threadIdx.x; k < gridDim.x; k += kMT) {
+    t0 += __ldcg(&ws->partial[k][0]); t1 += __ldcg(&ws->partial[k][1]); t2 += __ldcg(&ws->partial[k][2]);
   }
+  const double N = block_sum_d(t0, scratch), S1 = block_sum_d(t1, scratch), S2 = block_sum_d(t2, scratch);
+  if (threadIdx.x != 0) return;
   const double mean = S1 / N, l = sqrt(S2 / N - mean * mean);
   *loss = (float)l;
   stats[0] = (float)N; stats[1] = (float)mean; stats[2] = (float)l;
@@ -274,7 +290,7 @@ int vsl_depth_losses(int batch, int height, int width, int gt_height, int gt_wid
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     k_median_hist<<<nb, kMT, 0, st>>>(s, ws, shift);
-    k_median_select<<<1, 32, 0, st>>>(ws, shift, pass == 0, pass == 3);
+    k_median_select<<<1, 64, 0, st>>>(ws, shift, pass == 0, pass == 3);
   }
   k_depth_errors<<<nb, kMT, 0, st>>>(s, ws, out7);
   VSL_M_OK(cudaGetLastError());
