@@ -202,6 +202,25 @@ int vsl_pose_forward(int batch, int invert, int arith, const float* axisangle, c
 /* its backward: grad_T [B,4,4] -> grad_axisangle [B,3], grad_translation [B,3] */
 int vsl_pose_backward(int batch, int invert, const float* axisangle, const float* translation,
                       const float* grad_T, float* grad_axisangle, float* grad_translation, void* stream);
+/* The posecnn pose tail (--pose_model_type posecnn, trainer.py:516-525) for every scale and frame at once:
+ *   T[s][f] = transformation_from_parameters(axisangle_f, translation_f * mean_inv_depth_s, invert_f)   [S][F][B][16]
+ *   mean_inv_depth_s[b] = mean over the H x W pixels of 1 / depth_s (depth_s = disp_to_depth of the up-sampled disp_s)
+ * desc gives batch, sizes, scales and the depth range; axisangle / translation [B,3] per frame; invert [F] on the HOST.
+ * The per-pixel values are the reference's bits, the mean is accumulated in fp64 in a fixed order (the reference takes
+ * two fp32 torch means in a row), so T matches the torch ops to ~1e-7 relative rather than bit for bit.
+ * workspace: vsl_posecnn_workspace_bytes, 8-byte aligned.  mean_inv [S][B] is kept for the backward. */
+size_t vsl_posecnn_workspace_bytes(const VslDesc* desc);
+int vsl_posecnn_forward(const VslDesc* desc, const float* const disp[VSL_MAX_SCALES], int num_frames,
+                        const float* const axisangle[VSL_MAX_SRC], const float* const translation[VSL_MAX_SRC],
+                        const int32_t* invert, int pose_arith, float* T, float* mean_inv, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* its backward: grad_T [S][F][B][16] -> grad_axisangle / grad_translation [B,3] per frame and grad_disp_const [S][B],
+ * the value every pixel of d L / d disp_s[b] receives through the mean (the bilinear up-sample preserves the mean, so
+ * d mean_inv_depth_s / d disp_s[j] = disp_range / (hs ws) for every j). */
+int vsl_posecnn_backward(const VslDesc* desc, int num_frames, const float* const axisangle[VSL_MAX_SRC],
+                         const float* const translation[VSL_MAX_SRC], const int32_t* invert, const float* mean_inv,
+                         const float* grad_T, float* const grad_axisangle[VSL_MAX_SRC],
+                         float* const grad_translation[VSL_MAX_SRC], float* grad_disp_const, void* stream);
 /* BackprojectDepth.forward (layers.py:234-239): depth [B,1,h,w], inv_K [B,4,4] -> cam [B,4,hw] */
 int vsl_backproject_forward(int batch, int height, int width, int arith, const float* depth,
                             const float* inv_K, float* cam_points, void* stream);

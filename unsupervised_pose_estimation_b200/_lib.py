@@ -49,6 +49,7 @@ EXPORTED_SYMBOLS = [
     "vsl_pyramid_workspace_bytes", "vsl_pyramid_plan", "vsl_pyramid_forward", "vsl_pyramid_coefficients",
     "vsl_source_grad_upstream", "vsl_grid_sample_backward_source",
     "vsl_pyramid_forward_flip", "vsl_stereo_transform",
+    "vsl_posecnn_workspace_bytes", "vsl_posecnn_forward", "vsl_posecnn_backward",
     "vsl_metrics_workspace_bytes", "vsl_depth_errors", "vsl_depth_losses", "vsl_sllog_forward", "vsl_sllog_backward",
 ]
 
@@ -164,6 +165,14 @@ def load():
     lib.vsl_source_grad_upstream.argtypes = [POINTER(VslDesc), vp, POINTER(c_void_p * VSL_MAX_SCALES), vp,
                                              POINTER(c_void_p * VSL_MAX_SCALES), vp]
     lib.vsl_grid_sample_backward_source.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
+    lib.vsl_posecnn_workspace_bytes.restype = c_size_t
+    lib.vsl_posecnn_workspace_bytes.argtypes = [POINTER(VslDesc)]
+    lib.vsl_posecnn_forward.argtypes = [POINTER(VslDesc), POINTER(c_void_p * VSL_MAX_SCALES), c_int,
+                                        POINTER(c_void_p * VSL_MAX_SRC), POINTER(c_void_p * VSL_MAX_SRC),
+                                        POINTER(c_int32 * VSL_MAX_SRC), c_int, vp, vp, vp, c_size_t, vp]
+    lib.vsl_posecnn_backward.argtypes = [POINTER(VslDesc), c_int, POINTER(c_void_p * VSL_MAX_SRC),
+                                         POINTER(c_void_p * VSL_MAX_SRC), POINTER(c_int32 * VSL_MAX_SRC), vp, vp,
+                                         POINTER(c_void_p * VSL_MAX_SRC), POINTER(c_void_p * VSL_MAX_SRC), vp, vp]
     lib.vsl_metrics_workspace_bytes.restype = c_size_t
     lib.vsl_metrics_workspace_bytes.argtypes = []
     lib.vsl_depth_errors.argtypes = [c_size_t, vp, vp, vp, vp, c_size_t, vp]

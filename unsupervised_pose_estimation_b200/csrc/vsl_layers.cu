@@ -355,13 +355,8 @@ __global__ void __launch_bounds__(kNT) k_pose_fwd(int B, int invert, int arith, 
   for (int k = 0; k < 16; ++k) T[16 * b + k] = M[k];
 }
 // Rodrigues backward: R = ca I + sa [a]x + (1 - ca) a a^T, a = v / (|v| + 1e-7)
-__global__ void __launch_bounds__(kNT) k_pose_bwd(int B, int invert, const float* __restrict__ aa,
-                                                  const float* __restrict__ tr, const float* __restrict__ gT,
-                                                  float* __restrict__ gaa, float* __restrict__ gtr) {
-  int b = blockIdx.x * kNT + threadIdx.x;
-  if (b >= B) return;
-  const float v[3] = {aa[3 * b], aa[3 * b + 1], aa[3 * b + 2]}, t[3] = {tr[3 * b], tr[3 * b + 1], tr[3 * b + 2]};
-  const float* g = gT + 16 * b;
+__device__ __forceinline__ void pose_backward(const float v[3], const float t[3], bool invert, const float* __restrict__ g,
+                                              float gaa[3], float gtr[3]) {
   const float th = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), den = th + 1e-7f;
   const float a[3] = {v[0] / den, v[1] / den, v[2] / den};
   const float ca = cosf(th), sa = sinf(th), C = 1.0f - ca;
@@ -404,9 +399,116 @@ __global__ void __launch_bounds__(kNT) k_pose_bwd(int B, int invert, const float
   const float k = th > 0.f ? gth / th : 0.f;  // d|v|/dv = v/|v| (torch gives 0 at the origin)
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    gaa[3 * b + i] = ga[i] / den + k * v[i];
-    gtr[3 * b + i] = gt[i];
+    gaa[i] = ga[i] / den + k * v[i];
+    gtr[i] = gt[i];
   }
+}
+__global__ void __launch_bounds__(kNT) k_pose_bwd(int B, int invert, const float* __restrict__ aa,
+                                                  const float* __restrict__ tr, const float* __restrict__ gT,
+                                                  float* __restrict__ gaa, float* __restrict__ gtr) {
+  int b = blockIdx.x * kNT + threadIdx.x;
+  if (b >= B) return;
+  const float v[3] = {aa[3 * b], aa[3 * b + 1], aa[3 * b + 2]}, t[3] = {tr[3 * b], tr[3 * b + 1], tr[3 * b + 2]};
+  float ga[3], gt[3];
+  pose_backward(v, t, invert != 0, gT + 16 * b, ga, gt);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { gaa[3 * b + i] = ga[i]; gtr[3 * b + i] = gt[i]; }
+}
+
+// ---- posecnn pose tail (trainer.py:516-525) ------------------------------------------------------------------
+// T_{s,f} = transformation_from_parameters(axisangle_f, translation_f * mean_inv_depth_s, f < 0) with
+// mean_inv_depth_s = mean over the pixels of 1 / depth_s (depth_s from the up-sampled disp_s): one reduction
+// launch for every scale and image, one launch for every pose.  The per-pixel values are the reference's bits
+// (up-sample, disp_to_depth, two reciprocals); the MEAN is accumulated in fp64 in a fixed order, whereas the
+// reference takes two fp32 torch means in a row, so T agrees to ~1e-7 relative, not bit for bit (opt-in, see
+// trainer.vsl_posecnn_tail).
+constexpr int kPcChunk = 4096;  // pixels per block of the reduction
+struct PoseCnnParams {
+  const float* disp[VSL_MAX_SCALES];
+  int hs[VSL_MAX_SCALES], ws[VSL_MAX_SCALES], identity[VSL_MAX_SCALES];
+  float scale_h[VSL_MAX_SCALES], scale_w[VSL_MAX_SCALES];
+  const float* aa[VSL_MAX_SRC];
+  const float* tr[VSL_MAX_SRC];
+  int invert[VSL_MAX_SRC];
+  int B, H, W, S, F, arith, nchunk;
+  GeoConst g;
+  double* partial;   // [S][B][nchunk]
+  float* mean_inv;   // [S][B]
+  float* T;          // [S][F][B][16]
+};
+__global__ void __launch_bounds__(kNT) k_posecnn_partial(const PoseCnnParams p) {
+  __shared__ double scratch[kNT / 32];
+  const int s = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x, HW = p.H * p.W;
+  const float* d = p.disp[s] + (size_t)b * p.hs[s] * p.ws[s];
+  double acc = 0.0;
+  for (int i = chunk * kPcChunk + threadIdx.x; i < min(HW, (chunk + 1) * kPcChunk); i += kNT) {
+    const int v = i / p.W, u = i - v * p.W;
+    const float D = upsample_disp(d, p.hs[s], p.ws[s], p.scale_h[s], p.scale_w[s], p.identity[s] != 0, v, u, p.arith);
+    acc += (double)rcp_rn(disp_to_z(D, p.g));  // inv_depth = 1 / depth, depth = 1 / scaled_disp (layers.py:90-93)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < kNT / 32; ++i) r += scratch[i];
+    p.partial[((size_t)s * p.B + b) * p.nchunk + chunk] = r;
+  }
+}
+__global__ void __launch_bounds__(kNT) k_posecnn_pose(const PoseCnnParams p) {
+  // grid-stride over (s, f, b); every thread re-adds its (s, b) partials in chunk order (a few dozen values)
+  for (int idx = blockIdx.x * kNT + threadIdx.x; idx < p.S * p.F * p.B; idx += gridDim.x * kNT) {
+    const int b = idx % p.B, f = (idx / p.B) % p.F, s = idx / (p.B * p.F);
+    double sum = 0.0;
+    for (int c = 0; c < p.nchunk; ++c) sum += p.partial[((size_t)s * p.B + b) * p.nchunk + c];
+    const float mean = (float)(sum / (double)(p.H * p.W));
+    if (f == 0) p.mean_inv[s * p.B + b] = mean;
+    const float v[3] = {p.aa[f][3 * b], p.aa[f][3 * b + 1], p.aa[f][3 * b + 2]};
+    const float t[3] = {mul_rn(p.tr[f][3 * b], mean), mul_rn(p.tr[f][3 * b + 1], mean), mul_rn(p.tr[f][3 * b + 2], mean)};
+    float M[16];
+    pose_matrix(v, t, p.invert[f] != 0, p.arith, M);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) p.T[(size_t)idx * 16 + k] = M[k];
+  }
+}
+struct PoseCnnBwdParams {
+  const float* aa[VSL_MAX_SRC];
+  const float* tr[VSL_MAX_SRC];
+  int invert[VSL_MAX_SRC];
+  float* gaa[VSL_MAX_SRC];
+  float* gtr[VSL_MAX_SRC];
+  const float* mean_inv;   // [S][B]
+  const float* gT;         // [S][F][B][16]
+  float* gdisp_const;      // [S][B]: d L / d disp_s[b, any pixel] contributed through the mean
+  float per_pixel[VSL_MAX_SCALES];  // disp_range / (hs * ws): d mean_inv_depth_s / d disp_s[j] (the up-sample preserves the mean)
+  int B, S, F;
+};
+__global__ void __launch_bounds__(kNT) k_posecnn_bwd(const PoseCnnBwdParams p) {
+  const int b = blockIdx.x * kNT + threadIdx.x;
+  if (b >= p.B) return;
+  float gmean[VSL_MAX_SCALES] = {0.f, 0.f, 0.f, 0.f};
+  for (int f = 0; f < p.F; ++f) {
+    const float v[3] = {p.aa[f][3 * b], p.aa[f][3 * b + 1], p.aa[f][3 * b + 2]};
+    const float tr[3] = {p.tr[f][3 * b], p.tr[f][3 * b + 1], p.tr[f][3 * b + 2]};
+    float ga[3] = {0.f, 0.f, 0.f}, gt[3] = {0.f, 0.f, 0.f};
+    for (int s = 0; s < p.S; ++s) {
+      const float m = p.mean_inv[s * p.B + b];
+      const float t[3] = {tr[0] * m, tr[1] * m, tr[2] * m};
+      float ga_s[3], gt_s[3];
+      pose_backward(v, t, p.invert[f] != 0, p.gT + ((size_t)(s * p.F + f) * p.B + b) * 16, ga_s, gt_s);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        ga[i] += ga_s[i];
+        gt[i] += gt_s[i] * m;
+        gmean[s] += gt_s[i] * tr[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { p.gaa[f][3 * b + i] = ga[i]; p.gtr[f][3 * b + i] = gt[i]; }
+  }
+  for (int s = 0; s < p.S; ++s) p.gdisp_const[s * p.B + b] = gmean[s] * p.per_pixel[s];
 }
 
 static unsigned blocks_for(size_t n) { return (unsigned)((n + kNT - 1) / kNT); }
@@ -549,6 +651,78 @@ int vsl_smooth_loss_backward(int B, int H, int W, const float* disp, const float
   if (B < 1 || H < 2 || W < 2) return VSL_ERR_BAD_DESC;
   if (!disp || !img || !gl || !gdisp) return VSL_ERR_NULL_POINTER;
   k_smooth_bwd<<<dim3(blocks_for((size_t)H * W), B), kNT, 0, (cudaStream_t)stream>>>(B, H, W, disp, img, gl, gdisp);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+
+
+static bool posecnn_desc_ok(const VslDesc* d, int num_frames) {
+  if (!d || d->abi_version != VSL_ABI_VERSION) return false;
+  if (d->batch < 1 || d->height < 2 || d->width < 2 || d->num_scales < 1 || d->num_scales > VSL_MAX_SCALES) return false;
+  if (num_frames < 1 || num_frames > VSL_MAX_SRC) return false;
+  for (int s = 0; s < d->num_scales; ++s) {
+    const int e = d->scale_ids[s];
+    if (e < 0 || e > 3 || ((d->height >> e) << e) != d->height || ((d->width >> e) << e) != d->width) return false;
+  }
+  return true;
+}
+size_t vsl_posecnn_workspace_bytes(const VslDesc* d) {
+  if (!posecnn_desc_ok(d, 1)) return 0;
+  const size_t nchunk = ((size_t)d->height * d->width + kPcChunk - 1) / kPcChunk;
+  return (size_t)d->num_scales * d->batch * nchunk * sizeof(double);
+}
+int vsl_posecnn_forward(const VslDesc* d, const float* const disp[VSL_MAX_SCALES], int num_frames,
+                        const float* const axisangle[VSL_MAX_SRC], const float* const translation[VSL_MAX_SRC],
+                        const int32_t* invert, int pose_arith, float* T, float* mean_inv, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (!posecnn_desc_ok(d, num_frames)) return VSL_ERR_BAD_DESC;
+  if (!disp || !axisangle || !translation || !invert || !T || !mean_inv || !workspace) return VSL_ERR_NULL_POINTER;
+  if (workspace_bytes < vsl_posecnn_workspace_bytes(d)) return VSL_ERR_WORKSPACE;
+  if (((uintptr_t)workspace & 7u) != 0) return VSL_ERR_MISALIGNED;
+  PoseCnnParams p = {};
+  p.B = d->batch; p.H = d->height; p.W = d->width; p.S = d->num_scales; p.F = num_frames;
+  p.arith = d->arith | pose_arith;
+  p.nchunk = (d->height * d->width + kPcChunk - 1) / kPcChunk;
+  p.g.min_disp = d->min_disp; p.g.disp_range = d->disp_range; p.g.eps = d->eps; p.g.one = 1.0f;
+  p.g.W = d->width; p.g.H = d->height; p.g.arith = d->arith;
+  p.partial = (double*)workspace; p.mean_inv = mean_inv; p.T = T;
+  for (int s = 0; s < p.S; ++s) {
+    if (!disp[s]) return VSL_ERR_NULL_POINTER;
+    const int e = d->scale_ids[s];
+    p.disp[s] = disp[s]; p.hs[s] = d->height >> e; p.ws[s] = d->width >> e; p.identity[s] = e == 0;
+    p.scale_h[s] = (float)p.hs[s] / (float)d->height; p.scale_w[s] = (float)p.ws[s] / (float)d->width;
+  }
+  for (int f = 0; f < p.F; ++f) {
+    if (!axisangle[f] || !translation[f]) return VSL_ERR_NULL_POINTER;
+    p.aa[f] = axisangle[f]; p.tr[f] = translation[f]; p.invert[f] = invert[f];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  k_posecnn_partial<<<dim3(p.nchunk, p.B, p.S), kNT, 0, st>>>(p);
+  VSL_L_OK(cudaGetLastError());
+  k_posecnn_pose<<<blocks_for((size_t)p.S * p.F * p.B), kNT, 0, st>>>(p);
+  VSL_L_OK(cudaGetLastError());
+  return VSL_OK;
+}
+int vsl_posecnn_backward(const VslDesc* d, int num_frames, const float* const axisangle[VSL_MAX_SRC],
+                         const float* const translation[VSL_MAX_SRC], const int32_t* invert, const float* mean_inv,
+                         const float* grad_T, float* const grad_axisangle[VSL_MAX_SRC],
+                         float* const grad_translation[VSL_MAX_SRC], float* grad_disp_const, void* stream) {
+  if (!posecnn_desc_ok(d, num_frames)) return VSL_ERR_BAD_DESC;
+  if (!axisangle || !translation || !invert || !mean_inv || !grad_T || !grad_axisangle || !grad_translation || !grad_disp_const)
+    return VSL_ERR_NULL_POINTER;
+  PoseCnnBwdParams p = {};
+  p.B = d->batch; p.S = d->num_scales; p.F = num_frames;
+  p.mean_inv = mean_inv; p.gT = grad_T; p.gdisp_const = grad_disp_const;
+  for (int s = 0; s < p.S; ++s) {
+    const int e = d->scale_ids[s];
+    p.per_pixel[s] = d->disp_range / ((float)(d->height >> e) * (float)(d->width >> e));
+  }
+  for (int f = 0; f < p.F; ++f) {
+    if (!axisangle[f] || !translation[f] || !grad_axisangle[f] || !grad_translation[f]) return VSL_ERR_NULL_POINTER;
+    p.aa[f] = axisangle[f]; p.tr[f] = translation[f]; p.invert[f] = invert[f];
+    p.gaa[f] = grad_axisangle[f]; p.gtr[f] = grad_translation[f];
+  }
+  k_posecnn_bwd<<<blocks_for((size_t)p.B), kNT, 0, (cudaStream_t)stream>>>(p);
   VSL_L_OK(cudaGetLastError());
   return VSL_OK;
 }

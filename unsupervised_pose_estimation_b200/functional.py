@@ -161,6 +161,74 @@ def pose_matrix(axisangle, translation, invert=False, arith="auto"):
     return _PoseMatrix.apply(axisangle, translation, bool(invert), arith)
 
 
+class _PoseCnnTail(torch.autograd.Function):
+    """trainer.py:516-525 for every scale and frame: T[s][f] from (axisangle_f, translation_f, disp_s)."""
+
+    @staticmethod
+    def forward(ctx, plan, inverts, arith, n_frames, *tensors):
+        S, F, B = len(plan.scales), n_frames, plan.batch
+        aa = [_dev(t, "axisangle") for t in tensors[:F]]
+        tr = [_dev(t, "translation") for t in tensors[F:2 * F]]
+        disps = [_dev(t, "disp") for t in tensors[2 * F:]]
+        for t in aa + tr:
+            if t.numel() != 3 * B:
+                raise ValueError("axisangle / translation must hold [B,3] values, got %s" % (tuple(t.shape),))
+        for s, d in enumerate(disps):
+            if tuple(d.shape) != plan.level_shapes[s]:
+                raise ValueError("disp[%d] has shape %s, plan expects %s" % (s, tuple(d.shape), plan.level_shapes[s]))
+        dev = disps[0].device
+        lib = plan.lib
+        T = torch.empty(S, F, B, 4, 4, dtype=torch.float32, device=dev)
+        mean_inv = torch.empty(S, B, dtype=torch.float32, device=dev)
+        nbytes = lib.vsl_posecnn_workspace_bytes(ctypes.byref(plan.desc))
+        ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+        dp, ap, tp = (ctypes.c_void_p * VSL_MAX_SCALES)(), (ctypes.c_void_p * VSL_MAX_SRC)(), (ctypes.c_void_p * VSL_MAX_SRC)()
+        inv = (ctypes.c_int32 * VSL_MAX_SRC)()
+        for s in range(S):
+            dp[s] = disps[s].data_ptr()
+        for f in range(F):
+            ap[f], tp[f], inv[f] = aa[f].data_ptr(), tr[f].data_ptr(), int(inverts[f])
+        check(lib.vsl_posecnn_forward(ctypes.byref(plan.desc), ctypes.byref(dp), F, ctypes.byref(ap), ctypes.byref(tp),
+                                      ctypes.byref(inv), int(arith), T.data_ptr(), mean_inv.data_ptr(), ws.data_ptr(),
+                                      nbytes, _stream()), "vsl_posecnn_forward")
+        ctx.save_for_backward(mean_inv, *aa, *tr)
+        ctx.meta = (plan, list(inverts), F, [t.shape for t in tensors[:2 * F]])
+        return T
+
+    @staticmethod
+    def backward(ctx, gT):
+        plan, inverts, F, shapes = ctx.meta
+        S, B = len(plan.scales), plan.batch
+        mean_inv = ctx.saved_tensors[0]
+        aa, tr = ctx.saved_tensors[1:1 + F], ctx.saved_tensors[1 + F:1 + 2 * F]
+        gT = _dev(gT, "grad_T")
+        dev = gT.device
+        gaa = [torch.empty(B, 3, dtype=torch.float32, device=dev) for _ in range(F)]
+        gtr = [torch.empty(B, 3, dtype=torch.float32, device=dev) for _ in range(F)]
+        gconst = torch.empty(S, B, dtype=torch.float32, device=dev)
+        ap, tp = (ctypes.c_void_p * VSL_MAX_SRC)(), (ctypes.c_void_p * VSL_MAX_SRC)()
+        gap, gtp = (ctypes.c_void_p * VSL_MAX_SRC)(), (ctypes.c_void_p * VSL_MAX_SRC)()
+        inv = (ctypes.c_int32 * VSL_MAX_SRC)()
+        for f in range(F):
+            ap[f], tp[f], inv[f] = aa[f].data_ptr(), tr[f].data_ptr(), int(inverts[f])
+            gap[f], gtp[f] = gaa[f].data_ptr(), gtr[f].data_ptr()
+        check(plan.lib.vsl_posecnn_backward(ctypes.byref(plan.desc), F, ctypes.byref(ap), ctypes.byref(tp), ctypes.byref(inv),
+                                            mean_inv.data_ptr(), gT.data_ptr(), ctypes.byref(gap), ctypes.byref(gtp),
+                                            gconst.data_ptr(), _stream()), "vsl_posecnn_backward")
+        gd = [gconst[s].view(B, 1, 1, 1).expand(plan.level_shapes[s]) for s in range(S)]
+        grads = [g.view(sh) for g, sh in zip(gaa + gtr, shapes)]
+        return (None, None, None, None) + tuple(grads) + tuple(gd)
+
+
+def posecnn_poses(plan, axisangles, translations, inverts, disps, arith="auto"):
+    """[[T_{s,f} for f] for s]: the posecnn pose tail (trainer.py:516-525) in two launches (+ one backward launch)."""
+    if arith == "auto":
+        arith = calibrate_pose_arith(plan.batch, disps[0].device)
+    F = len(axisangles)
+    T = _PoseCnnTail.apply(plan, list(inverts), arith, F, *(list(axisangles) + list(translations) + list(disps)))
+    return [[T[s, f] for f in range(F)] for s in range(len(plan.scales))]
+
+
 # --------------------------------------------------------------------------------------------------
 # fused loss
 # --------------------------------------------------------------------------------------------------

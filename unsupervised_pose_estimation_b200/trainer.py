@@ -43,6 +43,10 @@ class ViewSynthesisLossMixin:
 
     vsl_side_outputs = "eager"
     vsl_arith = "auto"  # VSL_ARITH_* bits, or "auto": calibrate against torch.bmm once per shape
+    # --pose_model_type posecnn (trainer.py:516-525): "torch" forms the per-scale poses with the reference's own ops
+    # (bit-identical sampling grids); "fused" uses vsl_posecnn_forward/backward — three launches instead of ~40 torch
+    # ops per step, the mean inverse depth accumulated in fp64 (poses agree to ~1e-7, not bit for bit)
+    vsl_posecnn_tail = "torch"
 
     # -- plan ---------------------------------------------------------------------------------
     vsl_image_dtype = torch.float32  # storage of the colour images: torch.float32 or torch.bfloat16
@@ -115,6 +119,13 @@ class ViewSynthesisLossMixin:
         opt = self.opt
         if getattr(opt, "pose_model_type", "separate_resnet") != "posecnn":
             return [inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)] for f in opt.frame_ids[1:]]
+        plan = getattr(self, "_vsl_plan_cache", (None, None))[1]
+        if (self.vsl_posecnn_tail == "fused" and scales is None and plan is not None and not isinstance(plan, list)
+                and outputs[("disp", opt.scales[0])].is_cuda):
+            frames = opt.frame_ids[1:]
+            return VF.posecnn_poses(plan, [outputs[("axisangle", 0, f)][:, 0] for f in frames],
+                                    [outputs[("translation", 0, f)][:, 0] for f in frames], [f < 0 for f in frames],
+                                    [outputs[("disp", s)] for s in opt.scales])
         from .layers import disp_to_depth, transformation_from_parameters
         per_scale = []
         for scale in (opt.scales if scales is None else scales):
