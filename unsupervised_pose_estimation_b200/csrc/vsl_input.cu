@@ -205,16 +205,18 @@ __global__ void __launch_bounds__(256) k_u8_to_tensor_x4(const uint8_t* __restri
 // the taps in use).  Optionally the CTA also writes the CHW tensor of ITS part of the input level
 // (out_in: the 64 x 16 input pixels under the tile), which saves the separate conversion launch.
 constexpr int kTX = 32, kTY = 8, kRowsMax = 2 * kTY + kKsize + 1, kRowBytes = (2 * kTX + kKsize + 6) * 3 / 4 * 4 + 4;
+struct LanczosSmem {
+  __align__(16) uint8_t tin[kRowsMax][kRowBytes];  // input window of the tile
+  uint8_t hrow[kRowsMax][kTX][3];                  // its horizontal pass, rounded to 8 bits
+  int32_t kx[kTX][kKsize], ky[kTY][kKsize];        // the tile's coefficient rows (13 words: conflict-free)
+  int bx[kTX], by[kTY];                            // first tap of every output column / row
+};
 template <class Out, bool kWords>
-__global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
-                                                     Out* __restrict__ out_t, Out* __restrict__ out_in, AxisTable tx,
-                                                     AxisTable ty, int hi, int wi, const uint8_t* __restrict__ flip) {
-  __shared__ __align__(16) uint8_t tin[kRowsMax][kRowBytes];  // input window of the tile
-  __shared__ uint8_t hrow[kRowsMax][kTX][3];                  // its horizontal pass, rounded to 8 bits
-  __shared__ int32_t kx[kTX][kKsize], ky[kTY][kKsize];        // the tile's coefficient rows (13 words: conflict-free)
-  __shared__ int bx[kTX], by[kTY];                            // first tap of every output column / row
+__device__ __forceinline__ void lanczos_tile(LanczosSmem& sm, const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
+                                             Out* __restrict__ out_t, Out* __restrict__ out_in, AxisTable tx, AxisTable ty,
+                                             int hi, int wi, const uint8_t* __restrict__ flip, int b, int x0, int y0) {
+  auto& tin = sm.tin; auto& hrow = sm.hrow; auto& kx = sm.kx; auto& ky = sm.ky; auto& bx = sm.bx; auto& by = sm.by;
   const int ho = hi >> 1, wo = wi >> 1;
-  const int b = blockIdx.z, x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
   const int ylast = min(y0 + kTY, ho) - 1, xlast = min(x0 + kTX, wo) - 1;
   const int row_lo = ty.bounds[2 * y0];
   const int row_hi = ty.bounds[2 * ylast] + ty.bounds[2 * ylast + 1];  // exclusive
@@ -234,22 +236,55 @@ __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict_
     bx[o] = x0 + o < wo ? tx.bounds[2 * (x0 + o)] - col_lo : 0;
     if (o < kTY) by[o] = y0 + o < ho ? ty.bounds[2 * (y0 + o)] - row_lo : 0;
   }
-  if (flip && flip[b]) {
-    // mirrored read of the raw frame (level 1 only): window column c holds source column wi - 1 - (col_lo + c);
-    // byte loads, each pixel's three channels kept in order.  Everything after the staging sees a flipped image.
+  // Staging: every global load of a thread is issued before its first shared-memory store (a plain load -> store
+  // loop serialises one memory round trip per row: eight in a row per tile, which is what the kernel used to cost)
+  constexpr int kStageIt = (kRowsMax + 3) / 4;
+  if (kWords && flip && flip[b]) {
+    // mirrored read of the raw frame (level 1 only): window column c holds source column wi - 1 - (col_lo + c).
+    // Word loads over the mirrored source span; each byte is stored at its pixel's mirrored place, channels in order.
     const int ncol = ncolb / 3;
+    const int sb0 = (wi - col_lo - ncol) * 3, a0 = sb0 & ~3;     // source byte span [sb0, sb0 + ncolb), word-aligned start
+    const int nw = (sb0 + ncolb - a0 + 3) >> 2;                    // <= 60 words; stays inside the row (wi * 3 % 4 == 0)
+    const uint8_t* row0 = in + ((size_t)b * hi + row_lo) * pitch + a0;
+    const int w = threadIdx.x & 63;
+    uint32_t v[kStageIt];
+#pragma unroll
+    for (int k = 0; k < kStageIt; ++k) {
+      const int r = (threadIdx.x >> 6) + 4 * k;
+      v[k] = (r < nrows && w < nw) ? reinterpret_cast<const uint32_t*>(row0 + r * pitch)[w] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kStageIt; ++k) {
+      const int r = (threadIdx.x >> 6) + 4 * k;
+      if (r >= nrows || w >= nw) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int rel = a0 + 4 * w + q - sb0;
+        if (rel < 0 || rel >= ncolb) continue;
+        const int ps = rel / 3, ch = rel - 3 * ps;
+        tin[r][(ncol - 1 - ps) * 3 + ch] = (uint8_t)(v[k] >> (8 * q));
+      }
+    }
+  } else if (flip && flip[b]) {  // ragged widths: byte loads
     const uint8_t* row0 = in + ((size_t)b * hi + row_lo) * pitch;
     for (int idx = threadIdx.x; idx < nrows * ncolb; idx += 256) {
       const int r = idx / ncolb, j = idx - r * ncolb;
       const int c = j / 3, ch = j - 3 * c;
-      (void)ncol;
       tin[r][j] = row0[r * pitch + (size_t)(wi - 1 - (col_lo + c)) * 3 + ch];
     }
   } else if (kWords) {  // rows start on a word boundary (wi % 4 == 0; col_lo is a multiple of 4): <= 59 words per row
     const int nw = (ncolb + 3) >> 2;  // the last word may reach up to 3 bytes past the taps: still inside the row
-    for (int r = threadIdx.x >> 6; r < nrows; r += 4) {
-      const int w = threadIdx.x & 63;
-      if (w < nw) reinterpret_cast<uint32_t*>(tin[r])[w] = reinterpret_cast<const uint32_t*>(src + r * pitch)[w];
+    const int w = threadIdx.x & 63;
+    uint32_t v[kStageIt];
+#pragma unroll
+    for (int k = 0; k < kStageIt; ++k) {
+      const int r = (threadIdx.x >> 6) + 4 * k;
+      v[k] = (r < nrows && w < nw) ? reinterpret_cast<const uint32_t*>(src + r * pitch)[w] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kStageIt; ++k) {
+      const int r = (threadIdx.x >> 6) + 4 * k;
+      if (r < nrows && w < nw) reinterpret_cast<uint32_t*>(tin[r])[w] = v[k];
     }
   } else if ((int)threadIdx.x < ncolb) {  // one thread per byte column, independent loads down the rows
     const uint8_t* q = src + threadIdx.x;
@@ -309,6 +344,16 @@ __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict_
     store_tensor<Out>(dt, hw, v1);
     store_tensor<Out>(dt, 2 * hw, v2);
   }
+}
+
+// one 2:1 level per launch
+template <class Out, bool kWords>
+__global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
+                                                     Out* __restrict__ out_t, Out* __restrict__ out_in, AxisTable tx,
+                                                     AxisTable ty, int hi, int wi, const uint8_t* __restrict__ flip) {
+  __shared__ LanczosSmem sm;
+  lanczos_tile<Out, kWords>(sm, in, out_u8, out_t, out_in, tx, ty, hi, wi, flip, blockIdx.z, blockIdx.x * kTX,
+                            blockIdx.y * kTY);
 }
 
 template <class Out>
