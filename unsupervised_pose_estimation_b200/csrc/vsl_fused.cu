@@ -185,7 +185,10 @@ __global__ void __launch_bounds__(C::NT, C::NT >= 512 ? 1 : 2) k_photometric(con
       if (s + 1 < p.S) phase_store_level<C>(sm, tid, pre);  // phase_smooth of this scale is done with the buffer (barrier above)
     }
     __syncthreads();
-    if (!p.forward_only) phase_backward<C>(p, g, t, sm, s, tid, ts);
+    if (!p.forward_only) {
+      if constexpr (VSL_ADJ_PAIR && !C::AVG && C::TH % 2 == 0 && C::IN >= 2 * C::NT) phase_backward_pair<C>(p, g, t, sm, s, tid, ts);
+      else phase_backward<C>(p, g, t, sm, s, tid, ts);
+    }
     // deterministic block reduction of (loss, dP) -> one partial per CTA and scale
     const int w = tid >> 5, l = tid & 31;
 #pragma unroll

@@ -74,7 +74,7 @@ struct TileCfg {
   static constexpr int oX = oTS + 6 * WN;       // warped / source region  [F][3][RN]
   static constexpr int oId = oX + F * 3 * RN;   // identity losses         [F][WN]
   static constexpr int oCoef = oId + F * WN;    // per window: CoefRec (winner's SSIM adjoint coefficients + winner id)
-  static constexpr int oG = oCoef + 12 * WN * NREC;  // d warped / d(ix,iy)  [F][6][IN]
+  static constexpr int oG = oCoef + 12 * WN * NREC;  // d warped / d(ix,iy)  [F][3][IN] pairs (d/d ix, d/d iy)
   static constexpr int oRed = oG + F * 6 * IN;  // block-reduction scratch [NT/32][1 + F*12]
   static constexpr int oGD = oRed + (NT / 32) * (1 + F * 12);  // d/d(up-sampled disp) of the tile [IN]
   static constexpr int oH = oGD + IN;           // row-reduced adjoint [TH][TW/2 + 2]
@@ -98,6 +98,7 @@ struct TileCfg {
   static constexpr int kPartial = 1 + F * 12;   // photometric partials per (CTA, scale): loss, dL/dP
   static constexpr int kPartialAll = kPartial + 4;  // + smoothness: sum d, sum |dx| e, sum |dy| e, sum g d
   static_assert(oCoef % 4 == 0, "CoefRec needs 16-byte alignment");
+  static_assert(oG % 2 == 0 && oX % 2 == 0, "pair storage needs 8-byte alignment");
 };
 
 // One record per SSIM window: the 9 adjoint coefficients (A,B,C per channel) of the frame that won the
@@ -333,6 +334,29 @@ struct XLayout {
   }
 };
 
+// Tail of a window's reprojection loss from its nine window sums (per channel c: sum x, sum x^2, sum xy at
+// 3c..3c+2) and the centre pixel's |y - x|: pooled means, SSIM per channel, 0.85 mean_c SSIM + 0.15 mean_c L1
+// (layers.py:318-332, trainer.py:546-553).  One definition for every window-phase variant, so they agree bit for bit.
+template <class C>
+VSL_HD float window_loss_from_sums(const float (&sums)[9], const float (&l1)[3], const float* __restrict__ TS, int widx,
+                                   int arith, SsimOut so[3], bool no_ssim = false) {
+  if (no_ssim) {  // trainer.py:549-550: reprojection loss = mean_c |target - pred|
+#pragma unroll
+    for (int c = 0; c < 3; ++c) so[c].live = false;
+    return mean3(l1[0], l1[1], l1[2], arith);
+  }
+  float mean[9], ss[3];
+  div9_all<9>(sums, mean);  // one guard branch for the nine quotients
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    so[c] = ssim_from_means(mean[3 * c], mean[3 * c + 1], mean[3 * c + 2], TS[c * C::WN + widx], TS[(3 + c) * C::WN + widx]);
+    ss[c] = so[c].val;
+  }
+  float ms = mean3(ss[0], ss[1], ss[2], arith);
+  float ml = mean3(l1[0], l1[1], l1[2], arith);
+  return add_rn(mul_rn(0.85f, ms), mul_rn(0.15f, ml));
+}
+
 // SSIM + L1 of one window for one frame X (3 channels `cs` floats apart, pixels XS floats apart: XS = 1
 // for a single-frame buffer, 2 for one half of a pair buffer); returns the reprojection loss
 // (trainer.py:546-553) and leaves the per-channel SSIM state in `so`.
@@ -340,7 +364,7 @@ template <class C, int XS = 1>
 VSL_HD float reproj_window(const float* __restrict__ X, int cs, const float* __restrict__ T,
                            const float* __restrict__ TS, int wy, int wx, int widx, int arith, SsimOut so[3],
                            bool no_ssim = false) {
-  float ss[3], l1[3];
+  float l1[3];
   const int center = (wy + 1) * C::RW + (wx + 1);
   if (no_ssim) {  // trainer.py:549-550: reprojection loss = mean_c |target - pred|
 #pragma unroll
@@ -353,7 +377,7 @@ VSL_HD float reproj_window(const float* __restrict__ X, int cs, const float* __r
   // Window sums in avg_pool2d's order (row-major, sequential).  The accumulator's initial 0 + v is skipped:
   // it changes the result only when every term is -0, and a -0 instead of +0 sum leaves every later value of
   // the SSIM chain unchanged (each is added to a non-zero constant before it is used).
-  float sums[9], mean[9];
+  float sums[9];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float* x = X + c * cs + XS * center;
@@ -375,15 +399,7 @@ VSL_HD float reproj_window(const float* __restrict__ X, int cs, const float* __r
     sums[3 * c] = sx; sums[3 * c + 1] = sxx; sums[3 * c + 2] = sxy;
     l1[c] = fabsf(sub_rn(y[0], x[0]));
   }
-  div9_all<9>(sums, mean);  // one guard branch for the nine quotients
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    so[c] = ssim_from_means(mean[3 * c], mean[3 * c + 1], mean[3 * c + 2], TS[c * C::WN + widx], TS[(3 + c) * C::WN + widx]);
-    ss[c] = so[c].val;
-  }
-  float ms = mean3(ss[0], ss[1], ss[2], arith);
-  float ml = mean3(l1[0], l1[1], l1[2], arith);
-  return add_rn(mul_rn(0.85f, ms), mul_rn(0.15f, ml));
+  return window_loss_from_sums<C>(sums, l1, TS, widx, arith, so);
 }
 
 // The same for a PAIR of frames at once (X2: pair storage of channel 0, channels 2*RN apart).  Returns
@@ -596,10 +612,7 @@ VSL_HD void phase_warp(const PhotoParams& p, const GeoConst& g, const TileCtx& t
           // grid_sampler_2d_backward's d out / d(ix, iy); zero where the border clip is active
           float ddx = pr[f].inx ? ((vne - vnw) * tp[f].wy1 + (vse - vsw) * tp[f].wy0) : 0.f;
           float ddy = pr[f].iny ? ((vsw - vnw) * tp[f].wx1 + (vse - vne) * tp[f].wx0) : 0.f;
-          if (keep) {
-            G[(f * 6 + c) * C::IN + j] = ddx;
-            G[(f * 6 + 3 + c) * C::IN + j] = ddy;
-          }
+          if (keep) reinterpret_cast<F2*>(G)[(f * 3 + c) * C::IN + j] = f2(ddx, ddy);
         }
       }
       if (p.side_any && interior) {  // the reference's outputs[("depth" | "sample" | "color", ...)] for this pixel
@@ -721,6 +734,26 @@ VSL_HD void store_rec(CoefRec* __restrict__ rec, const float coef[9], int idx, f
   for (int k = 0; k < 9; ++k) r.c[k] = coef[k];
   r.m = m; r.pad1 = 0.f; r.idx = idx;
   *rec = r;
+}
+
+// A record is always read whole, as three 128-bit shared loads.  Left to itself the compiler fetches the two words
+// of the last quarter it needs (c[8], idx) with scalar loads, which at the records' 48-byte pitch are 4-way bank
+// conflicted: 16 shared-memory wavefronts per record instead of 12 (r2c profile, vsl_tile.cuh Rec loads).
+VSL_HD CoefRec load_rec(const CoefRec* __restrict__ rec) {
+#if defined(__CUDA_ARCH__)
+  CoefRec r;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(rec);
+  float4 q0, q1, q2;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a));
+  r.c[0] = q0.x; r.c[1] = q0.y; r.c[2] = q0.z; r.c[3] = q0.w;
+  r.c[4] = q1.x; r.c[5] = q1.y; r.c[6] = q1.z; r.c[7] = q1.w;
+  r.c[8] = q2.x; r.m = q2.y; r.pad1 = q2.z; r.idx = __float_as_int(q2.w);
+  return r;
+#else
+  return *rec;
+#endif
 }
 
 // --predictive_mask (trainer.py:635-642, only reached with --disable_automasking): every frame's
@@ -1005,7 +1038,7 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
         const float cnt = cy * cx;
 #pragma unroll
         for (int rr = 0; rr < C::NREC; ++rr) {
-          const CoefRec rec = Rec[rr * C::WN + (iy + 1 + dy) * C::WW + (ix + 1 + dx)];  // 3 x 128-bit shared loads
+          const CoefRec rec = load_rec(Rec + rr * C::WN + (iy + 1 + dy) * C::WW + (ix + 1 + dx));  // 3 x 128-bit shared loads
           if (rec.idx >= 0) used |= 1u << rec.idx;
 #pragma unroll
           for (int f = 0; f < C::F; ++f) {
@@ -1036,8 +1069,9 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
           float xq = X[XL::at(f, c, center)], yq = T[c * C::RN + center];
           float gc = acc[f][c] + 2.f * xq * acc[f][3 + c] + yq * acc[f][6 + c];
           gc += (xq > yq) ? k1 : ((xq < yq) ? -k1 : 0.f);
-          gix += gc * G[(f * 6 + c) * C::IN + j];
-          giy += gc * G[(f * 6 + 3 + c) * C::IN + j];
+          const F2 dg = reinterpret_cast<const F2*>(G)[(f * 3 + c) * C::IN + j];  // d warped / d(ix, iy)
+          gix += gc * dg.x;
+          giy += gc * dg.y;
         }
         const float* P = sm + C::oP + f * 12;
         float c0 = P[0] * cam.X + P[1] * cam.Y + P[2] * cam.Z + P[3];
@@ -1062,6 +1096,117 @@ VSL_HD void phase_backward(const PhotoParams& p, const GeoConst& g, const TileCt
     else sm[C::oGD + j] = gDv;  // folded into d/d disp_s by phase_adjoint_rows / _cols
   }
 }
+
+#if defined(__CUDACC__)
+// Two vertically adjacent interior pixels per thread: their 3x3 record neighbourhoods share two of three rows, so
+// the pair reads 12 records instead of 18 (the adjoint phase waits on shared memory more than on anything else).
+// Per pixel the accumulation order (rows top to bottom, columns left to right) and every operation are those of
+// phase_backward, so the gradients have the same bits.  One record per window only (not --avg_reprojection).
+#ifndef VSL_ADJ_PAIR
+#define VSL_ADJ_PAIR 1
+#endif
+template <class C>
+__device__ __forceinline__ void phase_backward_pair(const PhotoParams& p, const GeoConst& g, const TileCtx& t,
+                                                    float* __restrict__ sm, int s, int tid, ThreadState<C>& ts) {
+  static_assert(!C::AVG && C::TH % 2 == 0, "one record per window, even tile height");
+  using XL = XLayout<C>;
+  const float* T = sm + C::oT;
+  const float* X = sm + C::oX;
+  const CoefRec* Rec = reinterpret_cast<const CoefRec*>(sm + C::oCoef);
+  const float* G = sm + C::oG;
+  const int HW = p.H * p.W;
+  const float* invK = sm + C::oInvK;
+  const float kl1 = p.no_ssim ? p.wpix * (1.0f / 3.0f) : p.wpix * (0.15f / 3.0f);
+  for (int item = tid; item < C::IN / 2; item += C::NT) {
+    const int py = item / C::TW, ix = item - py * C::TW;
+    const int iy0 = 2 * py;
+    const int gx = t.x0 + ix;
+    float acc[2][C::F][9];
+    unsigned used[2] = {0u, 0u};
+    int own_idx[2] = {-1, -1};
+    float own_m[2] = {1.f, 1.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int f = 0; f < C::F; ++f)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[q][f][k] = 0.f;
+    const bool col_ok = gx < p.W;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {  // record rows iy0 + r (window coordinates iy0 + r, i.e. pixel rows iy0 - 1 + r)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const CoefRec rec = load_rec(Rec + (iy0 + r) * C::WW + (ix + 1 + dx));
+        const float cx = ((dx == -1 && gx == 1) || (dx == 1 && gx == p.W - 2)) ? 2.f : 1.f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int dy = r - 1 - q;  // this record row relative to pixel q
+          if (dy < -1 || dy > 1) continue;
+          const int gy = t.y0 + iy0 + q;
+          const float cy = ((dy == -1 && gy == 1) || (dy == 1 && gy == p.H - 2)) ? 2.f : 1.f;
+          const float cnt = cy * cx;
+          if (rec.idx >= 0) used[q] |= 1u << rec.idx;
+          if (dy == 0 && dx == 0) { own_idx[q] = rec.idx; own_m[q] = rec.m; }
+#pragma unroll
+          for (int f = 0; f < C::F; ++f) {
+            const float cf = rec.idx == f ? cnt : 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[q][f][k] = fmaf(cf, rec.c[k], acc[q][f][k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int iy = iy0 + q, gy = t.y0 + iy, j = iy * C::TW + ix;
+      if (gy >= p.H || !col_ok) {
+        sm[C::oGD + j] = 0.f;
+        continue;
+      }
+      float gz = 0.f;
+      Cam cam;
+      cam.z = 0.f;
+      if (used[q]) {
+        cam = backproject_z(sm[C::oZ + j], invK, gx, gy, g);
+        const int center = (iy + 2) * C::RW + (ix + 2);
+#pragma unroll
+        for (int f = 0; f < C::F; ++f) {
+          if (!(used[q] & (1u << f))) continue;
+          float gix = 0.f, giy = 0.f;
+          const float k1 = own_idx[q] == f ? (C::PMASK ? kl1 * own_m[q] : kl1) : 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float xq = X[XL::at(f, c, center)], yq = T[c * C::RN + center];
+            float gc = acc[q][f][c] + 2.f * xq * acc[q][f][3 + c] + yq * acc[q][f][6 + c];
+            gc += (xq > yq) ? k1 : ((xq < yq) ? -k1 : 0.f);
+            const F2 dg = reinterpret_cast<const F2*>(G)[(f * 3 + c) * C::IN + j];  // d warped / d(ix, iy)
+            gix += gc * dg.x;
+            giy += gc * dg.y;
+          }
+          const float* P = sm + C::oP + f * 12;
+          float c0 = P[0] * cam.X + P[1] * cam.Y + P[2] * cam.Z + P[3];
+          float c1 = P[4] * cam.X + P[5] * cam.Y + P[6] * cam.Z + P[7];
+          float c2 = P[8] * cam.X + P[9] * cam.Y + P[10] * cam.Z + P[11];
+          float iz = fast_rcp(c2 + g.eps);
+          float g0 = gix * iz, g1 = giy * iz;
+          float g2 = -(g0 * c0 + g1 * c1) * iz;
+          float* dP = ts.dP + f * 12;
+          dP[0] += g0 * cam.X; dP[1] += g0 * cam.Y; dP[2] += g0 * cam.Z; dP[3] += g0;
+          dP[4] += g1 * cam.X; dP[5] += g1 * cam.Y; dP[6] += g1 * cam.Z; dP[7] += g1;
+          dP[8] += g2 * cam.X; dP[9] += g2 * cam.Y; dP[10] += g2 * cam.Z; dP[11] += g2;
+          float gX = g0 * P[0] + g1 * P[4] + g2 * P[8];
+          float gY = g0 * P[1] + g1 * P[5] + g2 * P[9];
+          float gZ = g0 * P[2] + g1 * P[6] + g2 * P[10];
+          gz += gX * cam.rx + gY * cam.ry + gZ * cam.rz;
+        }
+      }
+      const float gDv = -gz * g.disp_range * cam.z * cam.z;
+      if (p.identity_scale[s]) p.gD[s][(size_t)t.b * HW + gy * p.W + gx] = gDv;
+      else sm[C::oGD + j] = gDv;
+    }
+  }
+}
+#endif
 
 // ---- phases: adjoint of the bilinear up-sample of disp_s (trainer.py:500-501), tile-local part -----
 // d/d disp_s[jy,jx] = sum over fine pixels o of wy(oy,jy) wx(ox,jx) gD[o]; the footprint of a coarse pixel is
