@@ -350,6 +350,32 @@ int vsl_stereo_transform(int batch, const uint8_t* flip, const uint8_t* side_lef
  * tables with Pillow's without a GPU. */
 int vsl_pyramid_coefficients(int in_size, int out_size, int32_t* bounds, int32_t* coefs, int ksize_capacity);
 
+/* ------------------------------------------------------------------------------------
+ * Colour augmentation of the `color_aug` inputs (dataset-side remainder).
+ * Replaces `self.to_tensor(color_aug(f))` (datasets/mono_dataset2.py:124) with color_aug =
+ * transforms.Compose([ColorJitter(brightness, contrast, saturation, hue), RandomHorizontalFlip(0.5),
+ * RandomAutocontrast()]) (datasets/mono_dataset2.py:92-97) on 8-bit PIL images: torchvision's
+ * _functional_pil.py on top of Pillow's Image.blend / convert("L"|"HSV"|"RGB") / ImageOps.autocontrast,
+ * reproduced byte for byte.  The random draws stay with the caller (torch's global generator); one record
+ * per image describes the outcome of one call of the transform.
+ * ------------------------------------------------------------------------------------ */
+typedef struct VslAugParams {
+  int32_t order[4];     /* ColorJitter.get_params' randperm(4): 0 brightness, 1 contrast, 2 saturation, 3 hue   */
+  float factor[3];      /* brightness, contrast, saturation factors as C floats (Image.blend's alpha)           */
+  int32_t hue_shift;    /* uint8(int32(hue_factor * 255)): what adjust_hue adds to the H channel (8-bit wrap)   */
+  int32_t flip;         /* RandomHorizontalFlip's outcome                                                       */
+  int32_t autocontrast; /* RandomAutocontrast's outcome                                                         */
+  int32_t enabled;      /* 0: the item's do_color_aug is false (datasets/mono_dataset2.py:179-186): ToTensor only */
+  int32_t reserved;
+} VslAugParams;
+/* workspace: per-image statistics + the jittered 8-bit images; 256-byte aligned, caller-owned */
+size_t vsl_color_aug_workspace_bytes(int batch, int height, int width);
+/* frames_hwc [B,H,W,3] uint8 and params [B] on the device.  out: [B,3,H,W] of out_dtype (VSL_DTYPE_F32 /
+ * VSL_DTYPE_BF16) or null; out_u8: the augmented 8-bit images [B,H,W,3] or null (at least one of the two). */
+int vsl_color_aug_forward(int batch, int height, int width, int out_dtype, const uint8_t* frames_hwc,
+                          const VslAugParams* params, void* out, uint8_t* out_u8, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,7 @@ EXPORTED_SYMBOLS = [
     "vsl_pyramid_forward_flip", "vsl_stereo_transform",
     "vsl_posecnn_workspace_bytes", "vsl_posecnn_forward", "vsl_posecnn_backward",
     "vsl_metrics_workspace_bytes", "vsl_depth_errors", "vsl_depth_losses", "vsl_sllog_forward", "vsl_sllog_backward",
+    "vsl_color_aug_workspace_bytes", "vsl_color_aug_forward",
 ]
 
 
@@ -83,6 +84,13 @@ class VslPyramidDesc(Structure):
     _fields_ = [
         ("abi_version", c_int32), ("batch", c_int32), ("height", c_int32), ("width", c_int32),
         ("num_levels", c_int32), ("out_dtype", c_int32),
+    ]
+
+
+class VslAugParams(Structure):
+    _fields_ = [
+        ("order", c_int32 * 4), ("factor", c_float * 3), ("hue_shift", c_int32), ("flip", c_int32),
+        ("autocontrast", c_int32), ("enabled", c_int32), ("reserved", c_int32),
     ]
 
 
@@ -180,6 +188,9 @@ def load():
                                      vp, c_size_t, vp]
     lib.vsl_sllog_forward.argtypes = [c_size_t, vp, vp, vp, vp, vp, c_size_t, vp]
     lib.vsl_sllog_backward.argtypes = [c_size_t, vp, vp, vp, vp, vp, vp, vp]
+    lib.vsl_color_aug_workspace_bytes.restype = c_size_t
+    lib.vsl_color_aug_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.vsl_color_aug_forward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, c_size_t, vp]
     _LIB = lib
     return lib
 

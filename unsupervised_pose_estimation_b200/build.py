@@ -17,7 +17,7 @@ import tempfile
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvsl_b200.so")
-SOURCES = ["vsl_fused.cu", "vsl_layers.cu", "vsl_input.cu", "vsl_source_grad.cu", "vsl_metrics.cu"]
+SOURCES = ["vsl_fused.cu", "vsl_layers.cu", "vsl_input.cu", "vsl_source_grad.cu", "vsl_metrics.cu", "vsl_augment.cu"]
 HEADERS = ["vsl_math.cuh", "vsl_tile.cuh", os.path.join("..", "..", "include", "vsl.h")]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo", "--threads", "4",

@@ -23,7 +23,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import VSL_ABI_VERSION, VSL_MAX_SCALES, VslPyramidDesc, check
+from ._lib import VSL_ABI_VERSION, VSL_MAX_SCALES, VslAugParams, VslPyramidDesc, check
 
 
 def _stream():
@@ -164,6 +164,101 @@ class LossInputPipeline:
         if inputs is not None:
             inputs.update(self._intrinsics[key])
         return self._intrinsics[key]
+
+
+def draw_color_aug_params(brightness=(0.8, 1.2), contrast=(0.8, 1.2), saturation=(0.8, 1.2), hue=(-0.1, 0.1),
+                          p_flip=0.5, p_autocontrast=0.5):
+    """The random draws of ONE call of the reference's ``transforms_aug`` (datasets/mono_dataset2.py:92-97), taken
+    from torch's global generator in the order torchvision takes them: ``ColorJitter.get_params`` (``randperm(4)``,
+    then one ``uniform_`` each for brightness, contrast, saturation, hue), ``RandomHorizontalFlip`` (``rand(1) < p``),
+    ``RandomAutocontrast`` (``rand(1) < p``).  Host-side bookkeeping; the pixels are processed by ColorAugment."""
+    order = [int(v) for v in torch.randperm(4)]
+    b = float(torch.empty(1).uniform_(brightness[0], brightness[1]))
+    c = float(torch.empty(1).uniform_(contrast[0], contrast[1]))
+    s = float(torch.empty(1).uniform_(saturation[0], saturation[1]))
+    h = float(torch.empty(1).uniform_(hue[0], hue[1]))
+    flip = bool(torch.rand(1) < p_flip)
+    auto = bool(torch.rand(1).item() < p_autocontrast)
+    return dict(order=order, brightness=b, contrast=c, saturation=s, hue=h, flip=flip, autocontrast=auto)
+
+
+class ColorAugment:
+    """``self.to_tensor(color_aug(f))`` of ``MonoDataset.preprocess`` (datasets/mono_dataset2.py:124) for a batch of
+    equally sized 8-bit images on the GPU: ColorJitter + RandomHorizontalFlip + RandomAutocontrast + ToTensor, byte
+    for byte what torchvision / Pillow produce on the PIL images, given each image's draws.
+
+        aug = ColorAugment(batch=12, height=192, width=640)
+        params = [draw_color_aug_params() if do_color_aug else None for _ in range(12)]   # None: ToTensor only
+        color_aug = aug(frame_u8, params)            # [B,3,H,W] float32 (static buffer)
+
+    The reference calls the transform once per (frame, level), so every level has its own draws; use one instance per
+    level size.  CUDA only."""
+
+    def __init__(self, batch, height, width, device="cuda", dtype=torch.float32):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.VslError("ColorAugment runs on CUDA only (the reference's CPU augmentation is its own dataset code)")
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("dtype must be float32 or bfloat16")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib = _lib.load()
+        self.batch, self.height, self.width, self.dtype = batch, height, width, dtype
+        self.ws_bytes = int(self.lib.vsl_color_aug_workspace_bytes(batch, height, width))
+        if self.ws_bytes == 0:
+            raise ValueError("bad shape %dx%dx%d" % (batch, height, width))
+        with torch.cuda.device(self.device):
+            self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=self.device)
+            self.ws_ptr = self.ws.data_ptr() + (-self.ws.data_ptr()) % 256
+            self.out = torch.empty(batch, 3, height, width, dtype=dtype, device=self.device)
+            self.params_dev = torch.empty(batch * ctypes.sizeof(VslAugParams), dtype=torch.uint8, device=self.device)
+        self.params_host = torch.empty(batch * ctypes.sizeof(VslAugParams), dtype=torch.uint8).pin_memory()
+
+    def pack_params(self, params):
+        """list of per-image dicts (draw_color_aug_params) or None -> the pinned host array of VslAugParams"""
+        import numpy as np
+        if len(params) != self.batch:
+            raise ValueError("need %d parameter records, got %d" % (self.batch, len(params)))
+        arr = (VslAugParams * self.batch).from_buffer(self.params_host.numpy())
+        for rec, prm in zip(arr, params):
+            if prm is None:
+                rec.enabled = 0
+                rec.order[:] = [0, 1, 2, 3]
+                rec.factor[:] = [1.0, 1.0, 1.0]
+                rec.hue_shift = rec.flip = rec.autocontrast = rec.reserved = 0
+                continue
+            if sorted(prm["order"]) != [0, 1, 2, 3]:
+                raise ValueError("order must be a permutation of 0..3")
+            if not -0.5 <= prm["hue"] <= 0.5:
+                raise ValueError("hue_factor (%r) is not in [-0.5, 0.5]." % (prm["hue"],))  # torchvision's check
+            rec.enabled = 1
+            rec.order[:] = [int(v) for v in prm["order"]]
+            rec.factor[:] = [float(prm["brightness"]), float(prm["contrast"]), float(prm["saturation"])]
+            rec.hue_shift = int(np.int32(prm["hue"] * 255).astype(np.uint8))   # _functional_pil.adjust_hue
+            rec.flip = int(bool(prm["flip"]))
+            rec.autocontrast = int(bool(prm["autocontrast"]))
+            rec.reserved = 0
+        return self.params_host
+
+    def __call__(self, frame_u8, params, want_u8=False):
+        """frame_u8: [B,H,W,3] uint8 CUDA tensor; params: see pack_params.  Returns the float tensor (static
+        buffer), with want_u8 also the augmented 8-bit images."""
+        if frame_u8.device != self.device or frame_u8.dtype != torch.uint8 or not frame_u8.is_contiguous():
+            raise _lib.VslError("frames must be contiguous uint8 tensors on %s (got %s %s)"
+                                % (self.device, frame_u8.dtype, frame_u8.device))
+        if tuple(frame_u8.shape) != (self.batch, self.height, self.width, 3):
+            raise ValueError("frame has shape %s, expected %s"
+                             % (tuple(frame_u8.shape), (self.batch, self.height, self.width, 3)))
+        self.params_dev.copy_(self.pack_params(params), non_blocking=True)
+        u8 = torch.empty_like(frame_u8) if want_u8 else None
+        check(self.lib.vsl_color_aug_forward(self.batch, self.height, self.width,
+                                             _lib.DTYPE_BF16 if self.dtype == torch.bfloat16 else _lib.DTYPE_F32,
+                                             ctypes.c_void_p(frame_u8.data_ptr()), ctypes.c_void_p(self.params_dev.data_ptr()),
+                                             ctypes.c_void_p(self.out.data_ptr()),
+                                             ctypes.c_void_p(u8.data_ptr()) if u8 is not None else None,
+                                             ctypes.c_void_p(self.ws_ptr), self.ws_bytes, _stream()),
+              "vsl_color_aug_forward")
+        return (self.out, u8) if want_u8 else self.out
 
 
 def pyramid_coefficients(in_size, out_size):
