@@ -66,6 +66,21 @@ def profiled_traffic_bytes():
     return (float(m.group(1)) * 1e6, os.path.basename(files[-1])) if m else (None, None)
 
 
+def small_kernel_rooflines():
+    """HBM fractions of the kernels around k_photometric (k_epilogue, k_combine, the input-pipeline and side-output
+    kernels ...) from the newest committed small-kernel capture (profiles/*_small_kernels.json, written by
+    tools/summarize_small_kernels.py from one `ncu --set full` launch each at C1): algorithmic bytes / captured time
+    against the measured HBM peak.  Not timed in this run: they are microsecond kernels inside a CUDA graph."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_small_kernels.json")))
+    if not files:
+        return None
+    data = json.load(open(files[-1]))
+    return {"source": os.path.basename(files[-1]), "bound": "hbm", "unit": "fraction of the measured HBM peak",
+            "kernels": {k: {"ncu_us": v["ncu_us"], "algorithmic_bytes": v["algorithmic_bytes"], "frac": v["frac_of_hbm_peak"]}
+                        for k, v in data.items() if v.get("frac_of_hbm_peak") is not None}}
+
+
 def peak_hbm_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -776,6 +791,9 @@ def main():
                 "unfused_equivalent_gbs": unfused / (ms_total / args.steps * 1e-3) / 1e9,
                 "unfused_equivalent_over_hbm_peak": unfused / (ms_total / args.steps * 1e-3) / 1e9 / peak,
                 }
+        aux = small_kernel_rooflines()
+        if aux is not None and args.config == "C1":
+            line["roofline_aux"] = aux
         if grad_allreduce is not None:
             line["grad_allreduce"] = grad_allreduce
             line["train_step"] = train_step
