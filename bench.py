@@ -233,7 +233,11 @@ def workload_config(args, cfg):
                            "bf16 image storage + fp32 arithmetic" if getattr(args, "bf16_images", False) else "fp32",
                            args.family),
             "l2": "ring of input sets larger than L2 (126 MB) cycled between timed steps",
-            "side_outputs": "none (fused path; reference side outputs are materialised on logging steps only)"}
+            "side_outputs": "none (fused path; reference side outputs are materialised on logging steps only)",
+            "tie_break_noise": ("drawn inside every step, in front of its loss kernels" if getattr(args, "no_noise_prefetch", False)
+                                or getattr(args, "no_graph", False) else
+                                "software-pipelined: every step draws the NEXT step's four randn tensors (same draws, same "
+                                "order as the reference) while its own loss kernels run; `noise_inline` is the step without")}
 
 
 def shard_parity(cfg, family, device, rank, world, dist):
@@ -384,6 +388,9 @@ def main():
     ap.add_argument("--e2e-skip", default="", help="diagnostic: comma list of pipeline,h2d,readback to leave out of the "
                     "e2e loop (the line is then marked invalid)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling C5 sub-record")
+    ap.add_argument("--no-noise-prefetch", action="store_true",
+                    help="draw each step's tie-break noise in front of its loss kernels (the faithful default of "
+                         "compute_losses) instead of one step ahead, behind the previous step's loss kernels")
     ap.add_argument("--bf16-images", action="store_true",
                     help="store the colour images as bf16 (BASELINE config 3); arithmetic stays fp32")
     args = ap.parse_args()
@@ -445,10 +452,11 @@ def main():
     kernel_ms = events.drain_ms()
     wl.path._vsl_plan().kernel_events = None
     # (b) the timed region: the same step captured once per input set and replayed (one host call per step)
+    prefetch = not args.no_noise_prefetch and not args.no_graph
     if args.no_graph:
         run_step = lambda i: wl.step(wl.sets[i % ring])
     else:
-        graphs = [GraphedLossStep(wl.path, st["inputs"], st["leaves"]) for st in wl.sets]
+        graphs = [GraphedLossStep(wl.path, st["inputs"], st["leaves"], noise_prefetch=prefetch) for st in wl.sets]
         run_step = lambda i: graphs[i % ring].replay()
     sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs a moment to start: begin before
     for i in range(args.warmup):                                # the warm-up replays, same load as the timed region
@@ -477,6 +485,20 @@ def main():
     ms_total = float(t.item())
     value = world * n0 * args.steps / (ms_total * 1e-3)
 
+    # ---- the un-pipelined step: every replay draws its own noise in front of its loss kernels ----------------
+    noise_inline = None
+    if not args.no_graph and prefetch:
+        igraphs = [GraphedLossStep(wl.path, st["inputs"], st["leaves"]) for st in wl.sets]
+        for i in range(8):
+            igraphs[i % ring].replay()
+        n_i = min(args.steps, 100)
+        i_ms = timed_loop(lambda i: igraphs[i % ring].replay(), n_i, barrier, device, dist)
+        noise_inline = {"value": world * n0 / (i_ms * 1e-3), "unit": UNIT, "ms_per_step": i_ms,
+                        "note": "GraphedLossStep(noise_prefetch=False): the four randn launches of a step run alone "
+                                "in front of its k_photometric; the headline draws them one step ahead (same draws, "
+                                "same order), where they fill the SMs the loss kernel's last wave leaves idle"}
+        del igraphs
+
     # ---- L2-warm variant (SURVEY.md 8d asks for both): one input set re-used every step ----------------
     l2_warm = None
     if not args.no_graph:
@@ -503,7 +525,7 @@ def main():
     contract = None
     if not args.no_graph:
         wl.path.vsl_side_outputs = "fused"
-        cgraphs = [GraphedLossStep(wl.path, st["inputs"], st["leaves"]) for st in wl.sets[:2]]
+        cgraphs = [GraphedLossStep(wl.path, st["inputs"], st["leaves"], noise_prefetch=prefetch) for st in wl.sets[:2]]
         wl.path.vsl_side_outputs = "none"
         for i in range(4):
             cgraphs[i % 2].replay()
@@ -605,7 +627,7 @@ def main():
                         return losses, grads, wl_h.path.vsl_last_loss_vector
                     slot_steps[key] = eager
                 else:
-                    g = GraphedLossStep(wl_h.path, inputs, leaves)
+                    g = GraphedLossStep(wl_h.path, inputs, leaves, noise_prefetch=not args.no_noise_prefetch)
                     slot_steps[key] = lambda g=g: g.replay() + (g.loss_vector,)
             return slot_steps[key]
 
@@ -732,7 +754,7 @@ def main():
         cfg5 = dict(synthetic.CONFIGS["C5"])
         cfg5["batch"] = 96 // world
         wl5 = Workload(cfg5, args.family, device, 2, bf16_images=args.bf16_images)
-        g5 = [GraphedLossStep(wl5.path, st["inputs"], st["leaves"]) for st in wl5.sets]
+        g5 = [GraphedLossStep(wl5.path, st["inputs"], st["leaves"], noise_prefetch=not args.no_noise_prefetch) for st in wl5.sets]
         for i in range(4):
             g5[i % 2].replay()
         n5 = min(args.steps, 40)
@@ -754,6 +776,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, cfg),
             "l2_warm": l2_warm,
+            "noise_inline": noise_inline,
             "contract_mode": contract,
             "e2e": e2e_u8,
             "e2e_f32_host_tensors": e2e_f32,

@@ -579,6 +579,51 @@ def test_graph_replay_equals_eager():
         assert torch.equal(after_eager, after_graph)
 
 
+def test_noise_prefetch_consumes_the_same_draws():
+    """Opt-in software pipelining of the tie-break noise (vsl_noise_prefetch, GraphedLossStep(noise_prefetch=True)):
+    call k still receives the k-th group of randn draws of the global generator, so losses, masks and gradients are
+    bit-identical to the un-pipelined step's -- eagerly and through the two alternating captured graphs."""
+    from unsupervised_pose_estimation_b200.graph import GraphedLossStep
+    opt, inputs, outputs, _ = build_case("mono_iid_64x96")
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in outputs.items() if k[0] == "disp"}
+    for f in opt.frame_ids[1:]:
+        T = L.transformation_from_parameters(outputs[("axisangle", 0, f)][:, 0].detach(),
+                                             outputs[("translation", 0, f)][:, 0].detach(), f < 0)
+        leaves[("cam_T_cam", 0, f)] = T.clone().requires_grad_(True)
+
+    def steps(path, n):
+        res = []
+        for _ in range(n):
+            out = dict(leaves)
+            losses = path.compute_losses(inputs, out)
+            g = torch.autograd.grad(losses["loss"], list(leaves.values()))
+            res.append(({k: v.detach().clone() for k, v in losses.items()},   # detached: nothing keeps the autograd graph alive
+                        [out["identity_selection/%d" % s].clone() for s in opt.scales], [x.clone() for x in g]))
+        return res
+
+    torch.manual_seed(31)
+    ref = steps(LossPath(make_opt(**vars(opt)), device=DEV, side_outputs="none"), 4)
+    assert not torch.equal(ref[0][1][0], ref[1][1][0]) or not torch.equal(ref[0][0]["loss"], ref[1][0]["loss"])
+    pipelined = LossPath(make_opt(**vars(opt)), device=DEV, side_outputs="none")
+    pipelined.vsl_noise_prefetch = True
+    torch.manual_seed(31)
+    got = steps(pipelined, 4)
+    for a, b in zip(ref, got):
+        assert all(torch.equal(a[0][k], b[0][k]) for k in a[0])
+        assert all(torch.equal(x, y) for x, y in zip(a[1], b[1])) and all(torch.equal(x, y) for x, y in zip(a[2], b[2]))
+    # captured: replay r+1 consumes what replay r drew, i.e. group r after the seed
+    path = LossPath(make_opt(**vars(opt)), device=DEV, side_outputs="none")
+    step = GraphedLossStep(path, inputs, leaves, noise_prefetch=True)
+    assert step.noise_prefetch and not path.vsl_noise_prefetch
+    torch.manual_seed(31)
+    step.replay()
+    for r in range(3):
+        losses, grads = step.replay()
+        assert all(torch.equal(ref[r][0][k], losses[k]) for k in losses), r
+        assert all(torch.equal(m, step.outputs["identity_selection/%d" % s]) for m, s in zip(ref[r][1], opt.scales)), r
+        assert all(torch.equal(g, grads[k]) for g, k in zip(ref[r][2], leaves)), r
+
+
 @pytest.mark.parametrize("batch", [1, 2, 12, 257])
 def test_transformation_from_parameters_kernel(batch):
     """layers.transformation_from_parameters on CUDA is one kernel: bit-identical to the torch op sequence

@@ -79,3 +79,20 @@ for name, fn in (("one tiny kernel (graph launch floor)", empty), ("4 x randn, o
     g, keep = capture(fn)
     res[name] = time_graph(g)
     print("%-45s %8.1f us" % (name, res[name]), flush=True)
+
+from unsupervised_pose_estimation_b200.graph import GraphedLossStep  # noqa: E402
+for pf in (False, True):
+    gs = GraphedLossStep(path, inputs, leaves, noise_prefetch=pf)
+    for _ in range(20):
+        gs.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(3):
+        e0.record()
+        for _ in range(300):
+            gs.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 300)
+    print("%-45s %8.1f us" % ("GraphedLossStep(noise_prefetch=%s)" % pf, best * 1e3), flush=True)

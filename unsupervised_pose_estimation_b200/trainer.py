@@ -223,13 +223,27 @@ class ViewSynthesisLossMixin:
         disps = [outputs[("disp", s)] for s in opt.scales]
         dev = disps[0].device
         # one draw per scale, same shape/order/device as trainer.py:656-657
-        noise = self._vsl_draw_noise(plan, dev, len(opt.scales)) if plan.automask else None
+        prefetch = plan.automask and self.vsl_noise_prefetch
+        fork = None
+        if prefetch:
+            # the draws for THIS call were made during the previous one (first call: made here); the point where
+            # the next call's draws may start is recorded before the loss kernels are enqueued
+            noise = self._vsl_noise_ahead if self._vsl_noise_ahead is not None else self._vsl_draw_noise(plan, dev, S)
+            self._vsl_noise_ahead = None
+            fork = torch.cuda.Event()
+            fork.record(torch.cuda.current_stream(dev))
+        else:
+            noise = self._vsl_draw_noise(plan, dev, S) if plan.automask else None
         pmasks, weighting = self._vsl_predictive_masks(outputs)
         side = getattr(self, "_vsl_side_pending", None)
         self._vsl_side_pending = None
         vec, masks = VF.fused_loss(plan, targets, sources, disps, inputs[("inv_K", 0)], None, noise,
                                    K=inputs[("K", 0)], Ts=self._vsl_poses(inputs, outputs), predictive_masks=pmasks,
                                    side=side)
+        if prefetch:
+            # enqueued BEHIND the loss kernels but dependent only on `fork`: the generator kernels fill the SMs the
+            # loss kernel's last wave leaves idle instead of running alone in front of the next step
+            self._vsl_noise_ahead = self._vsl_draw_noise(plan, dev, S, after=fork, out=self._vsl_noise_out)
         # the whole loss dict as one contiguous device vector (min_loss/s..., loss/s..., loss): a logger can
         # read it back with one copy instead of one per entry
         self.vsl_last_loss_vector = vec.detach() if weighting is None else None
@@ -244,26 +258,39 @@ class ViewSynthesisLossMixin:
         return losses
 
     vsl_parallel_noise = True   # the S draws run as parallel branches (side streams); False: back to back on one stream
+    # Opt-in software pipelining of the tie-break noise: every compute_losses call consumes the noise drawn during
+    # the previous call and draws the next call's while its own loss kernels run.  The k-th call still receives the
+    # k-th group of S randn draws of the global generator, in the reference's order (trainer.py:656-657) -- what
+    # changes is WHEN the generator is advanced (one call early), so it is off by default: a caller that draws other
+    # CUDA random numbers between steps, or checkpoints the generator state, sees a different interleaving.
+    vsl_noise_prefetch = False
+    _vsl_noise_ahead = None     # noise drawn ahead for the next call (list of S tensors)
+    _vsl_noise_out = None       # optional static buffers the ahead draws are written to (graph.GraphedLossStep)
 
-    def _vsl_draw_noise(self, plan, dev, S):
+    def _vsl_draw_noise(self, plan, dev, S, after=None, out=None):
         """The tie-break noise of trainer.py:656-657: one ``randn`` per scale, in the reference's order, so the
         global Philox stream is consumed exactly like the reference does (the offsets are assigned on the host, call
         by call).  The S generator kernels are independent; enqueued on side streams they run as parallel branches
         (also inside a captured CUDA graph) instead of four launch-latency-bound kernels in a row."""
         shape = (plan.batch, plan.noise_channels, plan.height, plan.width)
-        if not self.vsl_parallel_noise or S == 1:
+        if after is None and (not self.vsl_parallel_noise or S == 1):
             return [torch.randn(shape, device=dev) for _ in range(S)]
         cur = torch.cuda.current_stream(dev)
+        nside = S if after is not None else S - 1   # drawing ahead: every draw leaves the current stream
         side = getattr(self, "_vsl_noise_streams", None)
-        if side is None or len(side) < S - 1 or side[0].device != dev:
-            side = self._vsl_noise_streams = [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
-        noise = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(S)]   # allocated on `cur`
-        fork = torch.cuda.Event()
-        fork.record(cur)
-        noise[0].normal_()                         # randn == empty + normal_(0, 1): same generator calls, same order
+        if side is None or len(side) < nside or side[0].device != dev:
+            side = self._vsl_noise_streams = [torch.cuda.Stream(device=dev) for _ in range(max(nside, 1))]
+        noise = out if out is not None else [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(S)]   # allocated on `cur`
+        if len(noise) != S or any(t.shape != torch.Size(shape) or t.dtype != torch.float32 for t in noise):
+            raise ValueError("noise buffers must be %d float32 tensors of shape %s" % (S, (shape,)))
+        fork = after
+        if fork is None:
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            noise[0].normal_()                     # randn == empty + normal_(0, 1): same generator calls, same order
         joins = []
-        for s in range(1, S):
-            st = side[s - 1]
+        for s in range(0 if after is not None else 1, S):
+            st = side[s if after is not None else s - 1]
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 noise[s].normal_()
