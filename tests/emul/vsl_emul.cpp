@@ -122,7 +122,7 @@ extern "C" int vsl_emul_photometric(int B, int H, int W, int S, int F, const int
         gdisp[s][(size_t)b * hs * ws + i] =
             p.identity_scale[s] ? gD[s][(size_t)b * H * W + i]
                                 : gather_adjoint_partials(gpart[s].data(), b, i / ws, i % ws, ilog2(tw) - ilog2(W / ws),
-                                                          ilog2(th) - ilog2(W / ws), tiles_x, tiles_y);
+                                                          th / (W / ws), ilog2(th) - ilog2(W / ws), tiles_x, tiles_y);
     }
   }
   return 0;

@@ -14,6 +14,16 @@
 #include "../../include/vsl.h"
 #include "vsl_tile.cuh"
 
+// Three source frames run as one 512-thread CTA per SM (the tile needs > 114 KB).  With the whole SM's shared memory
+// to itself the tile can be 32 x 24 (201 KB): halo recomputation 1.31x / 1.15x instead of 1.41x / 1.20x, and 1,008
+// region pixels / 884 windows fill two passes of 512 threads (98 % / 86 %) where 720 / 612 filled 70 % / 60 %.
+#ifndef VSL_F3_TILE_H
+#define VSL_F3_TILE_H 24
+#endif
+#ifndef VSL_ADJ_PAIR_F3
+#define VSL_ADJ_PAIR_F3 0   // paired adjoint for three frames: 54 accumulators next to 36 dL/dP sums (measured)
+#endif
+
 namespace vsl {
 
 thread_local int g_last_cuda_error = 0;  // shared with vsl_layers.cu
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(C::NT, C::NT >= 512 ? 1 : 2) k_photometric(con
     }
     __syncthreads();
     if (!p.forward_only) {
-      if constexpr (VSL_ADJ_PAIR && !C::AVG && C::TH % 2 == 0 && C::IN >= 2 * C::NT) phase_backward_pair<C>(p, g, t, sm, s, tid, ts);
+      if constexpr (VSL_ADJ_PAIR && !C::AVG && C::TH % 2 == 0 && C::IN > C::NT && (C::F < 3 || VSL_ADJ_PAIR_F3)) phase_backward_pair<C>(p, g, t, sm, s, tid, ts);
       else phase_backward<C>(p, g, t, sm, s, tid, ts);
     }
     // deterministic block reduction of (loss, dP) -> one partial per CTA and scale
@@ -231,13 +241,14 @@ __global__ void __launch_bounds__(kSmallNT) k_epilogue(const SmallParams p) {
   if (!p.identity_scale[s] && p.gphoto[s]) {  // gphoto is null with VSL_FLAG_FORWARD_ONLY
     // d(min_loss/s)/d disp_s: add the (<= 4) tile partials of every coarse pixel, tiles in a fixed order
     float* gp = p.gphoto[s] + (size_t)b * n;
-    const int lcw = p.log_tw - p.level_shift[s], lch = p.log_th - p.level_shift[s];
+    const int lcw = p.log_tw - p.level_shift[s], ch = p.th >> p.level_shift[s];
+    const int lch = p.log_th >= 0 ? p.log_th - p.level_shift[s] : -1;
     // one division per thread instead of two per pixel: the pixels of a thread are kSmallNT apart
     int i = chunk * kChunk + threadIdx.x;
     int jy = i / w, jx = i - jy * w;
     const int dy = kSmallNT / w, dx = kSmallNT - dy * w;
     for (; i < min(n, (chunk + 1) * kChunk); i += kSmallNT) {
-      gp[i] = gather_adjoint_partials(p.gpart[s], b, jy, jx, lcw, lch, p.tiles_x, p.tiles_y);
+      gp[i] = gather_adjoint_partials(p.gpart[s], b, jy, jx, lcw, ch, lch, p.tiles_x, p.tiles_y);
       jy += dy; jx += dx;
       if (jx >= w) { jx -= w; ++jy; }
     }
@@ -490,7 +501,8 @@ struct Plan {  // sizes derived from the descriptor; identical in workspace_byte
 // bf16 kernels: 11 % faster than 32x8, whose halo overhead is 1.69x / 1.33x instead of 1.41x / 1.20x) or, for
 // the rarely used --avg_reprojection / --predictive_mask kernels, 32x8 tiles with 256 threads.
 static int tile_height(const VslDesc* d, bool avg, bool pmask) {
-  return (d->num_src >= 3 && (avg || pmask)) ? 8 : 16;
+  if (d->num_src >= 3) return (avg || pmask) ? 8 : VSL_F3_TILE_H;
+  return 16;
 }
 
 static Plan make_plan(const VslDesc* d, int th) {
@@ -565,7 +577,7 @@ size_t vsl_loss_workspace_bytes(const VslDesc* desc) {
   if (!desc_ok(desc)) return 0;
   // the variant (hence the tile height) depends on buffers the caller passes later: size for either
   size_t best = 0;
-  for (int th : {8, 16}) {
+  for (int th : {8, 16, VSL_F3_TILE_H}) {
     const size_t t = make_plan(desc, th).total;
     if (t > best) best = t;
   }
@@ -698,7 +710,7 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   sp.gradP = fwd_only ? nullptr : buf->grad_P;
   sp.norm = fwd_only ? nullptr : buf->smooth_norm;
   sp.tw = pl.tw; sp.th = pl.th; sp.tiles_x = pl.tiles_x; sp.tiles_y = pl.tiles_y;
-  sp.log_tw = ilog2(pl.tw); sp.log_th = ilog2(pl.th);
+  sp.log_tw = ilog2(pl.tw); sp.log_th = (pl.th & (pl.th - 1)) == 0 ? ilog2(pl.th) : -1;
   sp.losses = buf->losses;
   sp.counter = (unsigned*)(ws + pl.off_counter);
   sp.chunks0 = pl.chunks0;
@@ -728,11 +740,11 @@ int vsl_loss_forward_backward_timed(const VslDesc* d, const VslLossBuffers* buf,
   } else if (d->image_dtype == VSL_DTYPE_BF16) {
     if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256, bf16_t>>(pp, pl, d->batch, st);
     else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256, bf16_t>>(pp, pl, d->batch, st);
-    else rc = launch_photometric<TileCfg<32, 16, 3, 512, bf16_t>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, VSL_F3_TILE_H, 3, 512, bf16_t>>(pp, pl, d->batch, st);
   } else {
     if (F == 1) rc = launch_photometric<TileCfg<32, 16, 1, 256>>(pp, pl, d->batch, st);
     else if (F == 2) rc = launch_photometric<TileCfg<32, 16, 2, 256>>(pp, pl, d->batch, st);
-    else rc = launch_photometric<TileCfg<32, 16, 3, 512>>(pp, pl, d->batch, st);
+    else rc = launch_photometric<TileCfg<32, VSL_F3_TILE_H, 3, 512>>(pp, pl, d->batch, st);
   }
   if (rc != VSL_OK) return rc;
   if (event_after) VSL_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after, st));

@@ -937,6 +937,7 @@ template <class C>
 __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const GeoConst& g, const TileCtx& t,
                                                      float* __restrict__ sm, int s, int tid, ThreadState<C>& ts) {
   static_assert(C::F == 2, "paired variant is for two source frames");
+  static_assert(C::kLogTW > 0, "tile width must be a power of two");
   using XL = XLayout<C>;
   const float* T = sm + C::oT;
   const float* TS = sm + C::oTS;
@@ -947,9 +948,17 @@ __device__ __forceinline__ void phase_windows_paired(const PhotoParams& p, const
   const float kc = p.wpix * (0.85f / 3.0f) * (-0.5f) * (1.0f / 9.0f);
   for (int base = 0; base < 2 * C::WN; base += C::NT) {  // uniform trip count: every lane reaches the shuffle
     const int item = base + tid;
-    const int i = item >> 1, f = item & 1;
+    const int f = item & 1;
     const bool live = item < 2 * C::WN;
-    int wy = i / C::WW, wx = i - wy * C::WW;
+    // Item order: first the TW leftmost window columns of every row (a warp = 16 consecutive windows of ONE row x 2
+    // frames = 32 consecutive words of the pair storage: conflict-free), then the two rightmost columns.  In plain
+    // row-major order over the (TW + 2)-wide grid a warp straddles a row end every other time, and the jump of the
+    // region pitch puts 4 of its 32 words on banks already taken (1.38 wavefronts per load in the r2d profile).
+    constexpr int kMain = C::WH * 2 * C::TW;
+    int wy, wx;
+    if (item < kMain) { wy = item >> (C::kLogTW + 1); wx = (item & (2 * C::TW - 1)) >> 1; }
+    else { const int rest = item - kMain; wy = rest >> 2; wx = C::TW + ((rest >> 1) & 1); }
+    const int i = wy * C::WW + wx;
     int gy = t.y0 - 1 + wy, gx = t.x0 - 1 + wx;
     const bool inside = live && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
     float best = INFINITY, l = INFINITY, lraw = 0.f, m = 1.0f;
@@ -1286,12 +1295,13 @@ VSL_HD int ilog2(int v) {  // v a power of two
   return l;
 }
 // sum of the tile partials that touch coarse pixel (jy, jx) of image b; tiles in row-major order
-// lcw, lch: log2 of the tile's width / height in pixels of this level (tile and ratio are powers of two)
-VSL_HD float gather_adjoint_partials(const float* __restrict__ gpart, int b, int jy, int jx, int lcw, int lch,
+// lcw: log2 of the tile's width in pixels of this level (tile width and ratio are powers of two); ch: the tile's height
+// in pixels of this level, lch its log2 or -1 when it is not a power of two (the 24-row tiles of three source frames)
+VSL_HD float gather_adjoint_partials(const float* __restrict__ gpart, int b, int jy, int jx, int lcw, int ch, int lch,
                                      int tiles_x, int tiles_y) {
-  const int cw = 1 << lcw, ch = 1 << lch, ncx = cw + 2, ncy = ch + 2;
-  int ty_hi = (jy + 1) >> lch, tx_hi = (jx + 1) >> lcw;
-  int ty_lo = jy - ch <= 0 ? 0 : (jy - 1) >> lch, tx_lo = jx - cw <= 0 ? 0 : (jx - 1) >> lcw;
+  const int cw = 1 << lcw, ncx = cw + 2, ncy = ch + 2;
+  int ty_hi = lch >= 0 ? (jy + 1) >> lch : (jy + 1) / ch, tx_hi = (jx + 1) >> lcw;
+  int ty_lo = jy - ch <= 0 ? 0 : (lch >= 0 ? (jy - 1) >> lch : (jy - 1) / ch), tx_lo = jx - cw <= 0 ? 0 : (jx - 1) >> lcw;
   if (ty_hi >= tiles_y) ty_hi = tiles_y - 1;
   if (tx_hi >= tiles_x) tx_hi = tiles_x - 1;
   float acc = 0.f;
