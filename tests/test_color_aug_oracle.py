@@ -76,3 +76,15 @@ def test_autocontrast_equals_live_pillow():
         img = rng.integers(lo, hi + 1, (24, 40, 3)).astype(np.uint8)
         img[0, 0], img[0, 1] = lo, hi
         assert np.array_equal(np.asarray(ImageOps.autocontrast(Image.fromarray(img, "RGB"))), O.autocontrast(img))
+
+
+def test_host_side_draws_equal_the_oracle_restatement():
+    """input_pipeline.draw_color_aug_params (product, host-side bookkeeping) and the oracle's draw_params consume the
+    generator identically."""
+    torch = pytest.importorskip("torch")
+    from unsupervised_pose_estimation_b200.input_pipeline import draw_color_aug_params
+    torch.manual_seed(9)
+    a = [draw_color_aug_params() for _ in range(5)]
+    torch.manual_seed(9)
+    b = [O.draw_params() for _ in range(5)]
+    assert a == b

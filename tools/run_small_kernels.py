@@ -10,7 +10,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from unsupervised_pose_estimation_b200 import functional as VF, layers as L, synthetic  # noqa: E402
-from unsupervised_pose_estimation_b200.input_pipeline import LossInputPipeline  # noqa: E402
+from unsupervised_pose_estimation_b200.input_pipeline import ColorAugment, LossInputPipeline, draw_color_aug_params  # noqa: E402
 from unsupervised_pose_estimation_b200.trainer import LossPath, make_opt  # noqa: E402
 
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -22,7 +22,11 @@ pipe = LossInputPipeline(opt, "cuda")
 u8 = {f: (inputs[("color", f, 0)].permute(0, 2, 3, 1) * 255).round().clamp(0, 255).to(torch.uint8).contiguous() for f in frames}
 flip = torch.tensor([i % 2 for i in range(B)], dtype=torch.uint8, device="cuda")
 path = LossPath(opt, device="cuda", side_outputs="eager")
+aug = ColorAugment(B, H, W)
+torch.manual_seed(0)
+aug_params = [dict(draw_color_aug_params(), autocontrast=True) for _ in range(B)]   # every kernel has work in every image
 for it in range(int(os.environ.get("ITERS", "3"))):
+    aug(u8[0], aug_params)
     pin = pipe(u8, flip=flip if it == 2 else None)
     pin.update({k: v for k, v in inputs.items() if k[0] in ("K", "inv_K")})
     out = dict(outputs)

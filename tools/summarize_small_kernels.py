@@ -37,6 +37,9 @@ ALG = {
     "k_median_hist": ("depth_gt + depth_pred in (375x1242 ground truth)", 12 * 375 * 1242 * 4 + n0 * 4),
     "k_depth_errors": ("depth_gt + depth_pred in", 12 * 375 * 1242 * 4 + n0 * 4),
     "k_sllog_fwd": ("fake + real in", n0 * 8),
+    "k_aug_stats": ("8-bit frames in (grey sum of the partially jittered image)", n0 * 3),
+    "k_aug_apply": ("8-bit frames in, jittered 8-bit frames out", n0 * 6),
+    "k_aug_finish": ("jittered 8-bit frames in, fp32 tensor out", n0 * 15),
 }
 
 rows = list(csv.reader(open(os.path.join(ROOT, "gpurun_out", "small_raw_%s.csv" % tag))))

@@ -373,7 +373,11 @@ struct CombineParams {
   int n[kMaxScales], scale_id[kMaxScales], vec4[kMaxScales];
   float smooth_weight;
 };
-constexpr int kCombineChunk = kChunk;  // elements per k_combine block: one float4 per thread, every load in flight at once
+#ifndef VSL_COMBINE_VEC
+#define VSL_COMBINE_VEC 4
+#endif
+constexpr int kCombineVec = VSL_COMBINE_VEC;            // float4 groups per thread, all loaded before the first is used
+constexpr int kCombineChunk = kChunk * kCombineVec;     // elements per k_combine block
 
 __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
   pdl_wait();  // launched programmatically behind k_epilogue when the two are adjacent in the stream (graph replay)
@@ -389,10 +393,19 @@ __global__ void __launch_bounds__(kSmallNT) k_combine(const CombineParams p) {
     const float inv = p.norm[(s * p.B + b) * 2], corr = p.norm[(s * p.B + b) * 2 + 1];
     const int i0 = chunk * kCombineChunk, i1 = min(p.n[s], i0 + kCombineChunk);
     if (p.vec4[s]) {  // level size and the three buffers 16-byte aligned: four elements per access
-      for (int i = i0 + 4 * threadIdx.x; i < i1; i += 4 * kSmallNT) {
-        const float4 g1 = *reinterpret_cast<const float4*>(gp + i), g2 = *reinterpret_cast<const float4*>(gs + i);
-        *reinterpret_cast<float4*>(o + i) = make_float4(a * g1.x + bb * (g2.x * inv - corr), a * g1.y + bb * (g2.y * inv - corr),
-                                                        a * g1.z + bb * (g2.z * inv - corr), a * g1.w + bb * (g2.w * inv - corr));
+      float4 g1[kCombineVec], g2[kCombineVec];
+#pragma unroll
+      for (int k = 0; k < kCombineVec; ++k) {
+        const int i = i0 + 4 * (threadIdx.x + k * kSmallNT);
+        if (i < i1) { g1[k] = *reinterpret_cast<const float4*>(gp + i); g2[k] = *reinterpret_cast<const float4*>(gs + i); }
+      }
+#pragma unroll
+      for (int k = 0; k < kCombineVec; ++k) {
+        const int i = i0 + 4 * (threadIdx.x + k * kSmallNT);
+        if (i < i1)
+          *reinterpret_cast<float4*>(o + i) =
+              make_float4(a * g1[k].x + bb * (g2[k].x * inv - corr), a * g1[k].y + bb * (g2[k].y * inv - corr),
+                          a * g1[k].z + bb * (g2[k].z * inv - corr), a * g1[k].w + bb * (g2[k].w * inv - corr));
       }
     } else {
       for (int i = i0 + threadIdx.x; i < i1; i += kSmallNT) o[i] = a * gp[i] + bb * (gs[i] * inv - corr);
