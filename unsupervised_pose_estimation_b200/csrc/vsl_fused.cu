@@ -374,7 +374,7 @@ struct CombineParams {
   float smooth_weight;
 };
 #ifndef VSL_COMBINE_VEC
-#define VSL_COMBINE_VEC 4
+#define VSL_COMBINE_VEC 1   // measured at C1 (graph-replayed step): 1 -> 0.7968 ms, 4 -> 0.7989 ms, 8 -> 0.8071 ms
 #endif
 constexpr int kCombineVec = VSL_COMBINE_VEC;            // float4 groups per thread, all loaded before the first is used
 constexpr int kCombineChunk = kChunk * kCombineVec;     // elements per k_combine block
