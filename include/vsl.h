@@ -350,6 +350,18 @@ int vsl_stereo_transform(int batch, const uint8_t* flip, const uint8_t* side_lef
  * tables with Pillow's without a GPU. */
 int vsl_pyramid_coefficients(int in_size, int out_size, int32_t* bounds, int32_t* coefs, int ksize_capacity);
 
+/* The decoded file image -> level 0: `self.resize[0](inputs[(n, im, -1)])` (datasets/mono_dataset2.py:85-89, :107-109),
+ * PIL Image.resize((out_width, out_height), LANCZOS) from any native resolution; byte-exact (the same two 8-bit
+ * passes as the pyramid levels with per-size tap counts; a pass whose size does not change is skipped, like Pillow's).
+ * workspace: coefficient tables + the horizontal pass's output; 256-byte aligned, caller-owned.  vsl_resize_plan once
+ * per (shape, workspace), then vsl_resize_forward: frames_hwc [B,in_h,in_w,3] uint8 -> out_hwc [B,out_h,out_w,3] uint8
+ * (device), which is what vsl_pyramid_forward takes. */
+size_t vsl_resize_workspace_bytes(int batch, int in_height, int in_width, int out_height, int out_width);
+int vsl_resize_plan(int batch, int in_height, int in_width, int out_height, int out_width, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int vsl_resize_forward(int batch, int in_height, int in_width, int out_height, int out_width, const uint8_t* frames_hwc,
+                       uint8_t* out_hwc, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Colour augmentation of the `color_aug` inputs (dataset-side remainder).
  * Replaces `self.to_tensor(color_aug(f))` (datasets/mono_dataset2.py:124) with color_aug =

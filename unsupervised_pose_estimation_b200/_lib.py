@@ -52,6 +52,7 @@ EXPORTED_SYMBOLS = [
     "vsl_posecnn_workspace_bytes", "vsl_posecnn_forward", "vsl_posecnn_backward",
     "vsl_metrics_workspace_bytes", "vsl_depth_errors", "vsl_depth_losses", "vsl_sllog_forward", "vsl_sllog_backward",
     "vsl_color_aug_workspace_bytes", "vsl_color_aug_forward",
+    "vsl_resize_workspace_bytes", "vsl_resize_plan", "vsl_resize_forward",
 ]
 
 
@@ -191,6 +192,10 @@ def load():
     lib.vsl_color_aug_workspace_bytes.restype = c_size_t
     lib.vsl_color_aug_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.vsl_color_aug_forward.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, c_size_t, vp]
+    lib.vsl_resize_workspace_bytes.restype = c_size_t
+    lib.vsl_resize_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
+    lib.vsl_resize_plan.argtypes = [c_int, c_int, c_int, c_int, c_int, vp, c_size_t, vp]
+    lib.vsl_resize_forward.argtypes = [c_int, c_int, c_int, c_int, c_int, vp, vp, vp, c_size_t, vp]
     _LIB = lib
     return lib
 

@@ -85,15 +85,19 @@ static double lanczos_filter(double x) {
   if (-3.0 <= x && x < 3.0) return sinc_filter(x) * sinc_filter(x / 3);
   return 0.0;
 }
-// Pillow's precompute_coeffs (box = the whole axis) followed by normalize_coeffs_8bpc
-static bool axis_coeffs(int in_size, int out_size, std::vector<int32_t>& bounds, std::vector<int32_t>& coefs) {
+// Pillow's precompute_coeffs (box = the whole axis) followed by normalize_coeffs_8bpc.  `stride`: words reserved per
+// output in `coefs` (>= axis_ksize; the tail stays zero)
+static int axis_ksize(int in_size, int out_size) {
+  const double scale = (double)in_size / (double)out_size;
+  return (int)ceil(3.0 * (scale < 1.0 ? 1.0 : scale)) * 2 + 1;
+}
+static void axis_coeffs_stride(int in_size, int out_size, int stride, std::vector<int32_t>& bounds, std::vector<int32_t>& coefs) {
   const double scale = (double)in_size / (double)out_size;
   const double filterscale = scale < 1.0 ? 1.0 : scale;
   const double support = 3.0 * filterscale;
   const int ksize = (int)ceil(support) * 2 + 1;
-  if (ksize > kKsize) return false;
   bounds.assign((size_t)out_size * 2, 0);
-  coefs.assign((size_t)out_size * kKsize, 0);
+  coefs.assign((size_t)out_size * stride, 0);
   const double ss = 1.0 / filterscale;
   std::vector<double> k(ksize);
   for (int xx = 0; xx < out_size; ++xx) {
@@ -111,12 +115,16 @@ static bool axis_coeffs(int in_size, int out_size, std::vector<int32_t>& bounds,
     }
     for (int x = 0; x < xmax; ++x) {
       if (ww != 0.0) k[x] /= ww;
-      coefs[(size_t)xx * kKsize + x] = k[x] < 0 ? (int32_t)(-0.5 + k[x] * (1 << kPrecisionBits))
+      coefs[(size_t)xx * stride + x] = k[x] < 0 ? (int32_t)(-0.5 + k[x] * (1 << kPrecisionBits))
                                                 : (int32_t)(0.5 + k[x] * (1 << kPrecisionBits));
     }
     bounds[2 * xx] = xmin;
     bounds[2 * xx + 1] = xmax;
   }
+}
+static bool axis_coeffs(int in_size, int out_size, std::vector<int32_t>& bounds, std::vector<int32_t>& coefs) {
+  if (axis_ksize(in_size, out_size) > kKsize) return false;
+  axis_coeffs_stride(in_size, out_size, kKsize, bounds, coefs);
   return true;
 }
 
@@ -390,6 +398,57 @@ static int pyramid_forward_impl(const VslPyramidDesc* d, const PyramidPlan& pl, 
   return VSL_OK;
 }
 
+// ---- arbitrary-ratio resize: the decoded file image -> level 0 ---------------------------------------------
+// `self.resize[0](inputs[(n, im, -1)])` (datasets/mono_dataset2.py:85-89, :107-109): PIL Image.resize with LANCZOS
+// from the native resolution (e.g. 1242 x 375, 1280 x 1024) to (width, height).  Same two 8-bit passes as the pyramid
+// levels (horizontal first, each rounded to 8 bits) with per-size tap counts; one thread per output pixel.
+struct ResizePlan {
+  int ksx, ksy;                       // taps reserved per output column / row
+  size_t off_xb, off_xc, off_yb, off_yc, off_mid, total;
+};
+static bool resize_dims_ok(int batch, int in_h, int in_w, int out_h, int out_w) {
+  return batch >= 1 && in_h >= 1 && in_w >= 1 && out_h >= 1 && out_w >= 1 && in_h <= 16384 && in_w <= 16384 &&
+         out_h <= 16384 && out_w <= 16384;
+}
+static ResizePlan make_resize_plan(int batch, int in_h, int in_w, int out_h, int out_w) {
+  ResizePlan pl = {};
+  pl.ksx = axis_ksize(in_w, out_w);
+  pl.ksy = axis_ksize(in_h, out_h);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  pl.off_xb = take((size_t)out_w * 2 * 4);
+  pl.off_xc = take((size_t)out_w * pl.ksx * 4);
+  pl.off_yb = take((size_t)out_h * 2 * 4);
+  pl.off_yc = take((size_t)out_h * pl.ksy * 4);
+  pl.off_mid = take((size_t)batch * in_h * out_w * 3);   // the horizontal pass's output
+  pl.total = off;
+  return pl;
+}
+// one pass (ImagingResampleHorizontal_8bpc / Vertical_8bpc): out[b, y, x] from n taps along the axis
+template <bool kHorizontal>
+__global__ void __launch_bounds__(256) k_resample_axis(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                       const int32_t* __restrict__ bounds, const int32_t* __restrict__ coefs,
+                                                       int ksize, int in_h, int in_w, int out_h, int out_w, size_t total) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % out_w);
+  const size_t t = i / out_w;
+  const int y = (int)(t % out_h), b = (int)(t / out_h);
+  const int o = kHorizontal ? x : y;
+  const int lo = bounds[2 * o], n = bounds[2 * o + 1];
+  const int32_t* k = coefs + (size_t)o * ksize;
+  const uint8_t* src = kHorizontal ? in + (((size_t)b * in_h + y) * in_w + lo) * 3 : in + (((size_t)b * in_h + lo) * in_w + x) * 3;
+  const size_t step = kHorizontal ? 3 : (size_t)in_w * 3;
+  int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int j = 0; j < n; ++j) {
+    const int w = k[j];
+    const uint8_t* q = src + j * step;
+    a0 += q[0] * w; a1 += q[1] * w; a2 += q[2] * w;
+  }
+  uint8_t* d = out + i * 3;
+  d[0] = clip8(a0); d[1] = clip8(a1); d[2] = clip8(a2);
+}
+
 }  // namespace vsl
 
 using namespace vsl;
@@ -482,6 +541,64 @@ int vsl_pyramid_forward_flip(const VslPyramidDesc* d, const uint8_t* frames_hwc,
                                        (size_t)d->batch * (d->height >> s) * (d->width >> s) * 3,
                                        cudaMemcpyDeviceToDevice, st));
   }
+  return VSL_OK;
+}
+
+size_t vsl_resize_workspace_bytes(int batch, int in_height, int in_width, int out_height, int out_width) {
+  if (!resize_dims_ok(batch, in_height, in_width, out_height, out_width)) return 0;
+  return make_resize_plan(batch, in_height, in_width, out_height, out_width).total;
+}
+
+int vsl_resize_plan(int batch, int in_height, int in_width, int out_height, int out_width, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (!resize_dims_ok(batch, in_height, in_width, out_height, out_width)) return VSL_ERR_BAD_DESC;
+  if (!workspace) return VSL_ERR_NULL_POINTER;
+  if (((uintptr_t)workspace & 255u) != 0) return VSL_ERR_MISALIGNED;
+  const ResizePlan pl = make_resize_plan(batch, in_height, in_width, out_height, out_width);
+  if (workspace_bytes < pl.total) return VSL_ERR_WORKSPACE;
+  uint8_t* ws = (uint8_t*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int32_t> b, c;
+  axis_coeffs_stride(in_width, out_width, pl.ksx, b, c);
+  VSL_CUDA_OK_IN(cudaMemcpyAsync(ws + pl.off_xb, b.data(), b.size() * 4, cudaMemcpyHostToDevice, st));
+  VSL_CUDA_OK_IN(cudaMemcpyAsync(ws + pl.off_xc, c.data(), c.size() * 4, cudaMemcpyHostToDevice, st));
+  axis_coeffs_stride(in_height, out_height, pl.ksy, b, c);
+  VSL_CUDA_OK_IN(cudaMemcpyAsync(ws + pl.off_yb, b.data(), b.size() * 4, cudaMemcpyHostToDevice, st));
+  VSL_CUDA_OK_IN(cudaMemcpyAsync(ws + pl.off_yc, c.data(), c.size() * 4, cudaMemcpyHostToDevice, st));
+  return VSL_OK;
+}
+
+int vsl_resize_forward(int batch, int in_height, int in_width, int out_height, int out_width, const uint8_t* frames_hwc,
+                       uint8_t* out_hwc, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!resize_dims_ok(batch, in_height, in_width, out_height, out_width)) return VSL_ERR_BAD_DESC;
+  if (!frames_hwc || !out_hwc || !workspace) return VSL_ERR_NULL_POINTER;
+  if (((uintptr_t)workspace & 255u) != 0) return VSL_ERR_MISALIGNED;
+  const ResizePlan pl = make_resize_plan(batch, in_height, in_width, out_height, out_width);
+  if (workspace_bytes < pl.total) return VSL_ERR_WORKSPACE;
+  uint8_t* ws = (uint8_t*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  // Pillow: a pass whose size does not change is skipped altogether (no filtering, no rounding)
+  const bool need_h = in_width != out_width, need_v = in_height != out_height;
+  if (!need_h && !need_v) {
+    VSL_CUDA_OK_IN(cudaMemcpyAsync(out_hwc, frames_hwc, (size_t)batch * in_height * in_width * 3, cudaMemcpyDeviceToDevice, st));
+    return VSL_OK;
+  }
+  const uint8_t* cur = frames_hwc;
+  if (need_h) {
+    uint8_t* dst = need_v ? ws + pl.off_mid : out_hwc;
+    const size_t total = (size_t)batch * in_height * out_width;
+    k_resample_axis<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        cur, dst, (const int32_t*)(ws + pl.off_xb), (const int32_t*)(ws + pl.off_xc), pl.ksx, in_height, in_width, in_height,
+        out_width, total);
+    cur = dst;
+  }
+  if (need_v) {
+    const size_t total = (size_t)batch * out_height * out_width;
+    k_resample_axis<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        cur, out_hwc, (const int32_t*)(ws + pl.off_yb), (const int32_t*)(ws + pl.off_yc), pl.ksy, in_height, out_width,
+        out_height, out_width, total);
+  }
+  VSL_CUDA_OK_IN(cudaGetLastError());
   return VSL_OK;
 }
 

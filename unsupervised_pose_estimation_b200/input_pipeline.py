@@ -96,6 +96,49 @@ class FramePyramid:
         return (self.out, u8) if want_u8 else self.out
 
 
+class FrameResize:
+    """``self.resize[0]`` of ``MonoDataset`` (datasets/mono_dataset2.py:85-89, :107-109) for a batch on the GPU: the
+    decoded 8-bit file images at their native resolution -> level 0 at (height, width), byte for byte what
+    ``transforms.Resize((height, width), interpolation=Image.ANTIALIAS)`` gives on the PIL images.  The result is the
+    uint8 HWC batch ``FramePyramid`` takes.  Optional: shipping native-resolution frames costs more host->device
+    bytes than shipping level 0 (3.8x at KITTI's 1242 x 375), so it only pays where the host cannot resize.
+
+        to_level0 = FrameResize(batch=12, in_height=375, in_width=1242, height=192, width=640)
+        frame_u8 = to_level0(native_u8)          # [B,192,640,3] uint8 (static buffer)
+    """
+
+    def __init__(self, batch, in_height, in_width, height, width, device="cuda"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.VslError("FrameResize runs on CUDA only (the reference's CPU resize is its own dataset code)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib = _lib.load()
+        self.shape = (batch, in_height, in_width, height, width)
+        self.ws_bytes = int(self.lib.vsl_resize_workspace_bytes(*self.shape))
+        if self.ws_bytes == 0:
+            raise ValueError("bad resize shape %s" % (self.shape,))
+        with torch.cuda.device(self.device):
+            self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=self.device)
+            self.ws_ptr = self.ws.data_ptr() + (-self.ws.data_ptr()) % 256
+            self.out = torch.empty(batch, height, width, 3, dtype=torch.uint8, device=self.device)
+            check(self.lib.vsl_resize_plan(*self.shape, ctypes.c_void_p(self.ws_ptr), self.ws_bytes, _stream()),
+                  "vsl_resize_plan")
+            torch.cuda.current_stream().synchronize()  # the tables come from temporary host memory
+
+    def __call__(self, native_u8):
+        batch, in_h, in_w, _, _ = self.shape
+        if native_u8.device != self.device or native_u8.dtype != torch.uint8 or not native_u8.is_contiguous():
+            raise _lib.VslError("frames must be contiguous uint8 tensors on %s (got %s %s)"
+                                % (self.device, native_u8.dtype, native_u8.device))
+        if tuple(native_u8.shape) != (batch, in_h, in_w, 3):
+            raise ValueError("frame has shape %s, expected %s" % (tuple(native_u8.shape), (batch, in_h, in_w, 3)))
+        check(self.lib.vsl_resize_forward(*self.shape, ctypes.c_void_p(native_u8.data_ptr()),
+                                          ctypes.c_void_p(self.out.data_ptr()), ctypes.c_void_p(self.ws_ptr),
+                                          self.ws_bytes, _stream()), "vsl_resize_forward")
+        return self.out
+
+
 class LossInputPipeline:
     """``MonoDataset.preprocess`` + the host->device copy for the frames the loss path reads.
 
