@@ -237,3 +237,42 @@ def test_stereo_T_and_cached_intrinsics():
     inputs = pipe(frames, flip=flip, side_left=left)
     assert torch.equal(inputs["stereo_T"].cpu(), torch.from_numpy(T))
     assert torch.equal(inputs[("color", "s", 0)][1].cpu(), torch.from_numpy(O.to_tensor(frames["s"][1].cpu().numpy()[:, ::-1])))
+
+
+def _resize_cases():
+    import importlib.util
+    here = os.path.join(os.path.dirname(__file__), "golden", "pyramid")
+    src = open(os.path.join(here, "make_golden_resize.py")).read()
+    ns = {}
+    # CASES and make_input only (the generator's own imports, PIL / torchvision, are not needed on the GPU box)
+    exec(src[src.index("# (name, native h"):src.index("def main():")], {"np": np}, ns)
+    return ns["CASES"], ns["make_input"], np.load(os.path.join(here, "resize_pil.npz"))
+
+
+def test_level0_resize_equals_pillow_goldens_and_oracle():
+    """FrameResize (vsl_resize_forward): the decoded file image -> level 0 at arbitrary ratios, byte for byte."""
+    from unsupervised_pose_estimation_b200.input_pipeline import FrameResize
+    cases, make_input, g = _resize_cases()
+    for name, h, w, oh, ow, family in cases:
+        img = make_input(name, h, w, family)
+        batch = np.stack([img, img[::-1].copy(), img[:, ::-1].copy()])
+        out = FrameResize(3, h, w, oh, ow)(torch.from_numpy(batch).cuda()).cpu().numpy()
+        assert np.array_equal(out[0], g[name]), name
+        assert np.array_equal(out[1], O.resize_lanczos(batch[1], oh, ow)), name
+        assert np.array_equal(out[2], O.resize_lanczos(batch[2], oh, ow)), name
+
+
+def test_native_frames_through_resize_and_pyramid():
+    """native frame -> FrameResize -> FramePyramid equals the reference's whole preprocess chain (oracle)."""
+    from unsupervised_pose_estimation_b200.input_pipeline import FramePyramid, FrameResize
+    rng = np.random.RandomState(77)
+    native = rng.randint(0, 256, (2, 375, 1242, 3)).astype(np.uint8)
+    lvl0 = FrameResize(2, 375, 1242, 192, 640)(torch.from_numpy(native).cuda())
+    out = FramePyramid(2, 192, 640, 4)(lvl0)
+    torch.cuda.synchronize()
+    ref0 = O.resize_lanczos(native, 192, 640)
+    _, tensors = O.pyramid(ref0, 4)
+    for s in range(4):
+        assert np.array_equal(out[s].cpu().numpy(), tensors[s]), s
+    with pytest.raises(Exception):
+        FrameResize(2, 375, 1242, 192, 640, "cpu")

@@ -62,3 +62,20 @@ def test_pyramid_needs_cuda():
     if not torch.cuda.is_available():
         desc = _lib.VslPyramidDesc(_lib.VSL_ABI_VERSION, 1, 30, 64, 4, 0)   # 30 is not a multiple of 8
         assert _lib.load().vsl_pyramid_workspace_bytes(desc) == 0
+
+
+def test_oracle_reproduces_the_level0_resize_goldens():
+    """resize_lanczos at arbitrary ratios (the decoded file image -> level 0, datasets/mono_dataset2.py:85-89, :107-109)
+    against outputs of the reference's own transforms.Resize(..., LANCZOS) on PIL images."""
+    import importlib.util
+    here = os.path.join(os.path.dirname(__file__), "golden", "pyramid")
+    spec = importlib.util.spec_from_file_location("make_golden_resize", os.path.join(here, "make_golden_resize.py"))
+    gen = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(gen)     # imports PIL / torchvision at module level
+    except ImportError:
+        pytest.skip("the golden generator's imports are not installed")
+    g = np.load(os.path.join(here, "resize_pil.npz"))
+    for name, h, w, oh, ow, family in gen.CASES:
+        img = gen.make_input(name, h, w, family)
+        assert np.array_equal(O.resize_lanczos(img, oh, ow), g[name]), name
