@@ -219,11 +219,17 @@ __global__ void __launch_bounds__(kAugNT) k_aug_apply(const uint8_t* __restrict_
 }
 
 template <class Out> __device__ __forceinline__ void aug_store(Out* p, size_t i, int v);
+// transforms.ToTensor(): byte.div(255), correctly rounded in three instructions (see div255 in vsl_input.cu)
+__device__ __forceinline__ float aug_div255(int v) {
+  const float a = (float)v, y = 1.0f / 255.0f;
+  const float q = __fmul_rn(a, y);
+  return __fmaf_rn(__fmaf_rn(-255.0f, q, a), y, q);
+}
 template <> __device__ __forceinline__ void aug_store<float>(float* p, size_t i, int v) {
-  p[i] = __fdiv_rn((float)v, 255.0f);  // transforms.ToTensor(): .div(255)
+  p[i] = aug_div255(v);
 }
 template <> __device__ __forceinline__ void aug_store<bf16_t>(bf16_t* p, size_t i, int v) {
-  const uint32_t u = __float_as_uint(__fdiv_rn((float)v, 255.0f));  // round-to-nearest-even, like Tensor.bfloat16()
+  const uint32_t u = __float_as_uint(aug_div255(v));  // round-to-nearest-even, like Tensor.bfloat16()
   p[i].bits = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
 }
 

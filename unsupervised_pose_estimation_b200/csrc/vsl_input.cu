@@ -132,13 +132,22 @@ __device__ __forceinline__ uint8_t clip8(int acc) {  // Pillow: clip8_lookups[ac
   int v = acc >> kPrecisionBits;
   return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
+// transforms.ToTensor(): byte.div(255) as a correctly rounded fp32 quotient in three instructions: q = v * RN(1/255)
+// and one Markstein correction with the exact residual.  Equal to __fdiv_rn(v, 255) for all 256 bytes (checked
+// exhaustively on the host, and by every byte-exact test of the pipeline); the IEEE division costs ~10 instructions
+// and made the conversion kernels instruction-bound.
+__device__ __forceinline__ float div255(uint8_t v) {
+  const float a = (float)v, y = 1.0f / 255.0f;
+  const float q = __fmul_rn(a, y);
+  return __fmaf_rn(__fmaf_rn(-255.0f, q, a), y, q);
+}
 template <class Out> __device__ __forceinline__ void store_tensor(Out* p, size_t i, uint8_t v);
 template <> __device__ __forceinline__ void store_tensor<float>(float* p, size_t i, uint8_t v) {
-  p[i] = __fdiv_rn((float)v, 255.0f);  // transforms.ToTensor(): .div(255)
+  p[i] = div255(v);
 }
 template <> __device__ __forceinline__ void store_tensor<bf16_t>(bf16_t* p, size_t i, uint8_t v) {
   // bf16 image storage (BASELINE config 3): round-to-nearest-even of the fp32 value, like Tensor.bfloat16()
-  const uint32_t u = __float_as_uint(__fdiv_rn((float)v, 255.0f));
+  const uint32_t u = __float_as_uint(div255(v));
   p[i].bits = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
 }
 
@@ -166,8 +175,7 @@ __global__ void __launch_bounds__(256) k_u8_to_tensor(const uint8_t* __restrict_
 // the same for four consecutive pixels per thread: 3 x 32-bit loads, one float4 (or 4 x bf16) store per plane.
 // Needs H*W % 4 == 0 (then every 12-byte group and every plane segment is aligned).
 __device__ __forceinline__ void store4(float* p, const uint8_t v[4]) {
-  *reinterpret_cast<float4*>(p) = make_float4(__fdiv_rn((float)v[0], 255.0f), __fdiv_rn((float)v[1], 255.0f),
-                                              __fdiv_rn((float)v[2], 255.0f), __fdiv_rn((float)v[3], 255.0f));
+  *reinterpret_cast<float4*>(p) = make_float4(div255(v[0]), div255(v[1]), div255(v[2]), div255(v[3]));
 }
 __device__ __forceinline__ void store4(bf16_t* p, const uint8_t v[4]) {
 #pragma unroll
