@@ -1,6 +1,7 @@
 """GPU parity of the on-device input pipeline (vsl_pyramid_forward) against the Pillow-pinned oracle:
 byte-exact 8-bit levels, bit-exact float tensors."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -240,13 +241,11 @@ def test_stereo_T_and_cached_intrinsics():
 
 
 def _resize_cases():
-    import importlib.util
     here = os.path.join(os.path.dirname(__file__), "golden", "pyramid")
-    src = open(os.path.join(here, "make_golden_resize.py")).read()
-    ns = {}
-    # CASES and make_input only (the generator's own imports, PIL / torchvision, are not needed on the GPU box)
-    exec(src[src.index("# (name, native h"):src.index("def main():")], {"np": np}, ns)
-    return ns["CASES"], ns["make_input"], np.load(os.path.join(here, "resize_pil.npz"))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import resize_cases
+    return resize_cases.CASES, resize_cases.make_input, np.load(os.path.join(here, "resize_pil.npz"))
 
 
 def test_level0_resize_equals_pillow_goldens_and_oracle():
