@@ -61,6 +61,22 @@ __device__ __forceinline__ int gray_of(Rgb v) {
 }
 __device__ __forceinline__ int clip8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
+// Per-CTA tables of the two quotients of hsv2rgb that depend on one byte only (built once per CTA with the exact
+// double divisions, read per pixel): i = floor(h * 6.0 / 255.0), f = float(h * 6.0 / 255.0 - i), fs = float(s / 255.0)
+struct HueLut {
+  double f[256], fs[256];
+  uint8_t i[256];
+};
+__device__ __forceinline__ void build_hue_lut(HueLut& lut, int tid, int nthreads) {
+  for (int k = tid; k < 256; k += nthreads) {
+    const double hf = __ddiv_rn(__dmul_rn((double)k, 6.0), 255.0);
+    const int i = (int)floor(hf);
+    lut.i[k] = (uint8_t)i;
+    lut.f[k] = (double)__double2float_rn(__dsub_rn(hf, (double)i));
+    lut.fs[k] = (double)__double2float_rn(__ddiv_rn((double)k, 255.0));
+  }
+}
+
 // convert("HSV") (Convert.c rgb2hsv_row): float ratios, double hue wrap
 __device__ __forceinline__ Rgb rgb_to_hsv(Rgb v) {
   const int maxc = max(v.r, max(v.g, v.b)), minc = min(v.r, min(v.g, v.b));
@@ -76,7 +92,12 @@ __device__ __forceinline__ Rgb rgb_to_hsv(Rgb v) {
   if (v.r == maxc) h = __fsub_rn(bc, gc);
   else if (v.g == maxc) h = __double2float_rn(__dsub_rn(__dadd_rn(2.0, (double)rc), (double)bc));
   else h = __double2float_rn(__dsub_rn(__dadd_rn(4.0, (double)gc), (double)rc));
-  double w = __dadd_rn(__ddiv_rn((double)h, 6.0), 1.0);   // in (0.8, 2): fmod(w, 1.0) = w - floor(w), exact
+  // h / 6.0 as q = h * RN(1/6) with one fused correction of the exact residual: the correctly rounded quotient for
+  // every h this function can produce (tests/test_gpu_color_aug.py compares all 2^24 RGB triples with the oracle)
+  const double x = (double)h, c6 = 1.0 / 6.0;
+  double q = __dmul_rn(x, c6);
+  q = __fma_rn(__fma_rn(-6.0, q, x), c6, q);
+  double w = __dadd_rn(q, 1.0);   // in (0.8, 2): fmod(w, 1.0) = w - floor(w), exact
   w = w - floor(w);
   h = __double2float_rn(w);
   o.r = clip8((int)__dmul_rn((double)h, 255.0));
@@ -84,19 +105,17 @@ __device__ __forceinline__ Rgb rgb_to_hsv(Rgb v) {
   return o;
 }
 // HSV -> RGB (Convert.c hsv2rgb, "following colorsys.py"); (h, s, v) in (r, g, b)
-__device__ __forceinline__ Rgb hsv_to_rgb(Rgb hsv) {
+__device__ __forceinline__ Rgb hsv_to_rgb(Rgb hsv, const HueLut& lut) {
   const int h = hsv.r, s = hsv.g, v = hsv.b;
   Rgb o;
   if (s == 0) { o.r = o.g = o.b = v; return o; }
-  const double hf = __ddiv_rn(__dmul_rn((double)h, 6.0), 255.0);
-  const int i = (int)floor(hf);
-  const double f = (double)__double2float_rn(__dsub_rn(hf, (double)i));
-  const double fs = (double)__double2float_rn(__ddiv_rn((double)s, 255.0));
+  const int i = lut.i[h];
+  const double f = lut.f[h], fs = lut.fs[s];
   const double vf = (double)v;
   const int p = clip8((int)floor(__dadd_rn(__dmul_rn(vf, __dsub_rn(1.0, fs)), 0.5)));
   const int q = clip8((int)floor(__dadd_rn(__dmul_rn(vf, __dsub_rn(1.0, __dmul_rn(fs, f))), 0.5)));
   const int t = clip8((int)floor(__dadd_rn(__dmul_rn(vf, __dsub_rn(1.0, __dmul_rn(fs, __dsub_rn(1.0, f)))), 0.5)));
-  switch (i % 6) {
+  switch (i == 6 ? 0 : i) {   // i % 6 for i in 0..6
     case 0: o.r = v; o.g = t; o.b = p; break;
     case 1: o.r = q; o.g = v; o.b = p; break;
     case 2: o.r = p; o.g = v; o.b = t; break;
@@ -115,26 +134,38 @@ __device__ __forceinline__ int contrast_pos(const VslAugParams& prm) {
     if (prm.order[k] == 1) return k;
   return -1;
 }
-// the first `upto` steps of the jitter chain (ColorJitter.forward's loop over fn_idx) on one pixel
-__device__ __forceinline__ Rgb apply_chain(Rgb v, const VslAugParams& prm, int upto, int mean) {
+// the first `upto` steps of the jitter chain (ColorJitter.forward's loop over fn_idx) on N pixels at once: the step is
+// chosen once (it is uniform over the image) and applied to the N independent pixels back to back, so their long
+// fp64 / division chains overlap
+template <int N>
+__device__ __forceinline__ void apply_chain(Rgb (&v)[N], const VslAugParams& prm, int upto, int mean, const HueLut& lut) {
   for (int k = 0; k < upto; ++k) {
     const int fn = prm.order[k];
     if (fn == 0) {  // adjust_brightness: blend(black, img, factor)
       Rgb z; z.r = z.g = z.b = 0;
-      v = blend3(z, v, prm.factor[0]);
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = blend3(z, v[j], prm.factor[0]);
     } else if (fn == 1) {  // adjust_contrast: blend(mean grey, img, factor)
       Rgb z; z.r = z.g = z.b = mean;
-      v = blend3(z, v, prm.factor[1]);
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = blend3(z, v[j], prm.factor[1]);
     } else if (fn == 2) {  // adjust_saturation: blend(grey image, img, factor)
-      Rgb z; z.r = z.g = z.b = gray_of(v);
-      v = blend3(z, v, prm.factor[2]);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        Rgb z; z.r = z.g = z.b = gray_of(v[j]);
+        v[j] = blend3(z, v[j], prm.factor[2]);
+      }
     } else if (fn == 3) {  // adjust_hue: H += shift (8-bit wrap) in HSV
-      Rgb hsv = rgb_to_hsv(v);
-      hsv.r = (hsv.r + prm.hue_shift) & 255;
-      v = hsv_to_rgb(hsv);
+      Rgb hsv[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        hsv[j] = rgb_to_hsv(v[j]);
+        hsv[j].r = (hsv[j].r + prm.hue_shift) & 255;
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = hsv_to_rgb(hsv[j], lut);
     }
   }
-  return v;
 }
 // int(ImageStat.Stat(grey).mean[0] + 0.5): Python float division of the two integer sums
 __device__ __forceinline__ int contrast_mean(unsigned long long gray_sum, int hw) {
@@ -158,17 +189,22 @@ __global__ void __launch_bounds__(kAugNT) k_aug_stats(const uint8_t* __restrict_
   const VslAugParams prm = params[b];
   const int cpos = contrast_pos(prm);
   if (cpos < 0) return;  // block-uniform
+  __shared__ HueLut lut;
+  build_hue_lut(lut, threadIdx.x, kAugNT);
+  __syncthreads();
   const uint8_t* img = in + (size_t)b * hw * 3;
   unsigned sum = 0;
   const int base = (blockIdx.x * kAugNT + threadIdx.x) * kAugPer;
+  Rgb v[kAugPer];
 #pragma unroll
   for (int k = 0; k < kAugPer; ++k) {
-    const int i = base + k;
-    if (i < hw) {
-      Rgb v; v.r = img[3 * i]; v.g = img[3 * i + 1]; v.b = img[3 * i + 2];
-      sum += (unsigned)gray_of(apply_chain(v, prm, cpos, 0));
-    }
+    const int i = min(base + k, hw - 1);   // past the end: a duplicate of the last pixel, not counted below
+    v[k].r = img[3 * i]; v[k].g = img[3 * i + 1]; v[k].b = img[3 * i + 2];
   }
+  apply_chain<kAugPer>(v, prm, cpos, 0, lut);
+#pragma unroll
+  for (int k = 0; k < kAugPer; ++k)
+    if (base + k < hw) sum += (unsigned)gray_of(v[k]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   __shared__ unsigned wsum[kAugNT / 32];
@@ -189,18 +225,26 @@ __global__ void __launch_bounds__(kAugNT) k_aug_apply(const uint8_t* __restrict_
   const uint8_t* img = in + (size_t)b * hw * 3;
   uint8_t* dst = mid + (size_t)b * hw * 3;
   const int mean = contrast_pos(prm) >= 0 ? contrast_mean(st[b].gray_sum, hw) : 0;
+  __shared__ HueLut lut;
+  if (prm.enabled) build_hue_lut(lut, threadIdx.x, kAugNT);   // block-uniform
+  __syncthreads();
   unsigned lo[3] = {255u, 255u, 255u}, hi[3] = {0u, 0u, 0u};
   const int base = (blockIdx.x * kAugNT + threadIdx.x) * kAugPer;
+  Rgb v[kAugPer];
+#pragma unroll
+  for (int k = 0; k < kAugPer; ++k) {
+    const int i = min(base + k, hw - 1);   // past the end: a duplicate of the last pixel, neither stored nor counted
+    v[k].r = img[3 * i]; v[k].g = img[3 * i + 1]; v[k].b = img[3 * i + 2];
+  }
+  if (prm.enabled) apply_chain<kAugPer>(v, prm, 4, mean, lut);
 #pragma unroll
   for (int k = 0; k < kAugPer; ++k) {
     const int i = base + k;
     if (i < hw) {
-      Rgb v; v.r = img[3 * i]; v.g = img[3 * i + 1]; v.b = img[3 * i + 2];
-      if (prm.enabled) v = apply_chain(v, prm, 4, mean);
-      dst[3 * i] = (uint8_t)v.r; dst[3 * i + 1] = (uint8_t)v.g; dst[3 * i + 2] = (uint8_t)v.b;
-      lo[0] = min(lo[0], (unsigned)v.r); hi[0] = max(hi[0], (unsigned)v.r);
-      lo[1] = min(lo[1], (unsigned)v.g); hi[1] = max(hi[1], (unsigned)v.g);
-      lo[2] = min(lo[2], (unsigned)v.b); hi[2] = max(hi[2], (unsigned)v.b);
+      dst[3 * i] = (uint8_t)v[k].r; dst[3 * i + 1] = (uint8_t)v[k].g; dst[3 * i + 2] = (uint8_t)v[k].b;
+      lo[0] = min(lo[0], (unsigned)v[k].r); hi[0] = max(hi[0], (unsigned)v[k].r);
+      lo[1] = min(lo[1], (unsigned)v[k].g); hi[1] = max(hi[1], (unsigned)v[k].g);
+      lo[2] = min(lo[2], (unsigned)v[k].b); hi[2] = max(hi[2], (unsigned)v[k].b);
     }
   }
   if (!(prm.enabled && prm.autocontrast)) return;  // block-uniform
@@ -248,11 +292,13 @@ __global__ void __launch_bounds__(kAugNT) k_aug_finish(const uint8_t* __restrict
   const int b = blockIdx.y;
   const VslAugParams prm = params[b];
   const bool on = prm.enabled != 0, fl = on && prm.flip, ac = on && prm.autocontrast;
-  int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-  if (ac) {
+  __shared__ uint8_t aclut[3][256];   // ImageOps.autocontrast's lookup tables of this image, one entry per thread and band
+  if (ac) {  // block-uniform
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { lo[c] = (int)st[b].lo[c]; hi[c] = (int)st[b].hi[c]; }
+    for (int c = 0; c < 3; ++c)
+      for (int k = threadIdx.x; k < 256; k += kAugNT) aclut[c][k] = (uint8_t)autocontrast1(k, (int)st[b].lo[c], (int)st[b].hi[c]);
   }
+  __syncthreads();
   const uint8_t* img = mid + (size_t)b * hw * 3;
   Out* dst = out ? out + (size_t)b * 3 * hw : nullptr;
   const int base = (blockIdx.x * kAugNT + threadIdx.x) * kAugPer;
@@ -268,7 +314,7 @@ __global__ void __launch_bounds__(kAugNT) k_aug_finish(const uint8_t* __restrict
     int v[3] = {img[3 * src], img[3 * src + 1], img[3 * src + 2]};
     if (ac) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] = autocontrast1(v[c], lo[c], hi[c]);
+      for (int c = 0; c < 3; ++c) v[c] = aclut[c][v[c]];
     }
     if (dst) {
 #pragma unroll
