@@ -220,15 +220,22 @@ __global__ void __launch_bounds__(256) k_u8_to_tensor_x4(const uint8_t* __restri
 // output column / row held in registers and the 13 reserved taps fully unrolled (the table is zero beyond
 // the taps in use).  Optionally the CTA also writes the CHW tensor of ITS part of the input level
 // (out_in: the 64 x 16 input pixels under the tile), which saves the separate conversion launch.
-constexpr int kTX = 32, kTY = 8, kRowsMax = 2 * kTY + kKsize + 1, kRowBytes = (2 * kTX + kKsize + 6) * 3 / 4 * 4 + 4;
+// kTY output rows per tile: the horizontal pass covers the 2 kTY + 13 input rows the tile's vertical taps touch, so a
+// taller tile repeats less of it (29 rows for 8 outputs, 45 for 16); the large level uses 16, the small ones 8 (more CTAs)
+#ifndef VSL_LANCZOS_TALL
+#define VSL_LANCZOS_TALL 1
+#endif
+constexpr int kTX = 32, kRowBytes = (2 * kTX + kKsize + 6) * 3 / 4 * 4 + 4;
+template <int kTY>
 struct LanczosSmem {
+  static constexpr int kRowsMax = 2 * kTY + kKsize + 1;
   __align__(16) uint8_t tin[kRowsMax][kRowBytes];  // input window of the tile
   uint8_t hrow[kRowsMax][kTX][3];                  // its horizontal pass, rounded to 8 bits
   int32_t kx[kTX][kKsize], ky[kTY][kKsize];        // the tile's coefficient rows (13 words: conflict-free)
   int bx[kTX], by[kTY];                            // first tap of every output column / row
 };
-template <class Out, bool kWords>
-__device__ __forceinline__ void lanczos_tile(LanczosSmem& sm, const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
+template <class Out, bool kWords, int kTY>
+__device__ __forceinline__ void lanczos_tile(LanczosSmem<kTY>& sm, const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
                                              Out* __restrict__ out_t, Out* __restrict__ out_in, AxisTable tx, AxisTable ty,
                                              int hi, int wi, const uint8_t* __restrict__ flip, int b, int x0, int y0) {
   auto& tin = sm.tin; auto& hrow = sm.hrow; auto& kx = sm.kx; auto& ky = sm.ky; auto& bx = sm.bx; auto& by = sm.by;
@@ -254,6 +261,7 @@ __device__ __forceinline__ void lanczos_tile(LanczosSmem& sm, const uint8_t* __r
   }
   // Staging: every global load of a thread is issued before its first shared-memory store (a plain load -> store
   // loop serialises one memory round trip per row: eight in a row per tile, which is what the kernel used to cost)
+  constexpr int kRowsMax = LanczosSmem<kTY>::kRowsMax;
   constexpr int kStageIt = (kRowsMax + 3) / 4;
   if (kWords && flip && flip[b]) {
     // mirrored read of the raw frame (level 1 only): window column c holds source column wi - 1 - (col_lo + c).
@@ -340,36 +348,40 @@ __device__ __forceinline__ void lanczos_tile(LanczosSmem& sm, const uint8_t* __r
     }
   }
   __syncthreads();
-  const int xx = threadIdx.x & (kTX - 1), yy = threadIdx.x / kTX;
-  const int xo = x0 + xx, yo = y0 + yy;
-  if (xo >= wo || yo >= ho) return;
-  const int lo = by[yy];
-  int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  const int xx = threadIdx.x & (kTX - 1), xo = x0 + xx;
+  if (xo >= wo) return;
 #pragma unroll
-  for (int j = 0; j < kKsize; ++j) {
-    const int w = ky[yy][j];
-    a0 += hrow[lo + j][xx][0] * w; a1 += hrow[lo + j][xx][1] * w; a2 += hrow[lo + j][xx][2] * w;
-  }
-  const uint8_t v0 = clip8(a0), v1 = clip8(a1), v2 = clip8(a2);
-  const size_t o = (size_t)yo * wo + xo, hw = (size_t)ho * wo;
-  uint8_t* d8 = out_u8 + ((size_t)b * hw + o) * 3;
-  d8[0] = v0; d8[1] = v1; d8[2] = v2;
-  if (out_t) {
-    Out* dt = out_t + (size_t)b * 3 * hw + o;
-    store_tensor<Out>(dt, 0, v0);
-    store_tensor<Out>(dt, hw, v1);
-    store_tensor<Out>(dt, 2 * hw, v2);
+  for (int yy = threadIdx.x / kTX; yy < kTY; yy += 256 / kTX) {
+    const int yo = y0 + yy;
+    if (yo >= ho) break;
+    const int lo = by[yy];
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+#pragma unroll
+    for (int j = 0; j < kKsize; ++j) {
+      const int w = ky[yy][j];
+      a0 += hrow[lo + j][xx][0] * w; a1 += hrow[lo + j][xx][1] * w; a2 += hrow[lo + j][xx][2] * w;
+    }
+    const uint8_t v0 = clip8(a0), v1 = clip8(a1), v2 = clip8(a2);
+    const size_t o = (size_t)yo * wo + xo, hw = (size_t)ho * wo;
+    uint8_t* d8 = out_u8 + ((size_t)b * hw + o) * 3;
+    d8[0] = v0; d8[1] = v1; d8[2] = v2;
+    if (out_t) {
+      Out* dt = out_t + (size_t)b * 3 * hw + o;
+      store_tensor<Out>(dt, 0, v0);
+      store_tensor<Out>(dt, hw, v1);
+      store_tensor<Out>(dt, 2 * hw, v2);
+    }
   }
 }
 
 // one 2:1 level per launch
-template <class Out, bool kWords>
+template <class Out, bool kWords, int kTY>
 __global__ void __launch_bounds__(256) k_lanczos_half(const uint8_t* __restrict__ in, uint8_t* __restrict__ out_u8,
                                                      Out* __restrict__ out_t, Out* __restrict__ out_in, AxisTable tx,
                                                      AxisTable ty, int hi, int wi, const uint8_t* __restrict__ flip) {
-  __shared__ LanczosSmem sm;
-  lanczos_tile<Out, kWords>(sm, in, out_u8, out_t, out_in, tx, ty, hi, wi, flip, blockIdx.z, blockIdx.x * kTX,
-                            blockIdx.y * kTY);
+  __shared__ LanczosSmem<kTY> sm;
+  lanczos_tile<Out, kWords, kTY>(sm, in, out_u8, out_t, out_in, tx, ty, hi, wi, flip, blockIdx.z, blockIdx.x * kTX,
+                                 blockIdx.y * kTY);
 }
 
 template <class Out>
@@ -394,12 +406,19 @@ static int pyramid_forward_impl(const VslPyramidDesc* d, const PyramidPlan& pl, 
     AxisTable ty = {(const int32_t*)(ws + pl.off_yb[s]), (const int32_t*)(ws + pl.off_yc[s])};
     uint8_t* cur = ws + pl.off_u8[s];
     Out* out_in = (s == 1 && fuse0) ? (Out*)levels[0] : nullptr;
-    dim3 grid(((wi >> 1) + kTX - 1) / kTX, ((hi >> 1) + kTY - 1) / kTY, d->batch);
     const uint8_t* fl = s == 1 ? flip : nullptr;  // later levels read the already mirrored 8-bit level
-    if (wi % 4 == 0 && ((uintptr_t)prev & 3u) == 0)
-      k_lanczos_half<Out, true><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi, fl);
-    else
-      k_lanczos_half<Out, false><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi, fl);
+    const bool words = wi % 4 == 0 && ((uintptr_t)prev & 3u) == 0;
+    // taller tiles where the level is large enough to fill the GPU with them (>= 4 CTAs per SM)
+    const int ty16 = ((wi >> 1) + kTX - 1) / kTX * (((hi >> 1) + 15) / 16) * d->batch;
+    if (VSL_LANCZOS_TALL && ty16 >= 4 * 148) {
+      dim3 grid(((wi >> 1) + kTX - 1) / kTX, ((hi >> 1) + 15) / 16, d->batch);
+      if (words) k_lanczos_half<Out, true, 16><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi, fl);
+      else k_lanczos_half<Out, false, 16><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi, fl);
+    } else {
+      dim3 grid(((wi >> 1) + kTX - 1) / kTX, ((hi >> 1) + 7) / 8, d->batch);
+      if (words) k_lanczos_half<Out, true, 8><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi, fl);
+      else k_lanczos_half<Out, false, 8><<<grid, 256, 0, st>>>(prev, cur, (Out*)levels[s], out_in, tx, ty, hi, wi, fl);
+    }
     VSL_CUDA_OK_IN(cudaGetLastError());
     prev = cur;
   }
