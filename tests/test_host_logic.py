@@ -82,3 +82,33 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["config"]["workload"].startswith("C2")
+
+
+def test_input_pipeline_classes_have_no_cpu_path():
+    """FrameResize / FramePyramid / ColorAugment are CUDA only: asking for a CPU device fails loudly (before any
+    library call), like the loss path itself."""
+    from unsupervised_pose_estimation_b200 import _lib
+    from unsupervised_pose_estimation_b200.input_pipeline import ColorAugment, FramePyramid, FrameResize
+    with pytest.raises(_lib.VslError):
+        FrameResize(1, 20, 30, 16, 24, device="cpu")
+    with pytest.raises(_lib.VslError):
+        FramePyramid(1, 16, 24, 2, device="cpu")
+    with pytest.raises(_lib.VslError):
+        ColorAugment(1, 16, 24, device="cpu")
+
+
+def test_resize_workspace_and_argument_checks():
+    """vsl_resize_* argument validation through the C ABI (host only: no kernel is launched)."""
+    import ctypes
+    from unsupervised_pose_estimation_b200 import _lib
+    lib = _lib.load()
+    assert lib.vsl_resize_workspace_bytes(0, 10, 10, 5, 5) == 0
+    assert lib.vsl_resize_workspace_bytes(1, 10, 10, 0, 5) == 0
+    n = lib.vsl_resize_workspace_bytes(2, 375, 1242, 192, 640)
+    # tables (two axes) + the horizontal pass's output [2, 375, 640, 3]
+    assert n >= 2 * 375 * 640 * 3 and n % 256 == 0
+    assert lib.vsl_resize_forward(2, 375, 1242, 192, 640, None, None, None, n, None) == -2      # null pointers
+    assert lib.vsl_color_aug_workspace_bytes(0, 4, 4) == 0
+    assert lib.vsl_color_aug_workspace_bytes(3, 8, 8) >= 3 * 8 * 8 * 3
+    assert lib.vsl_color_aug_forward(1, 8, 8, 7, ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), None,
+                                     ctypes.c_void_p(256), 1 << 20, None) == -4                 # unsupported dtype
